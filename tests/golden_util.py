@@ -1,0 +1,54 @@
+"""Helpers shared by the CPU (oracle) and GPU (CUDA path) replays of tests/golden/*.npz."""
+import ast
+import glob
+import os
+
+import numpy as np
+
+from oracle import trackmpnn_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden_names(kind=None):
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+    if kind is not None:
+        names = [n for n in names if n.startswith(kind)]
+    return names
+
+
+class Golden:
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+        self.meta = ast.literal_eval(str(self.z['meta']))
+        self.n_steps = int(self.z['n_steps'])
+        self.X = self.z['X']
+        self.y = self.z['y']
+
+    def params(self, prefix='w/'):
+        return {k[len(prefix):]: self.z[k].copy() for k in self.z.files if k.startswith(prefix)}
+
+    def has(self, s, key):
+        return f's{s}/{key}' in self.z.files
+
+    def get(self, s, key):
+        return self.z[f's{s}/{key}']
+
+    def graph(self, s, prefix=''):
+        """Edge-list Graph for the reference's (y_pred, node_adj[, labels]) at step s."""
+        yp = self.get(s, prefix + 'y_pred').astype(np.int64)
+        r, c, v = self.get(s, prefix + 'adj').astype(np.int64)
+        n = yp.shape[0]
+        src = -np.ones(n, np.int64); dst = -np.ones(n, np.int64)
+        off = r != c
+        pos = off & (v > 0); neg = off & (v < 0)
+        src[r[pos]] = c[pos]; dst[r[neg]] = c[neg]
+        lab = self.get(s, prefix + 'labels').astype(np.int64) if self.has(s, prefix + 'labels') else None
+        return O.Graph(yp[:, 0].copy(), yp[:, 1].copy(), yp[:, 2].copy(), src, dst, lab)
+
+
+def assert_graph_equal(a, b, what=''):
+    for f in ('ts', 'det', 'ass', 'src', 'dst'):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f'{what}: {f}')
+    if a.label is not None and b.label is not None:
+        np.testing.assert_array_equal(a.label, b.label, err_msg=f'{what}: label')
