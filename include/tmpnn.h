@@ -1,0 +1,256 @@
+/* tmpnn.h -- C ABI of libtmpnn_sm100a.so: the TrackMPNN message-passing hot path on B200.
+ *
+ * The reference (arangesh/TrackMPNN) is pure Python/PyTorch and has no FFI of its own; the
+ * entry points below are what a binding for its hot path would call.  Each one names the
+ * reference code it replaces (paths relative to the reference repo).  INTEGRATION.md shows
+ * the ctypes stub and the sys.modules overlay that put them behind the reference's own
+ * module names (models.track_mpnn, models.layers, models.loss, utils.graph).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless
+ *    the parameter name ends in _host.  The caller owns all memory (in practice PyTorch's
+ *    caching allocator); the library allocates nothing that outlives a call.
+ *  - Every function returns 0 on success or a negative tmpnn_status; tmpnn_last_error()
+ *    returns a thread-local message.  Nothing throws.
+ *  - The last argument is the cudaStream_t (as void*) the work is enqueued on.  No function
+ *    synchronises the device unless its name ends in _sync.
+ *  - Re-entrant; one stream per call; safe for one host thread per GPU.
+ *  - Quantities that change every frame (row counts, detection counts) live in device
+ *    memory so a whole frame can be enqueued -- or captured in a CUDA graph -- without the
+ *    host ever reading them.  Capacity overflows raise a sticky flag in tmpnn_graph.status.
+ *
+ * Data layout (device resident, structure-of-arrays, never a dense N x N matrix)
+ *  The window graphs of S independent sequences live in S slabs of cap_rows rows each;
+ *  sequence s owns global rows [s*cap_rows, s*cap_rows + n_rows[s]).  A row is either a
+ *  detection row (ts >= 0) or an association ("edge") row (ts == -1) joining an earlier
+ *  detection row src to a later one dst, with src < row < dst (slab-local indices).  This
+ *  is the reference's y_pred[N,3] = [ts, det_id, ass_id] plus the two non-zeros of the
+ *  row of node_adj (utils/graph.py:137-163).  The hidden state h is [S*cap_rows, ldh] fp32
+ *  row-major with feature group g in columns [64 g, 64 g + 64) (= the reference's
+ *  states[N, G*H], models/track_mpnn.py:72).
+ */
+#ifndef TMPNN_H_
+#define TMPNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMPNN_HIDDEN 64 /* --num-hidden-feats (utils/training_options.py:22); kernels are specialised for it */
+
+typedef enum tmpnn_status {
+  TMPNN_OK = 0,
+  TMPNN_E_BADARG = -1,
+  TMPNN_E_CAPACITY = -2,
+  TMPNN_E_CUDA = -3,
+  TMPNN_E_UNSUPPORTED = -4
+} tmpnn_status;
+
+/* bits of the sticky device-side status word */
+#define TMPNN_FLAG_ROW_CAPACITY 1  /* a slab ran out of rows in tmpnn_graph_append        */
+#define TMPNN_FLAG_DET_CAPACITY 2  /* more detection rows than tmpnn_index.cap_dets        */
+#define TMPNN_FLAG_INC_CAPACITY 4  /* more incidences than tmpnn_index.cap_inc             */
+#define TMPNN_FLAG_SEG_CAPACITY 8  /* a detection has more incident edges than a CTA sorts */
+#define TMPNN_FLAG_MULTI_GT_EDGE 16 /* "More than one GT edge from same node!" (utils/graph.py:243) */
+#define TMPNN_FLAG_WALK_CAPACITY 32 /* more detection rows in one window than the decode walk holds */
+
+typedef struct tmpnn_graph {
+  int32_t num_seqs;   /* S */
+  int32_t cap_rows;   /* rows per slab */
+  int32_t *n_rows;    /* [S]   rows in use per sequence */
+  int32_t *ts;        /* [S*cap_rows]  timestamp, -1 for edge rows          (y_pred[:,0]) */
+  int32_t *det;       /* [S*cap_rows]  detection id, -1 for edge rows        (y_pred[:,1]) */
+  int32_t *ass;       /* [S*cap_rows]  associated detection id or -1         (y_pred[:,2]) */
+  int32_t *src;       /* [S*cap_rows]  slab-local row of the earlier endpoint, -1 for detections */
+  int32_t *dst;       /* [S*cap_rows]  slab-local row of the later endpoint,   -1 for detections */
+  int32_t *label;     /* [S*cap_rows]  ground-truth class, may be NULL        (labels[N]) */
+  float *score;       /* [S*cap_rows]  p = scores[:,1] */
+  float *logit;       /* [S*cap_rows]  */
+  int32_t *status;    /* [1] sticky TMPNN_FLAG_* bits */
+} tmpnn_graph;
+
+/* Per-step index over the slabs: detection-row list, per-detection incidence lists (CSR,
+ * "past" edges with dst == d first, then "future" edges with src == d, each ascending), and
+ * the tile table of the row-tiled kernels.  Rebuilt by tmpnn_index_build whenever rows were
+ * appended or deleted.  It replaces the reference's edge_adj = node_adj^T
+ * (utils/graph.py:158,300) and every np.where(node_adj[:, i]) column scan. */
+typedef struct tmpnn_index {
+  int32_t cap_dets;      /* capacity of det_rows (all sequences together) */
+  int32_t cap_inc;       /* capacity of inc (2 x edge rows) */
+  int32_t *n_dets;       /* [1]  */
+  int32_t *n_edges;      /* [1]  total edge rows (for throughput accounting) */
+  int32_t *det_rows;     /* [cap_dets] global row ids, ascending */
+  int32_t *det_of_row;   /* [S*cap_rows] position in det_rows, -1 for edge rows */
+  int32_t *seq_det_ptr;  /* [S+1] range of det_rows per sequence */
+  int32_t *seg_ptr;      /* [2*cap_dets+1] past segment of detection k = [seg_ptr[2k], seg_ptr[2k+1]), future = [seg_ptr[2k+1], seg_ptr[2k+2]) */
+  int32_t *inc;          /* [cap_inc] global edge-row ids */
+  int32_t *tile_ptr;     /* [S+1] prefix sum of ceil(n_rows[s] / TMPNN_TILE_ROWS) */
+  int32_t *scratch;      /* [tmpnn_index_scratch_ints(...)] */
+} tmpnn_index;
+
+#define TMPNN_TILE_ROWS 64
+
+const char *tmpnn_last_error(void);
+int tmpnn_version(void);
+
+/* ---- parameters ---------------------------------------------------------------------- */
+
+/* Floats in one packed GRU cell (kx = input width: 64, or 128 for the edge cell with
+ * --msg-type concat).  Layout: w_ih as [kx][3][64], w_hh as [64][3][64], bias [4][64]
+ * (b_ir+b_hr, b_iz+b_hz, b_in, b_hn), head weight slice [64], head bias [1] (+3 pad). */
+size_t tmpnn_gru_pack_floats(int kx);
+
+/* Re-lays one torch.nn.GRUCell (models/layers.py:59-68; gate order r,z,n) plus the 64-wide
+ * slice of the output head that scores this row type (models/track_mpnn.py:35-41,73) into
+ * the layout above. */
+int tmpnn_pack_gru(const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
+                   const float *head_w, const float *head_b, int kx, float *packed, void *stream);
+
+/* ---- K0: input transform (models/track_mpnn.py:45-52,59-61) ---------------------------- */
+
+/* Linear(f_in,64) on n detection feature rows: a[i,:] = W1 x[x_idx ? x_idx[i] : i, col0:col0+f_in] + b1.
+ * n = *n_dev when n_dev != NULL, else n_host. */
+int tmpnn_input_linear1(const float *x, int ldx, int col0, int f_in, const int32_t *x_idx,
+                        const float *w1, const float *b1, float *a, const int32_t *n_dev, int n_host,
+                        void *stream);
+
+/* Train-mode BatchNorm1d statistics over n detection rows plus n_edge_rows identical rows
+ * of value b1 (the all-zero edge rows the reference also feeds, track_mpnn.py:59).  Writes
+ * mean/biased var to stats[2][64] and updates running_mean/var (momentum 0.1, unbiased). */
+int tmpnn_input_bn_stats(const float *a, int n, int n_edge_rows, const float *b1, float *stats,
+                         float *running_mean, float *running_var, void *stream);
+
+/* BatchNorm (given mean/var) -> ReLU -> Linear(64,64); writes h[out_rows[i], col:col+64]. */
+int tmpnn_input_bn_relu_linear2(const float *a, const float *mean, const float *var, const float *gamma,
+                                const float *beta, const float *w2, const float *b2, float *h, int ldh,
+                                int col, const int32_t *out_rows, const int32_t *n_dev, int n_host,
+                                void *stream);
+
+/* ---- index --------------------------------------------------------------------------- */
+size_t tmpnn_index_scratch_ints(int num_seqs, int cap_rows, int cap_dets);
+/* active (may be NULL): sequences with active[s] == 0 are indexed as empty (they sit out this tick). */
+int tmpnn_index_build(const tmpnn_graph *g, const tmpnn_index *ix, const int32_t *active, void *stream);
+
+/* ---- K1: aggregation (models/layers.py:90-95,103) -------------------------------------- */
+
+/* edge_support for every detection row k of the index: agg[k,:] = sum_{future e} h[e] - sum_{past e} h[e]
+ * over columns [col, col+64) of h (the sparse product edge_adj_norm . h, layers.py:103). */
+int tmpnn_aggregate_dets(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
+                         float *agg, void *stream);
+
+/* node_support for every edge row (layers.py:91-95): diff -> h[src]-h[dst] (64 wide),
+ * concat -> [h[src] | h[dst]] (128 wide); rows of support that belong to detections are zero.
+ * Stand-alone form of what tmpnn_mp_step_fwd fuses; kept for the roofline study. */
+int tmpnn_aggregate_edges(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
+                          int concat, float *support, void *stream);
+
+/* ---- K2+K3: one message-passing step (models/layers.py:84-116 + track_mpnn.py:73-75) ---- */
+
+/* For feature group `group` (columns [64 group, 64 group + 64) of h): every edge row runs the
+ * edge GRUCell on h[src]-h[dst] (or the concat), every detection row runs the node GRUCell on
+ * agg (from tmpnn_aggregate_dets); both read h_in and write h_out (Jacobi update).  The output
+ * heads are fused: logit (+)= w . h' (+ b when group == 0) and, for the last group,
+ * score = sigmoid(logit).  agg is scratch of cap_dets*64 floats. */
+int tmpnn_mp_step_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                      int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
+                      float *agg, void *stream);
+
+/* ---- graph bookkeeping (utils/graph.py) ------------------------------------------------ */
+
+/* y_pred[N,3] int64 <-> ts/det/ass, scores[N,2] -> p, labels int64 -> int32 for ONE slab. */
+int tmpnn_ypred_unpack(const int64_t *y_pred, int n, int32_t *ts, int32_t *det, int32_t *ass, void *stream);
+int tmpnn_ypred_pack(const int32_t *ts, const int32_t *det, const int32_t *ass, int n, int64_t *y_pred, void *stream);
+
+/* Sparse COO of node_adj (with the I_node diagonal) from the edge list of one slab and back
+ * (utils/graph.py:152-163, 299-308).  idx is [2, nnz] int64, val [nnz] fp32,
+ * nnz = 2*n_edges + n_dets; entries are emitted row-major (coalesced COO order). */
+int tmpnn_coo_from_edges(const int32_t *ts, const int32_t *src, const int32_t *dst, int n, int transpose,
+                         int64_t *idx, float *val, int64_t nnz, int32_t *nnz_prefix_scratch, void *stream);
+int tmpnn_edges_from_coo(const int64_t *idx, const float *val, int64_t nnz, int n, int32_t *src, int32_t *dst,
+                         void *stream);
+
+/* Greedy association (utils/graph.py:251-268 == 437-454): for each detection row with p >= 0.5
+ * take its positive future edges whose far end is positive, keep the nearest timestep, pick the
+ * first arg-max; ass = det id of that far end.  mode 0 = greedy from scores, 1 = teacher forcing
+ * from labels (utils/graph.py:229-245). */
+int tmpnn_graph_associate(const tmpnn_graph *g, const tmpnn_index *ix, int mode, void *stream);
+
+/* Detections of the sequences, grouped by timestamp: frame_ptr[s*(t_max+2) + t] .. [+1] indexes
+ * frame_dets (ascending detection ids of sequence s at time t). */
+typedef struct tmpnn_frames {
+  int32_t t_max;            /* timestamps 0..t_max */
+  int32_t ldx;              /* floats per feature row */
+  const int32_t *frame_ptr; /* [S*(t_max+2)] */
+  const int32_t *frame_dets;/* [sum ND] detection ids (sequence-local) */
+  const int32_t *det_ptr;   /* [S+1] offset of sequence s in the per-detection arrays */
+  const int32_t *det_track; /* [sum ND] ground-truth track id (labels), may be NULL */
+} tmpnn_frames;
+
+/* Per-sequence driver state of the batched engine: the loop variables of infer.py:48-87
+ * (t_skip, t_end, "re-initialise when the graph and the frame are both empty") kept on the
+ * device so that many sequences advance in lock step without host round trips. */
+typedef struct tmpnn_seq_state {
+  int32_t *phase;      /* [S] 0 = not started, 1 = running, 2 = finished */
+  int32_t *skip_until; /* [S] infer.py's t_skip */
+  int32_t *t_end;      /* [S] last timestamp + 1 (initialize_graph's tN+1) */
+  int32_t *active;     /* [S] out: 1 if the sequence takes part in this tick */
+  int32_t *t_upto;     /* [S] out: decode_tracks' t_upto for this tick */
+  int32_t *fresh;      /* [S] out: 1 if the graph was (re-)initialised this tick (states = None) */
+} tmpnn_seq_state;
+
+/* update_graph steps 2-4 (utils/graph.py:270-327) and initialize_graph (utils/graph.py:96-186)
+ * for every sequence at timestep t = *t_dev.
+ *  Append: active set (mode 0: detection && ass == -1 && p >= 0.5; mode 1 (train):
+ *  (detection && ass == -1) || ts == t_prev), then A*Nt edge rows and Nt detection rows,
+ *  edge (a,j) at n + a*Nt + j with src = active[a], dst = n + A*Nt + j; labels from det_track.
+ *  Initialise: the first two non-empty timesteps t0 < t1 at or after t give rows
+ *  [N0 dets][N0*N1 edges][N1 dets], edge (i,j) at N0 + i*N1 + j.
+ * st == NULL: plain append for every sequence (the drop-in update_graph).  With st: start != 0
+ * initialises every sequence from t (t = 0 when t_dev == NULL; infer.py:48); start == 0 runs one iteration of
+ * infer.py:60-74 per sequence (skip / re-initialise / append) and sets st->active, st->t_upto
+ * (cur_win_size as in infer.py:86), st->fresh.
+ * New rows get h = 0 (ldh floats per row; fresh sequences are zeroed completely).
+ * new_det_rows / new_det_x (capacity cap_new) receive the global row and the feature-row index
+ * (det_ptr[s] + detection id) of every new detection row, n_new[0] their count, n_new[1] the
+ * number of new edge rows; n_appended[s] the rows added to sequence s. */
+int tmpnn_graph_append(const tmpnn_graph *g, const tmpnn_frames *fr, const tmpnn_seq_state *st,
+                       const int32_t *t_dev, int start, int cur_win_size, int mode, float *h, int ldh,
+                       int32_t *new_det_rows, int32_t *new_det_x, int32_t *n_new, int cap_new,
+                       int32_t *n_appended, int32_t *scratch, void *stream);
+size_t tmpnn_graph_append_scratch_ints(int num_seqs, int cap_rows);
+
+/* decode_tracks walk (utils/graph.py:456-490) + deletion mask (:492-512) for every sequence:
+ * y_out_track[det_ptr[s] + d] is the reference's y_out[d,1]; next_track_id[s] its running
+ * max+1.  t_upto = t_upto_seq[s] when given, else t_upto_host.  Sequences with active[s] == 0
+ * (when active != NULL) keep every row.  Writes keep[row] in {0,1} for all rows in use.
+ * Needs a fresh index and tmpnn_graph_associate first.  scratch: num_seqs ints. */
+int tmpnn_graph_decode(const tmpnn_graph *g, const tmpnn_index *ix, const tmpnn_frames *fr,
+                       int32_t *y_out_track, int32_t *next_track_id, const int32_t *t_upto_seq,
+                       int t_upto_host, const int32_t *active, int ret_win_size, uint8_t *keep,
+                       int32_t *scratch, void *stream);
+
+/* prune_graph mask (utils/graph.py:361-377): keep = p >= thr || detection || row < first || row > last
+ * detection row with t_st <= ts <= t_ed. */
+int tmpnn_graph_prune_mask(const tmpnn_graph *g, const tmpnn_index *ix, int t_st, int t_ed, float threshold,
+                           uint8_t *keep, int32_t *scratch /* 2*S ints */, void *stream);
+
+/* Order-preserving deletion of the rows with keep == 0 in every slab (the np.delete /
+ * advanced-indexing of utils/graph.py:379-387, 514-520): prefix-sum stream compaction of
+ * ts/det/ass/label/score/logit and of h (h_src -> h_dst, ldh floats per row), src/dst
+ * re-mapped to the new row numbers.  Out of place: reads g_in / h_src, writes g_out / h_dst
+ * (distinct arrays; the caller ping-pongs two sets) and g_out->n_rows;
+ * new_of_old[row] = new slab-local row or -1.  Sequences with active[s] == 0 (they sat out the
+ * message-passing step, so their current state is still in the step's input buffer) take h from
+ * h_src_inactive instead of h_src. */
+int tmpnn_graph_compact(const tmpnn_graph *g_in, const tmpnn_graph *g_out, const uint8_t *keep,
+                        const float *h_src, const float *h_src_inactive, const int32_t *active, float *h_dst,
+                        int ldh, int32_t *new_of_old, int32_t *scratch, void *stream);
+size_t tmpnn_graph_compact_scratch_ints(int num_seqs, int cap_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMPNN_H_ */

@@ -1,0 +1,147 @@
+"""ctypes binding of ``libtmpnn_sm100a.so`` (the C ABI declared in ``include/tmpnn.h``).
+
+There is deliberately no fallback: if the library is missing or a call fails, the
+product path raises.  PyTorch is used only to own device memory and streams; every
+argument that crosses this boundary is a raw device pointer or a plain integer.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtmpnn_sm100a.so')
+
+TILE_ROWS = 64
+HIDDEN = 64
+
+FLAG_NAMES = {
+    1: 'row capacity of a slab exceeded (tmpnn_graph_append)',
+    2: 'detection-row capacity of the index exceeded',
+    4: 'incidence capacity of the index exceeded',
+    8: 'a detection has more incident edges than one CTA can sort',
+    16: 'More than one GT edge from same node!',
+    32: 'more detection rows in one window than the decode walk holds',
+}
+
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+
+
+class Graph(C.Structure):
+    _fields_ = [('num_seqs', C.c_int32), ('cap_rows', C.c_int32), ('n_rows', C.c_void_p), ('ts', C.c_void_p),
+                ('det', C.c_void_p), ('ass', C.c_void_p), ('src', C.c_void_p), ('dst', C.c_void_p),
+                ('label', C.c_void_p), ('score', C.c_void_p), ('logit', C.c_void_p), ('status', C.c_void_p)]
+
+
+class Index(C.Structure):
+    _fields_ = [('cap_dets', C.c_int32), ('cap_inc', C.c_int32), ('n_dets', C.c_void_p), ('n_edges', C.c_void_p),
+                ('det_rows', C.c_void_p), ('det_of_row', C.c_void_p), ('seq_det_ptr', C.c_void_p),
+                ('seg_ptr', C.c_void_p), ('inc', C.c_void_p), ('tile_ptr', C.c_void_p), ('scratch', C.c_void_p)]
+
+
+class Frames(C.Structure):
+    _fields_ = [('t_max', C.c_int32), ('ldx', C.c_int32), ('frame_ptr', C.c_void_p), ('frame_dets', C.c_void_p),
+                ('det_ptr', C.c_void_p), ('det_track', C.c_void_p)]
+
+
+class SeqState(C.Structure):
+    _fields_ = [('phase', C.c_void_p), ('skip_until', C.c_void_p), ('t_end', C.c_void_p), ('active', C.c_void_p),
+                ('t_upto', C.c_void_p), ('fresh', C.c_void_p)]
+
+
+class TmpnnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_VP = C.c_void_p
+_I = C.c_int
+_PROTOS = {
+    'tmpnn_version': ([], C.c_int),
+    'tmpnn_gru_pack_floats': ([_I], C.c_size_t),
+    'tmpnn_pack_gru': ([_VP] * 6 + [_I, _VP, _VP], _I),
+    'tmpnn_input_linear1': ([_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP], _I),
+    'tmpnn_input_bn_stats': ([_VP, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_input_bn_relu_linear2': ([_VP] * 8 + [_I, _I, _VP, _VP, _I, _VP], _I),
+    'tmpnn_index_scratch_ints': ([_I, _I, _I], C.c_size_t),
+    'tmpnn_index_build': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP], _I),
+    'tmpnn_aggregate_dets': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP], _I),
+    'tmpnn_aggregate_edges': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _I, _VP, _VP], _I),
+    'tmpnn_mp_step_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_ypred_unpack': ([_VP, _I, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_ypred_pack': ([_VP, _VP, _VP, _I, _VP, _VP], _I),
+    'tmpnn_coo_from_edges': ([_VP, _VP, _VP, _I, _I, _VP, _VP, C.c_int64, _VP, _VP], _I),
+    'tmpnn_edges_from_coo': ([_VP, _VP, C.c_int64, _I, _VP, _VP, _VP], _I),
+    'tmpnn_graph_associate': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP], _I),
+    'tmpnn_graph_append_scratch_ints': ([_I, _I], C.c_size_t),
+    'tmpnn_graph_append': ([C.POINTER(Graph), C.POINTER(Frames), C.POINTER(SeqState), _VP, _I, _I, _I, _VP, _I,
+                            _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
+    'tmpnn_graph_decode': ([C.POINTER(Graph), C.POINTER(Index), C.POINTER(Frames), _VP, _VP, _VP, _I, _VP, _I,
+                            _VP, _VP, _VP], _I),
+    'tmpnn_graph_prune_mask': ([C.POINTER(Graph), C.POINTER(Index), _I, _I, C.c_float, _VP, _VP, _VP], _I),
+    'tmpnn_graph_compact_scratch_ints': ([_I, _I], C.c_size_t),
+    'tmpnn_graph_compact': ([C.POINTER(Graph), C.POINTER(Graph), _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
+}
+
+
+def lib():
+    """Loads the CUDA library once; raises if it was not built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TmpnnError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; '
+                             f'g.build()"` (nvcc, sm_100a).  trackmpnn_b200 has no CPU or PyTorch fallback path.')
+        l = C.CDLL(LIB_PATH)
+        l.tmpnn_last_error.restype = C.c_char_p
+        for name, (args, res) in _PROTOS.items():
+            f = getattr(l, name)
+            f.argtypes = args
+            f.restype = res
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return ['tmpnn_last_error'] + list(_PROTOS)
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().tmpnn_last_error().decode()
+        if rc == -1 and ('must be lesser' in msg or 'Only batch size' in msg):
+            raise AssertionError(msg)
+        raise TmpnnError(f'libtmpnn error {rc}: {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'libtmpnn needs contiguous CUDA tensors'
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
+_LAUNCHES = [0]
+# kernels launched per C-ABI call (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {
+    'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
+    'tmpnn_index_build': 9, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3,
+    'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
+    'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 2, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
+    'tmpnn_graph_compact': 4,
+}
+
+
+def call(name, *args):
+    _LAUNCHES[0] += KERNELS_PER_CALL.get(name, 0)
+    check(getattr(lib(), name)(*args))

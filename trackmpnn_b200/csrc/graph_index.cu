@@ -1,0 +1,238 @@
+// graph_index.cu -- per-step index over the slabs: detection-row list, per-detection
+// incidence CSR (past edges, then future edges, each ascending) and the tile table.
+//
+// Replaces the reference's dense edge_adj = node_adj^T (utils/graph.py:158, 300) and every
+// np.where(node_adj[:, i]) column scan (utils/graph.py:56, 232, 256, 508; models/loss.py:20, 34).
+// Pure integer work, HBM bound: ~4 B/row read for the detection list, ~40 B/edge row for the
+// CSR (src/dst read twice, two counters, one incidence written and sorted).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+constexpr int ROWS_PER_BLOCK = 1024;  // 256 threads x 4 rows
+constexpr int SORT_CAP = 4096;        // longest incidence segment one CTA sorts in shared memory
+
+// ---- detection list ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_dets(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                    const int32_t* __restrict__ ts, int cap_rows, int nblk,
+                                                    int32_t* __restrict__ blk_cnt) {
+  __shared__ int sm[33];
+  const int s = blockIdx.y, b = blockIdx.x;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  int c = 0;
+  const int r0 = b * ROWS_PER_BLOCK + threadIdx.x * 4;
+  if (r0 < n) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (r0 + q < n && ts[(size_t)s * cap_rows + r0 + q] >= 0) ++c;
+  }
+  int total;
+  block_exclusive_scan(c, sm, &total);
+  if (threadIdx.x == 0) blk_cnt[s * nblk + b] = total;
+}
+
+// single CTA: scan of the block counts, per-sequence ranges, tile table, totals
+__global__ void __launch_bounds__(1024) k_scan_det_blocks(const int32_t* __restrict__ n_rows,
+                                                          const int32_t* __restrict__ active, int num_seqs, int nblk,
+                                                          int32_t* __restrict__ blk_cnt, int32_t* __restrict__ seq_det_ptr,
+                                                          int32_t* __restrict__ tile_ptr, int32_t* __restrict__ n_dets,
+                                                          int32_t* __restrict__ n_edges, int cap_dets, int cap_inc,
+                                                          int32_t* __restrict__ status) {
+  __shared__ int sm[33];
+  const int nb = num_seqs * nblk;
+  int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nb ? blk_cnt[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, sm, &total);
+    if (i < nb) {
+      blk_cnt[i] = carry + ex;
+      if (i % nblk == 0) seq_det_ptr[i / nblk] = carry + ex;
+    }
+    carry += total;
+  }
+  const int nd = carry;
+  int tcarry = 0, rcarry = 0;
+  for (int s0 = 0; s0 < num_seqs; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    const int n = (s < num_seqs && !(active && !active[s])) ? n_rows[s] : 0;
+    int total;
+    const int ex = block_exclusive_scan((n + TMPNN_TILE_ROWS - 1) / TMPNN_TILE_ROWS, sm, &total);
+    if (s < num_seqs) tile_ptr[s] = tcarry + ex;
+    tcarry += total;
+    int rt;
+    block_exclusive_scan(n, sm, &rt);
+    rcarry += rt;
+  }
+  if (threadIdx.x == 0) {
+    seq_det_ptr[num_seqs] = nd;
+    tile_ptr[num_seqs] = tcarry;
+    const int ne = rcarry - nd;
+    int flags = 0;
+    if (nd > cap_dets) flags |= TMPNN_FLAG_DET_CAPACITY;
+    if (2 * ne > cap_inc) flags |= TMPNN_FLAG_INC_CAPACITY;
+    if (flags) atomicOr(status, flags);
+    // on overflow the consumers see an empty index instead of writing out of bounds
+    *n_dets = flags ? 0 : nd;
+    *n_edges = ne;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_write_dets(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                    const int32_t* __restrict__ ts, int cap_rows, int nblk,
+                                                    const int32_t* __restrict__ blk_off,
+                                                    const int32_t* __restrict__ n_dets, int32_t* __restrict__ det_rows,
+                                                    int32_t* __restrict__ det_of_row, int32_t* __restrict__ cnt) {
+  __shared__ int sm[33];
+  const int s = blockIdx.y, b = blockIdx.x;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  const int r0 = b * ROWS_PER_BLOCK + threadIdx.x * 4;
+  if (b * ROWS_PER_BLOCK >= n) return;  // whole block past the end (uniform)
+  int f[4];
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f[q] = (r0 + q < n && ts[(size_t)s * cap_rows + r0 + q] >= 0) ? 1 : 0;
+    c += f[q];
+  }
+  int total;
+  int k = block_exclusive_scan(c, sm, &total) + blk_off[s * nblk + b];
+  const bool overflow = (*n_dets == 0);  // set when capacity was exceeded (or the graph has no detections)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (r0 + q < n) {
+      const size_t row = (size_t)s * cap_rows + r0 + q;
+      if (f[q] && !overflow) {
+        det_rows[k] = (int32_t)row;
+        det_of_row[row] = k;
+        cnt[2 * k] = 0;
+        cnt[2 * k + 1] = 0;
+        ++k;
+      } else {
+        det_of_row[row] = -1;
+      }
+    }
+  }
+}
+
+// ---- incidence CSR -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_degree(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                const int32_t* __restrict__ src,
+                                                const int32_t* __restrict__ dst, int cap_rows,
+                                                const int32_t* __restrict__ det_of_row, const int32_t* __restrict__ n_dets,
+                                                int32_t* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  if (*n_dets == 0) return;
+  const size_t base = (size_t)s * cap_rows;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int a = src[base + r];
+    if (a < 0) continue;
+    const int b = dst[base + r];
+    atomicAdd(&cnt[2 * det_of_row[base + a] + 1], 1);  // future edge of src
+    atomicAdd(&cnt[2 * det_of_row[base + b]], 1);      // past edge of dst
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                const int32_t* __restrict__ src,
+                                              const int32_t* __restrict__ dst, int cap_rows,
+                                              const int32_t* __restrict__ det_of_row, const int32_t* __restrict__ n_dets,
+                                              int32_t* __restrict__ cnt, const int32_t* __restrict__ seg_ptr,
+                                              int32_t* __restrict__ inc) {
+  const int s = blockIdx.y;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  if (*n_dets == 0) return;
+  const size_t base = (size_t)s * cap_rows;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int a = src[base + r];
+    if (a < 0) continue;
+    const int b = dst[base + r];
+    const int ka = 2 * det_of_row[base + a] + 1, kb = 2 * det_of_row[base + b];
+    inc[seg_ptr[ka] + atomicSub(&cnt[ka], 1) - 1] = (int32_t)(base + r);
+    inc[seg_ptr[kb] + atomicSub(&cnt[kb], 1) - 1] = (int32_t)(base + r);
+  }
+}
+
+// Ascending order inside every segment (the atomic fill order is arbitrary): one CTA per
+// segment, bitonic network in shared memory.  Gives bit-reproducible aggregation sums and the
+// "first / last positive edge" semantics of models/loss.py:26-43.
+__global__ void __launch_bounds__(128) k_sort_segments(const int32_t* __restrict__ n_dets,
+                                                       const int32_t* __restrict__ seg_ptr, int32_t* __restrict__ inc,
+                                                       int32_t* __restrict__ status) {
+  __shared__ int32_t key[SORT_CAP];
+  const int nseg = 2 * (*n_dets);
+  for (int x = blockIdx.x; x < nseg; x += gridDim.x) {
+    const int s0 = seg_ptr[x], len = seg_ptr[x + 1] - s0;
+    if (len <= 1) continue;
+    if (len > SORT_CAP) {
+      if (threadIdx.x == 0) atomicOr(status, TMPNN_FLAG_SEG_CAPACITY);
+      continue;
+    }
+    int p = 2;
+    while (p < len) p <<= 1;
+    __syncthreads();
+    int unsorted = 0;
+    for (int i = threadIdx.x; i < p; i += blockDim.x) {
+      const int v = i < len ? inc[s0 + i] : 0x7fffffff;
+      key[i] = v;
+      if (i + 1 < len && inc[s0 + i + 1] < v) unsorted = 1;
+    }
+    if (!__syncthreads_or(unsorted)) continue;
+    for (int k = 2; k <= p; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < p; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const int a = key[i], b = key[l];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { key[i] = b; key[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < len; i += blockDim.x) inc[s0 + i] = key[i];
+  }
+}
+
+}  // namespace
+
+extern "C" size_t tmpnn_index_scratch_ints(int num_seqs, int cap_rows, int cap_dets) {
+  const size_t nblk = (size_t)tmpnn_div_up(cap_rows, ROWS_PER_BLOCK);
+  const size_t nchunks = (size_t)tmpnn_div_up(2 * (size_t)cap_dets + 2, SCAN_CHUNK);
+  return (size_t)num_seqs * nblk + (2 * (size_t)cap_dets + 4) + nchunks + 64;
+}
+
+extern "C" int tmpnn_index_build(const tmpnn_graph* g, const tmpnn_index* ix, const int32_t* active, void* stream) {
+  TMPNN_REQUIRE(g && ix && ix->scratch, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = g->num_seqs;
+  const int nblk = tmpnn_div_up(g->cap_rows, ROWS_PER_BLOCK);
+  int32_t* blk = ix->scratch;
+  int32_t* cnt = blk + (size_t)S * nblk;
+  int32_t* sums = cnt + (2 * (size_t)ix->cap_dets + 4);
+
+  dim3 grid_rows(nblk, S);
+  k_count_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk);
+  TMPNN_LAUNCH_CHECK();
+  k_scan_det_blocks<<<1, 1024, 0, st>>>(g->n_rows, active, S, nblk, blk, ix->seq_det_ptr, ix->tile_ptr, ix->n_dets, ix->n_edges,
+                                        ix->cap_dets, ix->cap_inc, g->status);
+  TMPNN_LAUNCH_CHECK();
+  k_write_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk, ix->n_dets, ix->det_rows,
+                                          ix->det_of_row, cnt);
+  TMPNN_LAUNCH_CHECK();
+  // one grid column per ~8K rows keeps the atomics kernels short without thousands of empty CTAs
+  dim3 grid_e(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 8), 64)), S);
+  k_degree<<<grid_e, 256, 0, st>>>(g->n_rows, active, g->src, g->dst, g->cap_rows, ix->det_of_row, ix->n_dets, cnt);
+  TMPNN_LAUNCH_CHECK();
+  TMPNN_CUDA_TRY(scan_exclusive(cnt, ix->seg_ptr, ix->n_dets, 2, 0, 2 * (long long)ix->cap_dets, sums, st));
+  k_fill<<<grid_e, 256, 0, st>>>(g->n_rows, active, g->src, g->dst, g->cap_rows, ix->det_of_row, ix->n_dets, cnt, ix->seg_ptr,
+                                 ix->inc);
+  TMPNN_LAUNCH_CHECK();
+  k_sort_segments<<<TMPNN_SM_COUNT * 8, 128, 0, st>>>(ix->n_dets, ix->seg_ptr, ix->inc, g->status);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
