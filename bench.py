@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- TrackMPNN hot path on B200: edge-updates/s and tracked frames/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--gpus N] ...                # CPU baseline arm (oracle port)
+
+Workload (BASELINE.json configs[2], "C3"): BDD100K-shaped synthetic detection streams
+(8 categories, F = 13, ~Poisson(80) detections / frame, --cur-win-size 5, greedy decode,
+stock random-init weights, torch.manual_seed(5)), 256 independent sequences PER GPU
+(weak scaling: sequences shard across ranks with no communication).  One "step" = one
+full tracking pass over the rank's batch: initialise, then for every frame
+update_graph -> TrackMPNN.forward -> decode_tracks (reference infer.py:48-87).
+
+metric: edge_updates_per_s = sum over forward calls of the edge rows in the graph / time
+(SURVEY.md section 8d); frames_per_s is reported beside it.  `value` is measured with the
+inputs resident in HBM; `e2e` re-uploads the detections from pinned host memory and reads
+the decoded tracks back every step.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_EDGE_UPDATE = 536   # h read 256 + h' write 256 + logit/score 8 + src/dst 8 + 2 incidences 8
+FLOP_PER_ROW_UPDATE = 49.5e3  # two 192x64 GEMVs + gates + head
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--seqs-per-gpu', type=int, default=256)
+    ap.add_argument('--frames', type=int, default=200)
+    ap.add_argument('--dets', type=int, default=80)
+    ap.add_argument('--dataset', default='bdd', choices=['bdd', 'kitti'])
+    ap.add_argument('--win', type=int, default=5)
+    ap.add_argument('--no-cuda-graph', action='store_true')
+    ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU-baseline sample (0 = auto)')
+    ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f'C3 {a.dataset}-shaped synthetic streams, F={8 + 5 if a.dataset == "bdd" else 3 + 5}, ~Poisson({a.dets}) dets/frame, '
+            f'{a.frames} frames, win {a.win}, greedy decode, stock init, {a.seqs_per_gpu} sequences per GPU')
+
+
+def make_sequences(a, rank):
+    from trackmpnn_b200 import synth
+    seqs = []
+    for i in range(a.seqs_per_gpu):
+        X, y = synth.make_sequence(5 + rank * a.seqs_per_gpu + i, a.frames, a.dets, a.dataset)
+        seqs.append((X[0], y[0]))
+    return seqs
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_oracle_sample(a, frames_cap, seed=5):
+    """One sequence of the workload through the oracle's inference loop, first `frames_cap` frames."""
+    from oracle import trackmpnn_oracle as O
+    from oracle.infer_loop import run_infer
+    from trackmpnn_b200 import synth
+    ncat = synth.num_categories(a.dataset)
+    params = O.init_params('2d', ncat, 64, 'diff', seed=5)
+    X, y = synth.make_sequence(seed, a.frames, a.dets, a.dataset)
+    t0 = time.perf_counter()
+    _, st = run_infer(params, X, y, ncategories=ncat, cur_win_size=a.win, max_frames=frames_cap)
+    dt = time.perf_counter() - t0
+    return st, dt
+
+
+def run_reference(a, rank):
+    """CPU baseline arm.  The reference is Python and does not travel to the GPU box, so this times the
+    oracle port (edge-list numpy restatement, validated against the reference's golden vectors) on the
+    host cores: numpy BLAS threads for the GEMMs, one thread for the graph bookkeeping."""
+    if rank != 0:
+        return
+    frames_cap = a.cpu_frames or 60
+    for _ in range(a.warmup):
+        cpu_oracle_sample(a, 2)
+    edges = frames = 0
+    t = 0.0
+    for k in range(a.steps):
+        st, dt = cpu_oracle_sample(a, frames_cap, seed=5 + k)
+        edges += st['edge_updates']; frames += st['frames']; t += dt
+    val = edges / t
+    sample = f'1 sequence of the workload, first {frames_cap} frames per step (oracle port, numpy)'
+    out = {'impl': 'reference', 'metric': 'edge_updates_per_s', 'value': val, 'unit': 'edge-updates/s',
+           'frames_per_s': frames / t, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+           'ms_per_step': 1e3 * t / max(1, a.steps), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': workload_name(a), 'sample': sample},
+           'cpu_baseline': {'value': val, 'unit': 'edge-updates/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+           'e2e': {'value': val, 'unit': 'edge-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if a.impl == 'reference':
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from trackmpnn_b200 import _lib as L, synth
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def reduce_(x, op):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=op)
+            return float(t.item())
+        return float(x)
+
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff').to(dev).eval()
+    seqs = make_sequences(a, rank)
+    eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph)
+
+    # ---- warm-up -------------------------------------------------------------------------
+    for _ in range(max(a.warmup, 1)):
+        eng.run()
+    _, st_w = eng.results()
+
+    # ---- timed region: K full passes, inputs resident in HBM ------------------------------
+    # the edge-row kernel is timed launch by launch with CUDA events (eager launches on the
+    # current stream), so the timed passes do not use CUDA-graph replay
+    eng.use_cuda_graph = False
+    eng.profile = []
+    clocks = ClockSampler(local)
+    barrier(); torch.cuda.synchronize()
+    clocks.start()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    edges = frames = dets = 0
+    for _ in range(a.steps):
+        eng.run()
+        edges += eng.edge_updates.clone(); frames += eng.frames_done.clone(); dets += eng.det_updates.clone()
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    clk = clocks.stop()
+    launches = L.launch_count() - l0
+    ms = reduce_(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    edges, frames, dets = int(edges.item()), int(frames.item()), int(dets.item())
+    tot_edges = reduce_(edges, dist.ReduceOp.SUM if world > 1 else None)
+    tot_frames = reduce_(frames, dist.ReduceOp.SUM if world > 1 else None)
+    prof = eng.profile
+    eng.profile = None
+    eng.ga.check_status()
+    k_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
+    k_edges = sum(int(p[2].item()) for p in prof)
+    hbm_peak, peak_src = measured_peaks()
+    achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roof = {'kernel': 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)', 'bound': 'hbm',
+            'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+            'peak_source': peak_src, 'launches_timed': len(prof), 'avg_launch_ms': k_ms / max(1, len(prof)),
+            'share_of_step': k_ms / ms if ms > 0 else None,
+            'fp32_tflops': FLOP_PER_ROW_UPDATE * k_edges / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
+            'algorithmic_bytes_per_edge_update': BYTES_PER_EDGE_UPDATE}
+
+    # ---- end to end: host buffers in, decoded tracks out, copies inside the timed region ---
+    e2e = None
+    if not a.skip_e2e:
+        eng.use_cuda_graph = not a.no_cuda_graph
+        x_host = eng.frames.x.cpu().pin_memory()
+        tab_host = [t.cpu().pin_memory() for t in (eng.frames.frame_ptr, eng.frames.frame_dets, eng.frames.det_ptr)]
+        out_host = torch.empty(eng.y_out_track.shape, dtype=eng.y_out_track.dtype).pin_memory()
+        h2d = x_host.numel() * 4 + sum(t.numel() * 4 for t in tab_host)
+        d2h = out_host.numel() * 4
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e_edges = 0
+        for _ in range(a.steps):
+            eng.frames.x.copy_(x_host, non_blocking=True)
+            for dst, src in zip((eng.frames.frame_ptr, eng.frames.frame_dets, eng.frames.det_ptr), tab_host):
+                dst.copy_(src, non_blocking=True)
+            eng.run()
+            out_host.copy_(eng.y_out_track, non_blocking=True)
+            torch.cuda.synchronize()
+            e_edges += int(eng.edge_updates.item())
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = reduce_(dt, dist.ReduceOp.MAX if world > 1 else None)
+        e_tot = reduce_(e_edges, dist.ReduceOp.SUM if world > 1 else None)
+        e2e = {'value': e_tot / dt, 'unit': 'edge-updates/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': 1e3 * dt / a.steps, 'api': 'TrackEngine.run() + results copy, CUDA-graph replay'}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.skip_cpu:
+        frames_cap = a.cpu_frames or 60
+        stc, dtc = cpu_oracle_sample(a, frames_cap)
+        cpu = {'value': stc['edge_updates'] / dtc, 'unit': 'edge-updates/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'frames_per_s': stc['frames'] / dtc, 'seconds': dtc,
+               'sample': f'1 sequence of the workload, first {frames_cap} frames (oracle port: numpy BLAS threads for '
+                         f'the GEMMs, one thread for graph bookkeeping)'}
+
+    if rank == 0:
+        sec = ms * 1e-3
+        out = {'metric': 'edge_updates_per_s', 'value': tot_edges / sec, 'unit': 'edge-updates/s',
+               'frames_per_s': tot_frames / sec, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 1),
+               'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': workload_name(a), 'l2': 'inputs_larger_than_l2 (state >= 4 GB per GPU vs 126 MB L2)',
+                          'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
+                          'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows,
+                          'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
+               'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

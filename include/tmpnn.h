@@ -95,6 +95,9 @@ typedef struct tmpnn_index {
 
 const char *tmpnn_last_error(void);
 int tmpnn_version(void);
+/* One-time per process: opts the kernels that need > 48 KB of shared memory in.  Entry points
+ * call it lazily; call it yourself before capturing a CUDA graph. */
+int tmpnn_init(void);
 
 /* ---- parameters ---------------------------------------------------------------------- */
 
@@ -157,6 +160,13 @@ int tmpnn_aggregate_edges(const tmpnn_graph *g, const tmpnn_index *ix, const flo
 int tmpnn_mp_step_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                       int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
                       float *agg, void *stream);
+
+/* The two row-type halves of tmpnn_mp_step_fwd, separately launchable (bench.py times the
+ * dominant edge-row kernel alone; tmpnn_mp_det_fwd needs agg from tmpnn_aggregate_dets). */
+int tmpnn_mp_edge_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                      int group, int num_groups, int concat, const float *edge_pack, void *stream);
+int tmpnn_mp_det_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                     int group, int num_groups, const float *node_pack, const float *agg, void *stream);
 
 /* ---- graph bookkeeping (utils/graph.py) ------------------------------------------------ */
 

@@ -592,6 +592,13 @@ inline dim3 stride_grid(const tmpnn_graph* g) {
 
 }  // namespace
 
+static bool g_graph_init_done = false;
+int tmpnn_init_graph_ops() {
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
+  g_graph_init_done = true;
+  return TMPNN_OK;
+}
+
 extern "C" int tmpnn_ypred_unpack(const int64_t* y_pred, int n, int32_t* ts, int32_t* det, int32_t* ass, void* stream) {
   if (n <= 0) return TMPNN_OK;
   k_ypred_unpack<<<min(tmpnn_div_up(n, 256), 1184), 256, 0, (cudaStream_t)stream>>>(y_pred, n, ts, det, ass);
@@ -676,11 +683,7 @@ extern "C" int tmpnn_graph_decode(const tmpnn_graph* g, const tmpnn_index* ix, c
                                   int32_t* scratch, void* stream) {
   TMPNN_REQUIRE(g && ix && fr && y_out_track && next_track_id && keep && scratch, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
-    attr_set = true;
-  }
+  if (!g_graph_init_done) { int rc0 = tmpnn_init_graph_ops(); if (rc0) return rc0; }
   k_decode<<<g->num_seqs, 256, sizeof(WalkSmem), st>>>(*g, ix->seq_det_ptr, ix->det_rows, fr->det_ptr, y_out_track,
                                                       next_track_id, t_upto_seq, t_upto_host, active, ret_win_size, keep,
                                                       scratch);

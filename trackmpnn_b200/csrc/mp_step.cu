@@ -496,24 +496,30 @@ k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int
   }
 }
 
-extern "C" int tmpnn_mp_step_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
-                                 int group, int num_groups, int concat, const float* edge_pack, const float* node_pack,
-                                 float* agg, void* stream) {
-  TMPNN_REQUIRE(g && ix && h_in && h_out && edge_pack && node_pack && agg, "null argument");
+int tmpnn_init_graph_ops();  // graph_ops.cu
+static bool g_init_done = false;
+
+// Opts the big-shared-memory kernels in (once per process / device).  Called lazily by the
+// entry points that need it; call it explicitly before capturing a CUDA graph.
+extern "C" int tmpnn_init(void) {
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<2 * H>)));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_det, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
+  int rc = tmpnn_init_graph_ops();
+  if (rc) return rc;
+  g_init_done = true;
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_mp_edge_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                 int group, int num_groups, int concat, const float* edge_pack, void* stream) {
+  TMPNN_REQUIRE(g && ix && h_in && h_out && edge_pack, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
+  if (!g_init_done) { int rc0 = tmpnn_init(); if (rc0) return rc0; }
   cudaStream_t st = (cudaStream_t)stream;
   const int col = group * H;
   const int first = group == 0, last = group == num_groups - 1;
-  int rc = tmpnn_aggregate_dets(g, ix, h_in, ldh, col, agg, stream);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
-    TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<2 * H>)));
-    TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_det, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
-    attr_set = true;
-  }
   if (concat)
     k_mp_edge<2 * H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<2 * H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
@@ -523,8 +529,29 @@ extern "C" int tmpnn_mp_step_fwd(const tmpnn_graph* g, const tmpnn_index* ix, co
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
         g->score, first, last);
   TMPNN_LAUNCH_CHECK();
-  k_mp_det<<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), st>>>(h_in, h_out, ldh, col, ix->n_dets, ix->det_rows, agg,
-                                                           node_pack, g->logit, g->score, first, last);
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                int group, int num_groups, const float* node_pack, const float* agg, void* stream) {
+  TMPNN_REQUIRE(g && ix && h_in && h_out && node_pack && agg, "null argument");
+  TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
+  TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
+  if (!g_init_done) { int rc0 = tmpnn_init(); if (rc0) return rc0; }
+  k_mp_det<<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), (cudaStream_t)stream>>>(
+      h_in, h_out, ldh, group * H, ix->n_dets, ix->det_rows, agg, node_pack, g->logit, g->score, group == 0,
+      group == num_groups - 1);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
+}
+
+extern "C" int tmpnn_mp_step_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                 int group, int num_groups, int concat, const float* edge_pack, const float* node_pack,
+                                 float* agg, void* stream) {
+  TMPNN_REQUIRE(g && ix && h_in && h_out && edge_pack && node_pack && agg, "null argument");
+  int rc = tmpnn_aggregate_dets(g, ix, h_in, ldh, group * H, agg, stream);
+  if (rc) return rc;
+  rc = tmpnn_mp_edge_fwd(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, stream);
+  if (rc) return rc;
+  return tmpnn_mp_det_fwd(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, stream);
 }

@@ -1,0 +1,232 @@
+"""Batched, device-resident tracking engine: many independent sequences advance in lock step.
+
+This is the loop of the reference's ``infer.py:48-87`` (initialise -> forward, then per frame
+update -> forward -> decode) for S sequences at once.  Every sequence owns one slab of the
+structure-of-arrays graph (``include/tmpnn.h``); per frame the engine enqueues a fixed list
+of kernels whose sizes come from device memory, so the host never reads the graph back and
+the whole frame can be replayed as a CUDA graph.  Sequences shard across GPUs with no
+communication (one engine per rank).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .device_graph import FrameTable, SlabGraph, SlabIndex
+from . import functional as F_
+
+H = L.HIDDEN
+_I32 = torch.int32
+
+
+def worst_case_rows(frame_counts, window):
+    """Upper bound of the rows one sequence's window graph can hold: all detections of
+    ``window`` consecutive timesteps active and pairwise connected."""
+    c = np.asarray(frame_counts, dtype=np.int64)
+    best = 0
+    for t in range(len(c)):
+        w = c[max(0, t - window + 1):t + 1]
+        s = int(w.sum())
+        pairs = (s * s - int((w * w).sum())) // 2
+        best = max(best, s + pairs)
+    return best
+
+
+class TrackEngine:
+    def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
+                 use_cuda_graph=True):
+        """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays."""
+        self.model = model
+        self.dev = device if device is not None else next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise L.TmpnnError('TrackEngine needs a CUDA device; there is no CPU path')
+        if any(g.msg_type not in ('diff', 'concat') for g in model.factor_grus):
+            raise ValueError('bad msg_type')
+        self.W, self.R = int(cur_win_size), int(ret_win_size)
+        self.S = len(sequences)
+        self.G = len(model.feature_idx)
+        self.ldh = self.G * H
+        xs = [np.asarray(x, dtype=np.float32).reshape(-1, np.asarray(x).shape[-1]) for x, _ in sequences]
+        ys = [np.asarray(y).reshape(-1, 2) for _, y in sequences]
+        self.frames = FrameTable(ys, self.dev, xs)
+        fp = self.frames.host_frame_ptr
+        counts = fp[:, 1:] - fp[:, :-1]
+        self.t_hi = int(self.frames.t_max) + 1
+        if cap_rows is None:
+            cap_rows = max(worst_case_rows(counts[s], self.W + self.R) for s in range(self.S))
+            cap_rows = max(64, (cap_rows + 63) // 64 * 64)
+        self.cap_rows = int(cap_rows)
+        max_frame = int(counts.max()) if counts.size else 1
+        self.cap_new = max(1, 2 * self.S * max_frame)
+        max_dets = int(max(worst_case_dets(counts[s], self.W + self.R) for s in range(self.S)))
+        dev = self.dev
+        self.ga = SlabGraph(self.S, self.cap_rows, dev, with_labels=False)
+        self.gb = SlabGraph(self.S, self.cap_rows, dev, with_labels=False, status=self.ga.status)
+        self._g0, self._g1 = self.ga, self.gb
+        n_all = self.S * self.cap_rows
+        self.h_cur = torch.zeros((n_all, self.ldh), dtype=torch.float32, device=dev)
+        self.h_alt = torch.zeros((n_all, self.ldh), dtype=torch.float32, device=dev)
+        self.index = SlabIndex(self.ga, cap_dets=self.S * max_dets, cap_inc=2 * n_all)
+        z = lambda n: torch.zeros(n, dtype=_I32, device=dev)
+        self.st = dict(phase=z(self.S), skip_until=z(self.S), t_end=z(self.S), active=z(self.S), t_upto=z(self.S),
+                       fresh=z(self.S))
+        self.st_c = L.SeqState(*[L.ptr(self.st[k]) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')])
+        self.y_out_track = torch.full((max(1, self.frames.total_dets),), -1, dtype=_I32, device=dev)
+        self.next_track_id = z(self.S)
+        self.t_dev = z(1)
+        self.new_rows = z(self.cap_new)
+        self.new_x = z(self.cap_new)
+        self.n_new = z(2)
+        self.n_appended = z(self.S)
+        self.append_scratch = z(int(L.lib().tmpnn_graph_append_scratch_ints(self.S, self.cap_rows)))
+        self.compact_scratch = z(int(L.lib().tmpnn_graph_compact_scratch_ints(self.S, self.cap_rows)))
+        self.decode_scratch = z(self.S + 4)
+        self.keep = torch.zeros(n_all, dtype=torch.uint8, device=dev)
+        self.new_of_old = z(n_all)
+        self.agg = torch.empty((self.index.cap_dets, H), dtype=torch.float32, device=dev)
+        self.a_scratch = torch.empty((self.cap_new, H), dtype=torch.float32, device=dev)
+        # work counters, accumulated on the device
+        self.edge_updates = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.det_updates = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.frames_done = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.use_cuda_graph = use_cuda_graph
+        self.profile = None  # list of (start event, end event, n_edges tensor) per edge-kernel launch when enabled
+        self._graph = None
+        self.ticks = 0
+
+    # ---- one engine tick --------------------------------------------------------------------
+    def _forward(self, g, h_in, h_out):
+        model = self.model
+        st = L.stream()
+        # K0 on the new detection rows (device-side count), all feature groups
+        for grp in range(self.G):
+            seq = model.input_transforms[grp]
+            lin1, bn, lin2 = seq[0], seq[1], seq[3]
+            cols = model.feature_idx[grp]
+            if bn.training:
+                raise L.TmpnnError('TrackEngine is an inference engine: call model.eval() first')
+            L.call('tmpnn_input_linear1', L.ptr(self.frames.x), self.frames.ldx, int(cols[0]), len(cols),
+                   L.ptr(self.new_x), L.ptr(lin1.weight.detach()), L.ptr(lin1.bias.detach()), L.ptr(self.a_scratch),
+                   L.ptr(self.n_new), 0, st)
+            L.call('tmpnn_input_bn_relu_linear2', L.ptr(self.a_scratch), L.ptr(bn.running_mean), L.ptr(bn.running_var),
+                   L.ptr(bn.weight.detach()), L.ptr(bn.bias.detach()), L.ptr(lin2.weight.detach()),
+                   L.ptr(lin2.bias.detach()), L.ptr(h_in), self.ldh, grp * H, L.ptr(self.new_rows),
+                   L.ptr(self.n_new), 0, st)
+        self.index.build(g, self.st['active'])
+        packs = F_.packed_cells(model)
+        for grp in range(self.G):
+            concat = int(model.factor_grus[grp].msg_type == 'concat')
+            L.call('tmpnn_aggregate_dets', g.c, self.index.c, L.ptr(h_in), self.ldh, grp * H, L.ptr(self.agg), st)
+            if self.profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            L.call('tmpnn_mp_edge_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G, concat,
+                   L.ptr(packs[grp][0]), st)
+            if self.profile is not None:
+                e1.record()
+                self.profile.append((e0, e1, self.index.n_edges.clone()))
+            L.call('tmpnn_mp_det_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
+                   L.ptr(packs[grp][1]), L.ptr(self.agg), st)
+        self.edge_updates += self.index.n_edges
+        self.det_updates += self.index.n_dets
+
+    def _start(self):
+        g = self.ga
+        # the initial step runs h_alt -> h_cur so that h_cur holds the current state afterwards
+        # (buffer roles never change: CUDA graphs bake the pointers in)
+        L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), None, 1, self.W, 0, L.ptr(self.h_alt),
+               self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
+               L.ptr(self.n_appended), L.ptr(self.append_scratch), L.stream())
+        self._forward(g, self.h_alt, self.h_cur)
+
+    def _tick(self):
+        """One iteration of infer.py:60-87 for every sequence at t = *t_dev, then t += 1."""
+        g, go = self.ga, self.gb
+        st = L.stream()
+        L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
+               L.ptr(self.h_cur), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
+               L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
+        self._forward(g, self.h_cur, self.h_alt)
+        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, st)
+        L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
+               L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
+               L.ptr(self.keep), L.ptr(self.decode_scratch), st)
+        L.call('tmpnn_graph_compact', g.c, go.c, L.ptr(self.keep), L.ptr(self.h_alt), L.ptr(self.h_cur),
+               L.ptr(self.st['active']), L.ptr(self.h_cur), self.ldh, L.ptr(self.new_of_old),
+               L.ptr(self.compact_scratch), st)
+        self.frames_done += self.st['active'].sum()
+        self.t_dev += 1
+
+    # ---- driver --------------------------------------------------------------------------------
+    def reset(self):
+        self.ga, self.gb = self._g0, self._g1
+        for t in self.st.values():
+            t.zero_()
+        for g in (self.ga, self.gb):
+            g.n_rows.zero_()
+        self.ga.status.zero_()
+        self.y_out_track.fill_(-1)
+        self.next_track_id.zero_()
+        self.t_dev.zero_()
+        self.edge_updates.zero_()
+        self.det_updates.zero_()
+        self.frames_done.zero_()
+        self.ticks = 0
+
+    def run(self, max_ticks=None):
+        """Tracks every sequence to its end (or ``max_ticks`` frames).  Enqueues only; call
+        ``results()`` (which synchronises) for the decoded tracks."""
+        self.reset()
+        self._start()
+        n_ticks = self.t_hi if max_ticks is None else min(self.t_hi, int(max_ticks))
+        # the two graph sets swap roles every tick -> capture two ticks per CUDA graph replay
+        t = 0
+        if self.use_cuda_graph and n_ticks >= 4:
+            if self._graph is None:
+                self._capture()
+            # state after capture warm-up was rewound by _capture; replay pairs
+            while t + 2 <= n_ticks:
+                self._graph.replay()
+                t += 2
+        while t < n_ticks:
+            self._tick()
+            self.ga, self.gb = self.gb, self.ga
+            t += 1
+        self.ticks = n_ticks
+        return self
+
+    def _capture(self):
+        """Captures two consecutive ticks (ga -> gb -> ga) as one CUDA graph.  Capturing does not
+        execute, so the engine state is untouched."""
+        L.check(L.lib().tmpnn_init())
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._tick()
+            self.ga, self.gb = self.gb, self.ga
+            self._tick()
+            self.ga, self.gb = self.gb, self.ga
+        self._graph = g
+
+    def results(self):
+        """Synchronises; returns (list of y_out [ND_s, 2] int64 arrays, stats dict)."""
+        torch.cuda.synchronize(self.dev)
+        self.ga.check_status()
+        track = self.y_out_track.cpu().numpy().astype(np.int64)
+        dp = self.frames.host_det_ptr
+        ts = self.frames  # noqa: F841
+        outs = []
+        for s in range(self.S):
+            outs.append(track[dp[s]:dp[s + 1]].copy())
+        stats = dict(edge_updates=int(self.edge_updates.item()), det_updates=int(self.det_updates.item()),
+                     frames=int(self.frames_done.item()), ticks=self.ticks)
+        return outs, stats
+
+
+def worst_case_dets(frame_counts, window):
+    c = np.asarray(frame_counts, dtype=np.int64)
+    best = 0
+    for t in range(len(c)):
+        best = max(best, int(c[max(0, t - window + 1):t + 1].sum()))
+    return max(best, 1)
