@@ -185,8 +185,10 @@ int tmpnn_edges_from_coo(const int64_t *idx, const float *val, int64_t nnz, int 
 /* Greedy association (utils/graph.py:251-268 == 437-454): for each detection row with p >= 0.5
  * take its positive future edges whose far end is positive, keep the nearest timestep, pick the
  * first arg-max; ass = det id of that far end.  mode 0 = greedy from scores, 1 = teacher forcing
- * from labels (utils/graph.py:229-245). */
-int tmpnn_graph_associate(const tmpnn_graph *g, const tmpnn_index *ix, int mode, void *stream);
+ * from labels (utils/graph.py:229-245).
+ * active must be the mask the index was built with (sequences sitting out keep their ass). */
+int tmpnn_graph_associate(const tmpnn_graph *g, const tmpnn_index *ix, int mode, const int32_t *active,
+                          void *stream);
 
 /* Detections of the sequences, grouped by timestamp: frame_ptr[s*(t_max+2) + t] .. [+1] indexes
  * frame_dets (ascending detection ids of sequence s at time t). */

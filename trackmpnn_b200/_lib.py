@@ -77,7 +77,7 @@ _PROTOS = {
     'tmpnn_ypred_pack': ([_VP, _VP, _VP, _I, _VP, _VP], _I),
     'tmpnn_coo_from_edges': ([_VP, _VP, _VP, _I, _I, _VP, _VP, C.c_int64, _VP, _VP], _I),
     'tmpnn_edges_from_coo': ([_VP, _VP, C.c_int64, _I, _VP, _VP, _VP], _I),
-    'tmpnn_graph_associate': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP], _I),
+    'tmpnn_graph_associate': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP], _I),
     'tmpnn_graph_append_scratch_ints': ([_I, _I], C.c_size_t),
     'tmpnn_graph_append': ([C.POINTER(Graph), C.POINTER(Frames), C.POINTER(SeqState), _VP, _I, _I, _I, _VP, _I,
                             _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
@@ -139,8 +139,6 @@ _LAUNCHES = [0]
 KERNELS_PER_CALL = {
     'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
     'tmpnn_index_build': 9, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1,
-    'tmpnn_mp_edge_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP], _I),
-    'tmpnn_mp_det_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _VP], _I),
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 2, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4,

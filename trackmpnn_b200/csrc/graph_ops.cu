@@ -78,8 +78,9 @@ __global__ void k_edges_from_coo(const int64_t* __restrict__ idx, const float* _
 }
 
 // ---- association -----------------------------------------------------------------------------
-__global__ void k_reset_ass(const int32_t* __restrict__ n_rows, int cap_rows, int32_t* __restrict__ ass) {
-  const int s = blockIdx.y, n = n_rows[s];
+__global__ void k_reset_ass(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active, int cap_rows,
+                            int32_t* __restrict__ ass) {
+  const int s = blockIdx.y, n = seq_off(active, s) ? 0 : n_rows[s];
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
     ass[(size_t)s * cap_rows + r] = -1;
 }
@@ -640,11 +641,12 @@ extern "C" int tmpnn_edges_from_coo(const int64_t* idx, const float* val, int64_
   return TMPNN_OK;
 }
 
-extern "C" int tmpnn_graph_associate(const tmpnn_graph* g, const tmpnn_index* ix, int mode, void* stream) {
+extern "C" int tmpnn_graph_associate(const tmpnn_graph* g, const tmpnn_index* ix, int mode, const int32_t* active,
+                                     void* stream) {
   TMPNN_REQUIRE(g && ix, "null argument");
   TMPNN_REQUIRE(mode == 0 || (mode == 1 && g->label), "teacher forcing needs labels");
   cudaStream_t st = (cudaStream_t)stream;
-  k_reset_ass<<<stride_grid(g), 256, 0, st>>>(g->n_rows, g->cap_rows, g->ass);
+  k_reset_ass<<<stride_grid(g), 256, 0, st>>>(g->n_rows, active, g->cap_rows, g->ass);
   TMPNN_LAUNCH_CHECK();
   k_associate<<<TMPNN_SM_COUNT * 4, 256, 0, st>>>(ix->n_dets, ix->det_rows, ix->seg_ptr, ix->inc, g->ts, g->det, g->dst,
                                                  g->label, g->score, g->cap_rows, mode, g->ass, g->status);

@@ -139,6 +139,10 @@ class TrackEngine:
                self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), L.stream())
         self._forward(g, self.h_alt, self.h_cur)
+        # update_graph re-associates from the previous scores before it appends (utils/graph.py:251-268).
+        # Inside the loop that result is carried over from decode_tracks (same scores, and deletion
+        # cannot change a survivor's association); after the initial forward it is computed here.
+        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), L.stream())
 
     def _tick(self):
         """One iteration of infer.py:60-87 for every sequence at t = *t_dev, then t += 1."""
@@ -148,7 +152,7 @@ class TrackEngine:
                L.ptr(self.h_cur), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
         self._forward(g, self.h_cur, self.h_alt)
-        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, st)
+        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), st)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
                L.ptr(self.keep), L.ptr(self.decode_scratch), st)

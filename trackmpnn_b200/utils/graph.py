@@ -143,13 +143,13 @@ def update_graph(node_adj, labels, scores, y_pred, X, y, t, use_hungraian=True, 
 
 def _associate(wg, scores, use_hungarian, mode):
     if mode == 'train':
-        L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 1, L.stream())
+        L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 1, None, L.stream())
         wg.g.check_status()
     elif use_hungarian:
         raise NotImplementedError('Hungarian association is not built yet (SURVEY.md section 8f-1); '
                                   'pass use_hungraian=False (the drivers\' default, --hungarian off)')
     else:
-        L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 0, L.stream())
+        L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 0, None, L.stream())
 
 
 def _compact(wg, keep, states, scores):
