@@ -56,6 +56,8 @@ typedef enum tmpnn_status {
 #define TMPNN_FLAG_SEG_CAPACITY 8  /* a detection has more incident edges than a CTA sorts */
 #define TMPNN_FLAG_MULTI_GT_EDGE 16 /* "More than one GT edge from same node!" (utils/graph.py:243) */
 #define TMPNN_FLAG_WALK_CAPACITY 32 /* more detection rows in one window than the decode walk holds */
+#define TMPNN_FLAG_TC_TIMEOUT 64    /* tensor-core kernel: an mbarrier wait timed out (results invalid) */
+#define TMPNN_FLAG_TC_RANGE 128     /* tensor-core kernel: |value| > 6e4 would overflow the fp16 split; use the FMA path */
 
 typedef struct tmpnn_graph {
   int32_t num_seqs;   /* S */
@@ -88,6 +90,7 @@ typedef struct tmpnn_index {
   int32_t *seg_ptr;      /* [2*cap_dets+1] past segment of detection k = [seg_ptr[2k], seg_ptr[2k+1]), future = [seg_ptr[2k+1], seg_ptr[2k+2]) */
   int32_t *inc;          /* [cap_inc] global edge-row ids */
   int32_t *tile_ptr;     /* [S+1] prefix sum of ceil(n_rows[s] / TMPNN_TILE_ROWS) */
+  int32_t *tile128_ptr;  /* [S+1] prefix sum of ceil(n_rows[s] / 128): tiles of the tensor-core kernel */
   int32_t *scratch;      /* [tmpnn_index_scratch_ints(...)] */
 } tmpnn_index;
 
@@ -167,6 +170,17 @@ int tmpnn_mp_edge_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *
                       int group, int num_groups, int concat, const float *edge_pack, void *stream);
 int tmpnn_mp_det_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                      int group, int num_groups, const float *node_pack, const float *agg, void *stream);
+
+/* Tensor-core form of tmpnn_mp_edge_fwd for msg_type 'diff' (tcgen05.mma kind::f16, 3-term fp16
+ * split of activations and weights, accumulators in TMEM; csrc/mp_step_tc.cu).  edge_image is the
+ * tmpnn_gru_tc_pack_bytes() byte image written by tmpnn_pack_gru_tc (fp16 hi/lo weights in the
+ * 128B-swizzled K-major UMMA layout + fused biases + head slice).  Same outputs as the FMA
+ * kernel to ~2e-6; sets TMPNN_FLAG_TC_RANGE if an activation exceeds the fp16 range. */
+size_t tmpnn_gru_tc_pack_bytes(void);
+int tmpnn_pack_gru_tc(const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
+                      const float *head_w, const float *head_b, void *packed, void *stream);
+int tmpnn_mp_edge_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                         int group, int num_groups, const void *edge_image, void *stream);
 
 /* ---- graph bookkeeping (utils/graph.py) ------------------------------------------------ */
 

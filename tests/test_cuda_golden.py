@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _model(gold, dev, train=False):
+def _model(gold, dev, train=False, tensor=False):
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     m = gold.meta
-    model = TrackMPNN(m['features'], m['ncategories'], 64, 0, m['msg_type'])
+    model = TrackMPNN(m['features'], m['ncategories'], 64, 0, m['msg_type'], use_tensor_cores=tensor)
     sd = {k: torch.from_numpy(v) for k, v in gold.params().items()}
     model.load_state_dict(sd, strict=True)
     model.to(dev)
@@ -48,13 +48,17 @@ def _fix(scores, y_pred, tp):
 NON_HUNG = [n for n in golden_names('infer') if 'hung' not in n]
 
 
+@pytest.mark.parametrize('tensor', [False, True], ids=['fma', 'tcgen05'])
 @pytest.mark.parametrize('name', NON_HUNG)
-def test_infer_free_running(name):
+def test_infer_free_running(name, tensor):
+    """tensor=False: fp32 FMA kernel; tensor=True: tcgen05 kernel (3-term fp16 split) -- same 1e-4 bar."""
     from trackmpnn_b200.utils.graph import initialize_graph, update_graph, prune_graph, decode_tracks
     gold = Golden(name)
     m = gold.meta
+    if tensor and m['msg_type'] != 'diff':
+        pytest.skip('the tensor-core kernel covers msg_type diff')
     dev = torch.device('cuda:0')
-    model = _model(gold, dev)
+    model = _model(gold, dev, tensor=tensor)
     X, y = torch.from_numpy(gold.X).to(dev), torch.from_numpy(gold.y).to(dev)
     y_out = gold.y[0].astype(np.int64); y_out[:, 1] = -1
     with torch.no_grad():

@@ -47,6 +47,8 @@ def _sequences(seeds, dataset='kitti', gap=()):
     dict(seeds=[35, 36, 40], msg_type='concat', ret=2, graph=True, gap=()),
     dict(seeds=[30, 49, 34, 52, 54], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54)),
     dict(seeds=[71, 72], msg_type='diff', ret=0, graph=False, gap=(), stock=True),
+    dict(seeds=[30, 34, 48, 58, 65], msg_type='diff', ret=0, graph=False, gap=(), tensor=True),
+    dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True),
 ])
 def test_engine_matches_oracle(cfg):
     from trackmpnn_b200.engine import TrackEngine
@@ -55,7 +57,8 @@ def test_engine_matches_oracle(cfg):
     model = _model(dev, msg_type=cfg['msg_type'], scale=1.0 if stock else 20.0, edge_bias=None if stock else 0.0)
     params = _params(model)
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
-    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'])
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],
+                      tensor_cores=cfg.get('tensor', False))
     outs, stats = eng.run().results()
     tot_e = tot_f = 0
     for (X, y), got in zip(seqs, outs):

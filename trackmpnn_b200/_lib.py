@@ -22,6 +22,8 @@ FLAG_NAMES = {
     8: 'a detection has more incident edges than one CTA can sort',
     16: 'More than one GT edge from same node!',
     32: 'more detection rows in one window than the decode walk holds',
+    64: 'tensor-core kernel: mbarrier wait timed out (results invalid)',
+    128: 'tensor-core kernel: activation exceeds the fp16 split range (use the FMA path)',
 }
 
 i32p = C.POINTER(C.c_int32)
@@ -37,7 +39,8 @@ class Graph(C.Structure):
 class Index(C.Structure):
     _fields_ = [('cap_dets', C.c_int32), ('cap_inc', C.c_int32), ('n_dets', C.c_void_p), ('n_edges', C.c_void_p),
                 ('det_rows', C.c_void_p), ('det_of_row', C.c_void_p), ('seq_det_ptr', C.c_void_p),
-                ('seg_ptr', C.c_void_p), ('inc', C.c_void_p), ('tile_ptr', C.c_void_p), ('scratch', C.c_void_p)]
+                ('seg_ptr', C.c_void_p), ('inc', C.c_void_p), ('tile_ptr', C.c_void_p), ('tile128_ptr', C.c_void_p),
+                ('scratch', C.c_void_p)]
 
 
 class Frames(C.Structure):
@@ -73,6 +76,9 @@ _PROTOS = {
     'tmpnn_mp_step_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_edge_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_mp_det_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _VP], _I),
+    'tmpnn_gru_tc_pack_bytes': ([], C.c_size_t),
+    'tmpnn_pack_gru_tc': ([_VP] * 8, _I),
+    'tmpnn_mp_edge_fwd_tc': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_ypred_unpack': ([_VP, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_ypred_pack': ([_VP, _VP, _VP, _I, _VP, _VP], _I),
     'tmpnn_coo_from_edges': ([_VP, _VP, _VP, _I, _I, _VP, _VP, C.c_int64, _VP, _VP], _I),
@@ -138,7 +144,7 @@ _LAUNCHES = [0]
 # kernels launched per C-ABI call (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
-    'tmpnn_index_build': 9, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1,
+    'tmpnn_index_build': 9, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 2, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4,

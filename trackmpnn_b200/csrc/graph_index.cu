@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) k_count_dets(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(1024) k_scan_det_blocks(const int32_t* __restrict__ n_rows,
                                                           const int32_t* __restrict__ active, int num_seqs, int nblk,
                                                           int32_t* __restrict__ blk_cnt, int32_t* __restrict__ seq_det_ptr,
-                                                          int32_t* __restrict__ tile_ptr, int32_t* __restrict__ n_dets,
+                                                          int32_t* __restrict__ tile_ptr, int32_t* __restrict__ tile128_ptr,
+                                                          int32_t* __restrict__ n_dets,
                                                           int32_t* __restrict__ n_edges, int cap_dets, int cap_inc,
                                                           int32_t* __restrict__ status) {
   __shared__ int sm[33];
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(1024) k_scan_det_blocks(const int32_t* __restr
     carry += total;
   }
   const int nd = carry;
-  int tcarry = 0, rcarry = 0;
+  int tcarry = 0, rcarry = 0, t128carry = 0;
   for (int s0 = 0; s0 < num_seqs; s0 += 1024) {
     const int s = s0 + threadIdx.x;
     const int n = (s < num_seqs && !(active && !active[s])) ? n_rows[s] : 0;
@@ -62,6 +63,12 @@ __global__ void __launch_bounds__(1024) k_scan_det_blocks(const int32_t* __restr
     const int ex = block_exclusive_scan((n + TMPNN_TILE_ROWS - 1) / TMPNN_TILE_ROWS, sm, &total);
     if (s < num_seqs) tile_ptr[s] = tcarry + ex;
     tcarry += total;
+    if (tile128_ptr) {
+      int t128;
+      const int ex128 = block_exclusive_scan((n + 127) / 128, sm, &t128);
+      if (s < num_seqs) tile128_ptr[s] = t128carry + ex128;
+      t128carry += t128;
+    }
     int rt;
     block_exclusive_scan(n, sm, &rt);
     rcarry += rt;
@@ -69,6 +76,7 @@ __global__ void __launch_bounds__(1024) k_scan_det_blocks(const int32_t* __restr
   if (threadIdx.x == 0) {
     seq_det_ptr[num_seqs] = nd;
     tile_ptr[num_seqs] = tcarry;
+    if (tile128_ptr) tile128_ptr[num_seqs] = t128carry;
     const int ne = rcarry - nd;
     int flags = 0;
     if (nd > cap_dets) flags |= TMPNN_FLAG_DET_CAPACITY;
@@ -218,7 +226,8 @@ extern "C" int tmpnn_index_build(const tmpnn_graph* g, const tmpnn_index* ix, co
   dim3 grid_rows(nblk, S);
   k_count_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk);
   TMPNN_LAUNCH_CHECK();
-  k_scan_det_blocks<<<1, 1024, 0, st>>>(g->n_rows, active, S, nblk, blk, ix->seq_det_ptr, ix->tile_ptr, ix->n_dets, ix->n_edges,
+  k_scan_det_blocks<<<1, 1024, 0, st>>>(g->n_rows, active, S, nblk, blk, ix->seq_det_ptr, ix->tile_ptr, ix->tile128_ptr, ix->n_dets,
+                                        ix->n_edges,
                                         ix->cap_dets, ix->cap_inc, g->status);
   TMPNN_LAUNCH_CHECK();
   k_write_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk, ix->n_dets, ix->det_rows,

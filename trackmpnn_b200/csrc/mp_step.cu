@@ -497,15 +497,19 @@ k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int
 }
 
 int tmpnn_init_graph_ops();  // graph_ops.cu
+int tmpnn_init_tc();         // mp_step_tc.cu
 static bool g_init_done = false;
 
 // Opts the big-shared-memory kernels in (once per process / device).  Called lazily by the
 // entry points that need it; call it explicitly before capturing a CUDA graph.
 extern "C" int tmpnn_init(void) {
+  if (g_init_done) return TMPNN_OK;
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge<2 * H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<2 * H>)));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_det, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<H>)));
   int rc = tmpnn_init_graph_ops();
+  if (rc) return rc;
+  rc = tmpnn_init_tc();
   if (rc) return rc;
   g_init_done = true;
   return TMPNN_OK;

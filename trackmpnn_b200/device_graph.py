@@ -62,10 +62,11 @@ class SlabIndex:
         self.seg_ptr = torch.zeros(2 * self.cap_dets + 2, **i32)
         self.inc = torch.empty(self.cap_inc, **i32)
         self.tile_ptr = torch.zeros(S + 1, **i32)
+        self.tile128_ptr = torch.zeros(S + 1, **i32)
         self.scratch = torch.empty(int(L.lib().tmpnn_index_scratch_ints(S, cap, self.cap_dets)), **i32)
         self._c = L.Index(self.cap_dets, self.cap_inc, L.ptr(self.n_dets), L.ptr(self.n_edges), L.ptr(self.det_rows),
                           L.ptr(self.det_of_row), L.ptr(self.seq_det_ptr), L.ptr(self.seg_ptr), L.ptr(self.inc),
-                          L.ptr(self.tile_ptr), L.ptr(self.scratch))
+                          L.ptr(self.tile_ptr), L.ptr(self.tile128_ptr), L.ptr(self.scratch))
 
     @property
     def c(self):

@@ -35,7 +35,7 @@ def worst_case_rows(frame_counts, window):
 
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, tensor_cores='auto'):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays."""
         self.model = model
         self.dev = device if device is not None else next(model.parameters()).device
@@ -91,6 +91,9 @@ class TrackEngine:
         self.det_updates = torch.zeros(1, dtype=torch.int64, device=dev)
         self.frames_done = torch.zeros(1, dtype=torch.int64, device=dev)
         self.use_cuda_graph = use_cuda_graph
+        diff = all(g.msg_type == 'diff' for g in model.factor_grus)
+        # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise
+        self.tensor = diff and (self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self.profile = None  # list of (start event, end event, n_edges tensor) per edge-kernel launch when enabled
         self._graph = None
         self.ticks = 0
@@ -115,14 +118,19 @@ class TrackEngine:
                    L.ptr(self.n_new), 0, st)
         self.index.build(g, self.st['active'])
         packs = F_.packed_cells(model)
+        tc = F_.packed_cells_tc(model) if self.tensor else None
         for grp in range(self.G):
             concat = int(model.factor_grus[grp].msg_type == 'concat')
             L.call('tmpnn_aggregate_dets', g.c, self.index.c, L.ptr(h_in), self.ldh, grp * H, L.ptr(self.agg), st)
             if self.profile is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            L.call('tmpnn_mp_edge_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G, concat,
-                   L.ptr(packs[grp][0]), st)
+            if self.tensor:
+                L.call('tmpnn_mp_edge_fwd_tc', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
+                       L.ptr(tc[grp]), st)
+            else:
+                L.call('tmpnn_mp_edge_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G, concat,
+                       L.ptr(packs[grp][0]), st)
             if self.profile is not None:
                 e1.record()
                 self.profile.append((e0, e1, self.index.n_edges.clone()))

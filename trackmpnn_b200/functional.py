@@ -46,6 +46,61 @@ def packed_cells(model):
     return cache.packs
 
 
+def packed_cells_tc(model):
+    """fp16 hi/lo UMMA weight images of the edge cells (tensor-core path, msg_type 'diff' only)."""
+    cache = model.__dict__.setdefault('_tmpnn_pack_cache_tc', _PackCache())
+    params = []
+    for gru in model.factor_grus:
+        cell = gru.edge_gru
+        params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+    params += [model.output_transform_edge.weight, model.output_transform_edge.bias]
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    if cache.key != key:
+        packs = []
+        nbytes = int(L.lib().tmpnn_gru_tc_pack_bytes())
+        for g, gru in enumerate(model.factor_grus):
+            cell, head = gru.edge_gru, model.output_transform_edge
+            if gru.msg_type != 'diff':
+                packs.append(None)
+                continue
+            out = torch.empty(nbytes, dtype=torch.uint8, device=cell.weight_ih.device)
+            hw = head.weight.detach()[0, g * H:(g + 1) * H]
+            L.call('tmpnn_pack_gru_tc', L.ptr(cell.weight_ih.detach()), L.ptr(cell.weight_hh.detach()),
+                   L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(hw), L.ptr(head.bias.detach()),
+                   L.ptr(out), L.stream())
+            packs.append(out)
+        cache.key, cache.packs = key, packs
+    return cache.packs
+
+
+TENSOR_MIN_ROWS = 8192  # below this a window graph cannot fill the 148 x 128-row tiles; the FMA path wins
+
+
+def use_tensor_path(model, n_rows):
+    mode = getattr(model, 'use_tensor_cores', 'auto')
+    if any(g.msg_type != 'diff' for g in model.factor_grus):
+        return False
+    if mode == 'auto':
+        return n_rows >= TENSOR_MIN_ROWS
+    return bool(mode)
+
+
+def mp_step(model, g_c, ix_c, h_in, h_out, ldh, agg, tensor):
+    """One message-passing step over all feature groups (K1-det, edge rows, detection rows)."""
+    G = len(model.feature_idx)
+    packs = packed_cells(model)
+    tc = packed_cells_tc(model) if tensor else None
+    st = L.stream()
+    for g in range(G):
+        concat = int(model.factor_grus[g].msg_type == 'concat')
+        L.call('tmpnn_aggregate_dets', g_c, ix_c, L.ptr(h_in), ldh, g * H, L.ptr(agg), st)
+        if tensor:
+            L.call('tmpnn_mp_edge_fwd_tc', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(tc[g]), st)
+        else:
+            L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
+        L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
+
+
 def input_transform_rows(model, g, x, x_idx, n, n_edge_rows, h, ldh, out_rows, n_dev=None):
     """K0 for feature group g on ``n`` detection feature rows ``x[x_idx]`` -> ``h[out_rows, 64g:64g+64]``."""
     seq = model.input_transforms[g]
@@ -101,11 +156,10 @@ def track_mpnn_forward(model, x, h_in, node_adj, edge_adj):
     ix = wg.index()
     h_out = torch.empty_like(h_cur)
     agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
-    packs = packed_cells(model)
-    for g in range(G):
-        concat = int(model.factor_grus[g].msg_type == 'concat')
-        L.call('tmpnn_mp_step_fwd', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]),
-               L.ptr(packs[g][1]), L.ptr(agg), L.stream())
+    tensor = use_tensor_path(model, n_tot)
+    mp_step(model, wg.g.c, ix.c, h_cur, h_out, ldh, agg, tensor)
+    if tensor:
+        wg.g.check_status()
     logits = wg.g.logit[:n_tot].clone().unsqueeze(1)
     scores = wg.g.score[:n_tot].clone().unsqueeze(1)
     return scores, logits, h_out, tuple(None for _ in range(G))

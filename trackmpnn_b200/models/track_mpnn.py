@@ -16,8 +16,11 @@ from .. import functional as F_
 
 
 class TrackMPNN(nn.Module):
-    def __init__(self, features, ncategories, nhidden, nattheads, msg_type, return_attention=True):
+    def __init__(self, features, ncategories, nhidden, nattheads, msg_type, return_attention=True,
+                 use_tensor_cores='auto'):
         super().__init__()
+        # 'auto': tcgen05 kernel for large graphs with msg_type 'diff', fp32 FMA kernel otherwise
+        self.use_tensor_cores = use_tensor_cores
         self.input_transforms = nn.ModuleList([])
         self.factor_grus = nn.ModuleList([])
         self.feature_idx = []
