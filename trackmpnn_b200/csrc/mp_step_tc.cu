@@ -9,15 +9,26 @@
 // relative), which keeps the result at fp32-reordering level (measured ~2e-6 max-abs vs the
 // reference, tolerance 1e-4) at 1.5x the tensor time of a single TF32 pass.
 //
-// One persistent CTA per SM, 288 threads, warp specialised:
-//   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld 32x32b, thread == row), gates, h', head
-//   warps 4-7  producers: gather h[src], h[dst], h[row] (128-bit loads), subtract, split to fp16
-//              hi/lo, store into the 128B-swizzled K-major UMMA layout
-//   warp  8    TMEM allocation + single-thread MMA issue (36 tcgen05.mma per 128-row tile)
+// One persistent CTA per SM, 512 threads (128 registers each), warp specialised:
+//   warps 0-7   epilogue: TMEM -> registers (tcgen05.ld 32x32b, thread == row; warp w owns TMEM
+//               lane quadrant w & 3 and the 32-column half w >> 2 of every gate), previous state
+//               from the stage's fp16 hi/lo images, gates, h', head; h' goes through a swizzled
+//               per-warp transpose buffer (the stage's h images, dead once read) so
+//               that global stores are full 128 B lines
+//   warps 8-15  producers: 16 lanes per row, float4 each (full-line loads): gather h[src], h[dst],
+//               h[row], subtract, split to fp16 hi/lo, store into the 128B-swizzled K-major UMMA
+//               layout.  Software pipelined in registers: the tile's src/dst and its own rows are
+//               loaded one tile ahead (HBM latency), the endpoint gathers one round ahead (L2 hits)
+//               The 36 tcgen05.mma of tile k are issued by lane 0 of producer warp k mod 8 once
+//               all producers have arrived (rotating the issuer keeps the producer warps balanced
+//               and the CTA at 16 warps, i.e. 128 registers per thread for the register pipeline)
 // Shared memory (227 KB): packed weights as fp16 hi/lo UMMA images (96 KB, resident for the whole
 // kernel) + two A stages of [128 x (64 x | 64 h)] fp16 hi/lo (2 x 64 KB).  TMEM: two accumulator
 // stages of 256 columns (r | z | i_n | h_n).  mbarriers: full[2] (producers -> MMA),
-// done[2] (tcgen05.commit -> epilogue), free[2] (epilogue -> producers / MMA).
+// done[2] (tcgen05.commit -> epilogue), xfree[2] (tcgen05.commit -> producers: the stage's x images
+// are reusable), hfree[2] (epilogue -> producers: the stage's h images, which the epilogue reads the
+// previous state from and then re-uses as its transpose buffer, are reusable),
+// tfree[2] (epilogue -> MMA: accumulator stage drained).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -26,20 +37,23 @@ namespace {
 
 constexpr int H = TMPNN_HIDDEN;
 constexpr int TCM = 128;            // rows per tile == UMMA M
-constexpr int TC_THREADS = 288;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
+constexpr int TC_THREADS = 32 * (EPI_WARPS + PROD_WARPS);  // 512 -> 128 registers per thread
 constexpr int B_BYTES = 192 * 128;  // one [192 x 64] fp16 weight image
 constexpr int OFF_BX_HI = 0, OFF_BX_LO = B_BYTES, OFF_BH_HI = 2 * B_BYTES, OFF_BH_LO = 3 * B_BYTES;
-constexpr int OFF_BIAS = 4 * B_BYTES;            // 4 x 64 floats
+constexpr int OFF_BIAS = 4 * B_BYTES;            // 4 x 64 floats: -log2e (b_ir+b_hr), -log2e (b_iz+b_hz), b_in, b_hn
 constexpr int OFF_HEADW = OFF_BIAS + 1024;       // 64 floats
 constexpr int OFF_HEADB = OFF_HEADW + 256;       // 1 float (+ pad)
 constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // what tmpnn_pack_gru_tc writes
-constexpr int OFF_BAR = IMAGE_BYTES;             // 6 mbarriers + tmem pointer, inside the alignment gap
+constexpr int OFF_BAR = IMAGE_BYTES;             // 10 mbarriers + tmem pointer, inside the alignment gap
+constexpr int OFF_DOT = OFF_BAR + 96;            // 128 floats: head partial sums of the upper column half
 constexpr int OFF_A = 98 * 1024;                 // first A stage (1024-aligned)
 constexpr int A_PART = TCM * 128;                // [128 rows x 64 fp16] = 16 KB
 constexpr int A_STAGE = 4 * A_PART;              // x_hi, x_lo, h_hi, h_lo
 constexpr int SMEM_BYTES = OFF_A + 2 * A_STAGE + 1024;  // + slack to 1024-align the base
-static_assert(OFF_BAR + 64 <= OFF_A, "barriers must fit in the gap");
+static_assert(OFF_DOT + 512 <= OFF_A, "barriers and head partials must fit in the gap");
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- PTX helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,15 +81,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 // Bounded wait: a protocol bug must never hang the GPU -- after 2 s the kernel flags an error
-// and runs to completion with garbage instead.
+// and runs to completion with garbage instead.  Failed polls back off with nanosleep so that a
+// waiting role does not steal issue slots from the roles doing work on the same SM sub-partition.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = globaltimer_ns();
   uint32_t spin = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spin & 255u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
-      atomicOr(status, TMPNN_FLAG_TC_TIMEOUT);
-      return;
+    __nanosleep(40);
+    if ((++spin & 1023u) == 0) {
+      const unsigned long long t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) {
+        atomicOr(status, TMPNN_FLAG_TC_TIMEOUT);
+        return;
+      }
     }
   }
 }
@@ -126,23 +146,85 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__device__ __forceinline__ void split8(const float* a, uint4& hi, uint4& lo, float& amax) {
-  __half2 h2[4], l2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a0 = a[2 * i], a1 = a[2 * i + 1];
-    amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
-    const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-    h2[i] = __halves2half2(h0, h1);
-    l2[i] = __halves2half2(__float2half_rn(a0 - __half2float(h0)), __float2half_rn(a1 - __half2float(h1)));
-  }
-  hi = *reinterpret_cast<uint4*>(h2);
-  lo = *reinterpret_cast<uint4*>(l2);
+// 4 floats -> 4 fp16 "hi" (round to nearest) + 4 fp16 "lo" (the residual)
+__device__ __forceinline__ void split4(const float4 a, uint2& hi, uint2& lo, float& amax) {
+  amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+  const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(a.x - f01.x, a.y - f01.y), l23 = __floats2half2_rn(a.z - f23.x, a.w - f23.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
-// sigmoid / tanh from ex2.approx + rcp.approx: ~1e-6 relative, far inside the 1e-4 tolerance
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): halves the issue slots of the gate math
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
+  float a, b;
+  up2(v, a, b);
+  return pk2(ex2_approx(a), ex2_approx(b));
+}
+__device__ __forceinline__ f32x2 rcp_2(f32x2 v) {
+  float a, b;
+  up2(v, a, b);
+  return pk2(rcp_approx(a), rcp_approx(b));
+}
+__device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// first sequence whose tile range contains `tile`, advancing a cursor (tiles are visited in
+// increasing order, so this is 0-1 steps per call after the first)
+__device__ __forceinline__ void seek_seq(const int32_t* __restrict__ tile_ptr, int num_seqs, int tile, int& seq) {
+  while (seq + 1 < num_seqs && __ldg(tile_ptr + seq + 1) <= tile) ++seq;
+}
 
 // ---- weight image ----------------------------------------------------------------------------
 __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
@@ -162,7 +244,7 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
   float* bias = reinterpret_cast<float*>(img + OFF_BIAS);
   for (int i = tid; i < 4 * H; i += nth) {
     const int g = i / H, j = i % H;
-    bias[i] = g < 2 ? b_ih[g * H + j] + b_hh[g * H + j] : g == 2 ? b_ih[2 * H + j] : b_hh[2 * H + j];
+    bias[i] = g < 2 ? -LOG2E * (b_ih[g * H + j] + b_hh[g * H + j]) : g == 2 ? b_ih[2 * H + j] : b_hh[2 * H + j];
   }
   float* hw = reinterpret_cast<float*>(img + OFF_HEADW);
   for (int i = tid; i < H; i += nth) hw[i] = head_w[i];
@@ -170,6 +252,35 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
     float* hb = reinterpret_cast<float*>(img + OFF_HEADB);
     hb[0] = head_b[0]; hb[1] = hb[2] = hb[3] = 0.f;
   }
+}
+
+// ---- MMA issue for one 128-row tile (one thread) ------------------------------------------------
+__device__ __forceinline__ void issue_tile_mma(uint32_t sm_u, uint32_t tmem_base, int stage) {
+  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
+  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+  // x part: columns [0,192) = r | z | i_n
+  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
+  const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192), acc);
+      acc = 1;
+    }
+  // h part: columns [0,128) += r | z, columns [192,256) = h_n
+  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
+  const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
+  uint32_t acc_n = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
+      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
+      acc_n = 1;
+    }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
@@ -185,8 +296,9 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = sm_u + OFF_BAR, bar_done = bar_full + 16, bar_free = bar_full + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 48);
+  const uint32_t bar_full = sm_u + OFF_BAR, bar_done = bar_full + 16, bar_xfree = bar_full + 32, bar_hfree = bar_full + 48,
+                 bar_tfree = bar_full + 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 80);
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
   {
@@ -196,13 +308,15 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, 4);  // one arrive per producer warp
-      mbar_init(bar_done + 8 * s, 1);  // tcgen05.commit
-      mbar_init(bar_free + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(bar_full + 8 * s, PROD_WARPS);  // one arrive per producer warp
+      mbar_init(bar_done + 8 * s, 1);           // tcgen05.commit
+      mbar_init(bar_xfree + 8 * s, 1);          // tcgen05.commit: the x images are dead once the MMAs retired
+      mbar_init(bar_hfree + 8 * s, EPI_WARPS);  // one arrive per epilogue warp: h images / transpose buffer released
+      mbar_init(bar_tfree + 8 * s, EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -211,170 +325,226 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int stride = gridDim.x;
 
-  const float* bias = reinterpret_cast<const float*>(sm + OFF_BIAS);
-  const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
-  const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
-
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-    unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
-
-    if (warp == 8) {
-      // ================= MMA issuer =================
-      if (lane == 0) {
-        mbar_wait(bar_free + 8 * stage, phase ^ 1u, status);  // accumulator stage drained
-        mbar_wait(bar_full + 8 * stage, phase, status);       // operands landed
-        tc_fence_after();
-        const uint32_t a_u = smem_u32(a_stage);
-        const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-        // x part: columns [0,192) = r | z | i_n
-        const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
-        const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
-        uint32_t acc = 0;
+  if (warp >= EPI_WARPS) {
+    // ================= producers =================
+    const int pt = threadIdx.x - 32 * EPI_WARPS;
+    const int g = pt >> 4, l = pt & 15, gl0 = lane & 16;  // row group (rows g + 16 p), float4 within the row
+    const uint32_t FULL = 0xffffffffu;
+    // all addressing in units of float4 from h_in: (global row) * ldh4 + col4 + l fits 32 bits
+    // (S * cap_rows * ldh / 4 < 2^32 is checked on the host)
+    const float4* __restrict__ h4p = reinterpret_cast<const float4*>(h_in);
+    const uint32_t ldh4 = (uint32_t)ldh >> 2, cl4 = ((uint32_t)col >> 2) + (uint32_t)l;
+    // lane l < 8 of a group keeps src of row g + 16 l, lane l >= 8 keeps dst of row g + 16 (l - 8)
+    const int32_t* __restrict__ idx_arr = l < 8 ? src : dst;
+    const int idx_row = g + 16 * (l & 7);
+    int seq = 0;
+    seek_seq(tile_ptr, num_seqs, blockIdx.x, seq);
+    uint32_t base = (uint32_t)seq * (uint32_t)cap_rows;                 // first global row of the slab
+    int r0 = (blockIdx.x - __ldg(tile_ptr + seq)) * TCM;                 // first slab row of the tile
+    int nleft = __ldg(n_rows + seq) - r0;                                // rows of the slab from r0 on
+    int idxv = idx_row < nleft ? __ldg(idx_arr + base + r0 + idx_row) : -1;
+    // Every load below is unconditional with a clamped (always valid) address: a predicated load
+    // is compiled as load + predicated move, and the move would wait for the load right away,
+    // which defeats the register pipeline.
+    float4 own[8];
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+    for (int p = 0; p < 8; ++p) own[p] = __ldg(h4p + (base + r0 + min(g + 16 * p, nleft - 1)) * ldh4 + cl4);
+    float4 gs[2][2], gd[2][2];
+    auto gather = [&](int buf, int round, uint32_t gbase, int iv) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192), acc);
-            acc = 1;
-          }
-        // h part: columns [0,128) += r | z, columns [192,256) = h_n
-        const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
-        const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
-        uint32_t acc_n = 0;
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
-            umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
-            acc_n = 1;
-          }
-        umma_commit(bar_done + 8 * stage);  // implies tcgen05.fence::before_thread_sync
+      for (int u = 0; u < 2; ++u) {
+        const int p = 2 * round + u;
+        const int a = __shfl_sync(FULL, iv, gl0 + p), b = __shfl_sync(FULL, iv, gl0 + 8 + p);
+        gs[buf][u] = __ldg(h4p + (gbase + (uint32_t)max(a, 0)) * ldh4 + cl4);
+        gd[buf][u] = __ldg(h4p + (gbase + (uint32_t)max(b, 0)) * ldh4 + cl4);
       }
-      __syncwarp();
-      continue;
-    }
-
-    // tile -> (sequence, first row); tile_ptr counts 128-row tiles per sequence
-    int lo = 0, hi = num_seqs;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (tile_ptr[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const int seq = lo;
-    const int r0 = (tile - tile_ptr[seq]) * TCM;
-    const int n = n_rows[seq];
-    const size_t base = (size_t)seq * cap_rows;
-
-    if (warp >= 4) {
-      // ================= producers =================
-      mbar_wait(bar_free + 8 * stage, phase ^ 1u, status);  // epilogue is done with this stage (h_prev lives here)
-      const int pt = threadIdx.x - 128, q = pt & 7, rsub = pt >> 3;
+    };
+    gather(0, 0, base, idxv);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+      unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+      // next tile (or this one again when it is the last: the loads are then simply unused)
+      uint32_t nbase = base;
+      int nr0 = r0, nnleft = nleft, nidx = -1;
+      if (tile + stride < total) {
+        seek_seq(tile_ptr, num_seqs, tile + stride, seq);
+        nbase = (uint32_t)seq * (uint32_t)cap_rows;
+        nr0 = (tile + stride - __ldg(tile_ptr + seq)) * TCM;
+        nnleft = __ldg(n_rows + seq) - nr0;
+        nidx = __ldg(idx_arr + nbase + nr0 + min(idx_row, nnleft - 1));  // in flight for the whole tile
+        if (idx_row >= nnleft) nidx = -1;
+      }
+      const uint32_t nown0 = (nbase + nr0) * ldh4 + cl4;
       float amax = 0.f;
-#pragma unroll 2
-      for (int p = 0; p < TCM / 16; ++p) {
-        const int r = rsub + 16 * p;
-        const int lr = r0 + r;
-        int a = -1, b = -1;
-        if (lr < n) { a = src[base + lr]; b = dst[base + lr]; }
-        float x[8], hp[8];
-        if (a >= 0) {
-          const float* ps = h_in + (base + a) * ldh + col + 8 * q;
-          const float* pd = h_in + (base + b) * ldh + col + 8 * q;
-          const float* pr = h_in + (base + lr) * ldh + col + 8 * q;
-          const float4 s0 = ldg4(ps), s1 = ldg4(ps + 4), d0 = ldg4(pd), d1 = ldg4(pd + 4);
-          const float4 h0 = ldg4(pr), h1 = ldg4(pr + 4);
-          x[0] = s0.x - d0.x; x[1] = s0.y - d0.y; x[2] = s0.z - d0.z; x[3] = s0.w - d0.w;
-          x[4] = s1.x - d1.x; x[5] = s1.y - d1.y; x[6] = s1.z - d1.z; x[7] = s1.w - d1.w;
-          hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w;
-          hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
-        } else {
+      // x images first: they are free as soon as the previous tile of this stage left the tensor core
+      mbar_wait(bar_xfree + 8 * stage, phase ^ 1u, status);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { x[i] = 0.f; hp[i] = 0.f; }
+      for (int round = 0; round < 4; ++round) {
+        // endpoint rows of the following round (or of round 0 of the next tile): L2 hits, one round ahead
+        if (round < 3) gather((round + 1) & 1, round + 1, base, idxv);
+        else gather(0, 0, nbase, nidx);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = 2 * round + u;
+          // rows that are not edge rows (detections inside the tile, rows past the end of the slab) carry
+          // real, finite h values from the clamped addresses; their results are masked by the epilogue
+          const float4 s4 = gs[round & 1][u], d4 = gd[round & 1][u];
+          const float4 x4 = make_float4(s4.x - d4.x, s4.y - d4.y, s4.z - d4.z, s4.w - d4.w);
+          uint2 xh, xl;
+          split4(x4, xh, xl, amax);
+          const uint32_t off = sw128(g + 16 * p, l >> 1) + ((l & 1) << 3);
+          *reinterpret_cast<uint2*>(a_stage + off) = xh;
+          *reinterpret_cast<uint2*>(a_stage + A_PART + off) = xl;
         }
-        uint4 xh, xl, hh, hl;
-        split8(x, xh, xl, amax);
-        split8(hp, hh, hl, amax);
-        const uint32_t off = sw128(r, q);
-        *reinterpret_cast<uint4*>(a_stage + off) = xh;
-        *reinterpret_cast<uint4*>(a_stage + A_PART + off) = xl;
-        *reinterpret_cast<uint4*>(a_stage + 2 * A_PART + off) = hh;
-        *reinterpret_cast<uint4*>(a_stage + 3 * A_PART + off) = hl;
+      }
+      // h images: released by the epilogue of the previous tile of this stage
+      mbar_wait(bar_hfree + 8 * stage, phase ^ 1u, status);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const float4 h4 = own[p];
+        // this row's slot of the next tile: HBM latency, one tile ahead
+        own[p] = __ldg(h4p + nown0 + (uint32_t)min(g + 16 * p, nnleft - 1) * ldh4);
+        uint2 hh, hl;
+        split4(h4, hh, hl, amax);
+        const uint32_t off = sw128(g + 16 * p, l >> 1) + ((l & 1) << 3);
+        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh;
+        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl;
       }
       if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-    } else {
-      // ================= epilogue =================
-      const int r = threadIdx.x;  // row of the tile == TMEM lane
-      const int lr = r0 + r;
-      const bool valid = lr < n && src[base + lr] >= 0;
-      const size_t row = base + lr;
-      mbar_wait(bar_done + 8 * stage, phase, status);
-      tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(stage * 256);
-      float dot = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        float ar[16], az[16], an[16], ahn[16];
-        tmem_ld16(t0 + ch * 16, ar);
-        tmem_ld16(t0 + 64 + ch * 16, az);
-        tmem_ld16(t0 + 128 + ch * 16, an);
-        tmem_ld16(t0 + 192 + ch * 16, ahn);
-        // h_prev = h_hi + h_lo from the stage's h images
-        float hp[16];
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          const uint32_t off = sw128(r, 2 * ch + c2);
-          const uint4 vh = *reinterpret_cast<const uint4*>(a_stage + 2 * A_PART + off);
-          const uint4 vl = *reinterpret_cast<const uint4*>(a_stage + 3 * A_PART + off);
-          const __half2* ph = reinterpret_cast<const __half2*>(&vh);
-          const __half2* pl = reinterpret_cast<const __half2*>(&vl);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
-            hp[8 * c2 + 2 * i] = fh.x + fl.x;
-            hp[8 * c2 + 2 * i + 1] = fh.y + fl.y;
-          }
-        }
-        tmem_ld_wait();
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = ch * 16 + i;
-          const float rg = fast_sigmoid(ar[i] + bias[j]);
-          const float zg = fast_sigmoid(az[i] + bias[H + j]);
-          const float ng = fast_tanh(an[i] + bias[2 * H + j] + rg * (ahn[i] + bias[3 * H + j]));
-          o[i] = (1.0f - zg) * ng + zg * hp[i];
-          dot = fmaf(o[i], headw[j], dot);
-        }
-        if (valid) {
-          float4* po = reinterpret_cast<float4*>(h_out + row * ldh + col + ch * 16);
-          po[0] = make_float4(o[0], o[1], o[2], o[3]);
-          po[1] = make_float4(o[4], o[5], o[6], o[7]);
-          po[2] = make_float4(o[8], o[9], o[10], o[11]);
-          po[3] = make_float4(o[12], o[13], o[14], o[15]);
+      if (lane == 0) {
+        mbar_arrive(bar_full + 8 * stage);
+        if (warp - EPI_WARPS == (it & (PROD_WARPS - 1))) {  // this tile's MMA issuer
+          mbar_wait(bar_tfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained
+          mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows
+          tc_fence_after();
+          issue_tile_mma(sm_u, tmem_base, stage);
+          umma_commit(bar_xfree + 8 * stage);  // x images reusable once these MMAs retire
+          umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
         }
       }
-      if (valid) {
-        const float lg = dot + (first_group ? headb : logit[row]);
-        logit[row] = lg;
-        if (last_group) score[row] = tmpnn_sigmoid(lg);
+      __syncwarp();
+      base = nbase; r0 = nr0; nleft = nnleft; idxv = nidx;
+    }
+  } else {
+    // ================= epilogue =================
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;  // row of the tile == TMEM lane
+    const int c0 = 32 * half;        // this warp's columns of every gate: [c0, c0 + 32)
+    const float* bias = reinterpret_cast<const float*>(sm + OFF_BIAS);
+    const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
+    const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
+    float* dot_part = reinterpret_cast<float*>(sm + OFF_DOT);
+    const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
+    const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+    int seq = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+      unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+      seek_seq(tile_ptr, num_seqs, tile, seq);
+      const int lr = (tile - __ldg(tile_ptr + seq)) * TCM + r;
+      const size_t row = (size_t)seq * cap_rows + lr;
+      const bool valid = lr < __ldg(n_rows + seq) && __ldg(src + row) >= 0;
+      mbar_wait(bar_done + 8 * stage, phase, status);
+      tc_fence_after();
+      // previous state of this row's 32 columns = hi + lo of the stage's h images; once every epilogue
+      // warp holds its part in registers the A stage goes back to the producers (before the gate math)
+      f32x2 hp[16];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint32_t off = sw128(r, 4 * half + ch);
+        const uint4 vh = *reinterpret_cast<const uint4*>(a_stage + 2 * A_PART + off);
+        const uint4 vl = *reinterpret_cast<const uint4*>(a_stage + 3 * A_PART + off);
+        const __half2* ph = reinterpret_cast<const __half2*>(&vh);
+        const __half2* pl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
+          hp[4 * ch + i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
+        }
+      }
+      // the pair of warps sharing this row quadrant has read both h images of its rows: from here on
+      // they are this warp's transpose buffer ([32 rows x 32 floats], 16 B chunks XOR-swizzled by row)
+      named_bar_sync(1 + quad, 64);
+      unsigned char* tbuf = a_stage + 2 * A_PART + warp * 4096;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
+      f32x2 dot2 = 0ull;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t ar[8], az[8], an[8], ahn[8];
+        tmem_ld8u(t0 + ch * 8, ar);
+        tmem_ld8u(t0 + 64 + ch * 8, az);
+        tmem_ld8u(t0 + 128 + ch * 8, an);
+        tmem_ld8u(t0 + 192 + ch * 8, ahn);
+        tmem_ld_wait();
+        const int j0 = c0 + ch * 8;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(bias + j0 + 4 * v);
+          const ulonglong2 bz = *reinterpret_cast<const ulonglong2*>(bias + H + j0 + 4 * v);
+          const ulonglong2 bi = *reinterpret_cast<const ulonglong2*>(bias + 2 * H + j0 + 4 * v);
+          const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
+          const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
+          f32x2 o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 4 * v + 2 * e;  // columns j0 + i, j0 + i + 1
+            // r, z = 1 / (1 + 2^(-log2e (acc + b)))   (2^x -> inf gives exactly 0, no clamp needed)
+            const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(ar[i], ar[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
+            const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(az[i], az[i + 1]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
+            // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + b_in + r (h_n + b_hn)
+            const f32x2 u = fma2(rg, add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), add2(pk2u(an[i], an[i + 1]), e ? bi.y : bi.x));
+            const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
+            const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[4 * ch + 2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
+            o[e] = ov;
+            dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+          }
+          *reinterpret_cast<ulonglong2*>(tbuf + lane * 128 + (((2 * ch + v) ^ (lane & 7)) << 4)) = make_ulonglong2(o[0], o[1]);
+        }
+      }
+      float dot;
+      {
+        float d0, d1;
+        up2(dot2, d0, d1);
+        dot = d0 + d1;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free + 8 * stage);
+      if (lane == 0) mbar_arrive(bar_tfree + 8 * stage);  // accumulator stage drained
+      // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
+      {
+        float* out0 = h_out + (row - lane) * ldh + col + c0;  // first row of this warp's quadrant
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = 4 * k + (lane >> 3), cc = lane & 7;
+          const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // the h images may be refilled
+      // head: the two column halves of a row live in warps quad and quad + 4
+      if (half == 1) dot_part[r] = dot;
+      named_bar_sync(1 + quad, 64);
+      if (half == 0 && valid) {
+        const float lg = dot + dot_part[r] + (first_group ? headb : logit[row]);
+        logit[row] = lg;
+        if (last_group) score[row] = tmpnn_sigmoid(lg);
+      }
+      named_bar_sync(1 + quad, 64);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
