@@ -375,8 +375,8 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         nbase = (uint32_t)seq * (uint32_t)cap_rows;
         nr0 = (tile + stride - __ldg(tile_ptr + seq)) * TCM;
         nnleft = __ldg(n_rows + seq) - nr0;
-        nidx = __ldg(idx_arr + nbase + nr0 + min(idx_row, nnleft - 1));  // in flight for the whole tile
-        if (idx_row >= nnleft) nidx = -1;
+        // in flight for the whole tile; rows past the end of the slab repeat its last row (masked by the epilogue)
+        nidx = __ldg(idx_arr + nbase + nr0 + min(idx_row, nnleft - 1));
       }
       const uint32_t nown0 = (nbase + nr0) * ldh4 + cl4;
       float amax = 0.f;
@@ -442,15 +442,26 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     float* dot_part = reinterpret_cast<float*>(sm + OFF_DOT);
     const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+    // this row's coordinates and its "is an edge row" flag are fetched one tile ahead
     int seq = 0, it = 0;
+    seek_seq(tile_ptr, num_seqs, blockIdx.x, seq);
+    int lr = ((int)blockIdx.x - __ldg(tile_ptr + seq)) * TCM + r;
+    size_t row = (size_t)seq * cap_rows + lr;
+    int nrem = __ldg(n_rows + seq) - lr;                       // > 0 iff the row exists
+    int srcv = __ldg(src + (nrem > 0 ? row : row - lr));       // clamped to the slab's first row
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
       const int stage = it & 1;
       const uint32_t phase = (uint32_t)(it >> 1) & 1u;
       unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
-      seek_seq(tile_ptr, num_seqs, tile, seq);
-      const int lr = (tile - __ldg(tile_ptr + seq)) * TCM + r;
-      const size_t row = (size_t)seq * cap_rows + lr;
-      const bool valid = lr < __ldg(n_rows + seq) && __ldg(src + row) >= 0;
+      const size_t row_cur = row;
+      const int nrem_cur = nrem, src_cur = srcv;
+      if (tile + stride < total) {
+        seek_seq(tile_ptr, num_seqs, tile + stride, seq);
+        lr = (tile + stride - __ldg(tile_ptr + seq)) * TCM + r;
+        row = (size_t)seq * cap_rows + lr;
+        nrem = __ldg(n_rows + seq) - lr;
+        srcv = __ldg(src + (nrem > 0 ? row : row - lr));
+      }
       mbar_wait(bar_done + 8 * stage, phase, status);
       tc_fence_after();
       // previous state of this row's 32 columns = hi + lo of the stage's h images; once every epilogue
@@ -472,6 +483,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       // the pair of warps sharing this row quadrant has read both h images of its rows: from here on
       // they are this warp's transpose buffer ([32 rows x 32 floats], 16 B chunks XOR-swizzled by row)
       named_bar_sync(1 + quad, 64);
+      const bool valid = nrem_cur > 0 && src_cur >= 0;
       unsigned char* tbuf = a_stage + 2 * A_PART + warp * 4096;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
@@ -520,7 +532,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       if (lane == 0) mbar_arrive(bar_tfree + 8 * stage);  // accumulator stage drained
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
       {
-        float* out0 = h_out + (row - lane) * ldh + col + c0;  // first row of this warp's quadrant
+        float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rr = 4 * k + (lane >> 3), cc = lane & 7;
@@ -534,9 +546,9 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       if (half == 1) dot_part[r] = dot;
       named_bar_sync(1 + quad, 64);
       if (half == 0 && valid) {
-        const float lg = dot + dot_part[r] + (first_group ? headb : logit[row]);
-        logit[row] = lg;
-        if (last_group) score[row] = tmpnn_sigmoid(lg);
+        const float lg = dot + dot_part[r] + (first_group ? headb : logit[row_cur]);
+        logit[row_cur] = lg;
+        if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
       }
       named_bar_sync(1 + quad, 64);
     }
