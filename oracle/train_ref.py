@@ -133,7 +133,8 @@ def train_chunk(params, X, y, features='2d', ncategories=3, msg_type='diff', tp_
     graphs, all_logits, all_h = [], [], []
     for t_cur in [None] + list(range(t_st, t_end)):
         if t_cur is not None:
-            g, feats = O.update_graph(g, None, X, y, t_cur, mode='train')
+            # teacher forcing: the graph growth does not read the scores (utils/graph.py:229-245, 271-274)
+            g, feats = O.update_graph(g, np.zeros((g.n, 2), np.float32), X, y, t_cur, mode='train')
         scores, logits, h = forward_train(p, torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float32)), h, g,
                                           groups, msg_type)
         lc, lf, _ = step_losses(scores, logits, g, tp_classifier)

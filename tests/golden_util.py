@@ -52,3 +52,16 @@ def assert_graph_equal(a, b, what=''):
         np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f'{what}: {f}')
     if a.label is not None and b.label is not None:
         np.testing.assert_array_equal(a.label, b.label, err_msg=f'{what}: label')
+
+
+def assert_grads_close(got, gold, rel=2e-3):
+    """Parameter gradients of a BPTT chunk against the reference's (``g/<name>`` in a train fixture).
+    Per parameter: max-abs error <= rel * max|want| + 1e-6 * (largest gradient entry of the model); the
+    second term covers gradients that are analytically zero (the Linear bias in front of a train-mode
+    BatchNorm) and hold nothing but round-off in the reference too."""
+    names = [k[2:] for k in gold.z.files if k.startswith('g/')]
+    gmax = max(float(np.abs(gold.z['g/' + k]).max()) for k in names)
+    for k in names:
+        want = gold.z['g/' + k]
+        atol = rel * float(np.abs(want).max()) + 1e-6 * gmax + 1e-9
+        np.testing.assert_allclose(np.asarray(got[k]).reshape(want.shape), want, atol=atol, rtol=0, err_msg=k)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import trackmpnn_oracle as O
-from golden_util import Golden, golden_names, assert_graph_equal
+from golden_util import Golden, golden_names, assert_graph_equal, assert_grads_close
 
 TOL = 1e-4
 
@@ -147,3 +147,17 @@ def test_train_chunk(name):
     for k in gold.z.files:
         if k.startswith('w_after/') and 'num_batches' not in k:
             np.testing.assert_allclose(params[k[len('w_after/'):]], gold.z[k], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', golden_names('train'))
+def test_train_gradients(name):
+    """oracle/train_ref.py (edge-list forward in torch fp32 + autograd) against the reference's own
+    loss.backward(): loss and every parameter gradient of a BPTT chunk."""
+    from oracle import train_ref as T
+    gold = Golden(name)
+    m = gold.meta
+    out = T.train_chunk(gold.params(), gold.X, gold.y, features=m['features'], ncategories=m['ncategories'],
+                        msg_type=m['msg_type'], tp_classifier=m['tp_classifier'])
+    np.testing.assert_allclose(out['loss'], float(gold.z['loss']), rtol=1e-4)
+    assert len(out['graphs']) == gold.n_steps
+    assert_grads_close(out['grads'], gold)
