@@ -182,6 +182,68 @@ int tmpnn_pack_gru_tc(const float *w_ih, const float *w_hh, const float *b_ih, c
 int tmpnn_mp_edge_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                          int group, int num_groups, const void *edge_image, void *stream);
 
+/* ---- training: backward of the step and the losses (train.py:65-134, models/loss.py) ------- */
+
+/* tmpnn_mp_step_fwd that also stores, per row, r | z | n | (W_hn h + b_hn) of feature group `group`
+ * into gates[row][4][64] -- what loss.backward() needs from torch.nn.GRUCell (models/layers.py:97,114). */
+int tmpnn_mp_step_fwd_train(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                            int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
+                            float *agg, float *gates, void *stream);
+
+/* Gate gradients of one feature group for every row of a single-slab graph (row type from src):
+ * dh' = dh_out (nullable) + (dlogits + dscores p (1-p)) w_type;  dgi = [dpr,dpz,dpn], dgh = [dpr,dpz,dpn r]
+ * ([n][192] each), dhself = dh' z ([n][64]).  Accumulates (atomically) the bias gradients of both cells
+ * (gbias_*: [2][192] = d bias_ih | d bias_hh), the 64-wide head weight slices and, when the pointers are
+ * non-null (pass them for group 0 only), the head biases. */
+int tmpnn_gate_bwd(int n_rows, const int32_t *src, const float *gates, const float *h_prev, const float *h_new,
+                   int ldh, int col, const float *dh_out, const float *dlogits, const float *dscores,
+                   const float *score, const float *head_w_edge, const float *head_w_node, float *dgi, float *dgh,
+                   float *dhself, float *gbias_edge, float *gbias_node, float *ghw_edge, float *ghw_node,
+                   float *ghb_edge, float *ghb_node, void *stream);
+
+/* C[rc(i)][0:n] (+)= A[ra(i)][0:192] . W[192][n] for rows i < R (R = *r_dev or r_host) whose
+ * mask[ra(i)] >= 0; ra = a_rows ? a_rows[i] : i, rc likewise.  n = 64 or 128.  (dx = dgi . W_ih,
+ * dh_self += dgh . W_hh with the torch.nn.GRUCell weight layouts [192][n].) */
+int tmpnn_rows_times_w(const int32_t *r_dev, int r_host, const int32_t *a_rows, const int32_t *c_rows,
+                       const int32_t *mask, const float *A, const float *W, int n, float *C, int ldc,
+                       int accumulate, void *stream);
+
+/* G[192][n] += sum_i A[ra(i)][0:192]^T B[rb(i)][0:n]  (weight gradients dW_ih += dgi^T x, dW_hh += dgh^T h). */
+int tmpnn_rows_outer(const int32_t *r_dev, int r_host, const int32_t *a_rows, const int32_t *b_rows,
+                     const int32_t *mask, const float *A, const float *B, int ldb, int n, float *G, void *stream);
+
+/* Transpose of the gather / segmented sum (models/layers.py:90-95,103) in gather form:
+ * edge row e: dh_in[e] = dhself[e] + dagg[det(src)] - dagg[det(dst)];
+ * detection d: dh_in[d] = dhself[d] + sum over its future edges of dx[e][0:64] -/+ sum over its past edges of
+ * dx[e][0:64] (diff) / dx[e][64:128] (concat).  dagg is indexed by detection-list position. */
+int tmpnn_scatter_bwd(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, const float *dhself, const float *dx,
+                      int kx, const float *dagg, float *dh_in, int ldh, int col, void *stream);
+
+/* Backward of Linear -> BatchNorm1d -> ReLU -> Linear (models/track_mpnn.py:45-52) on the n new detection
+ * rows of a step; `a`, mean, var are what the forward produced (batch statistics over n + n_edge_rows rows
+ * when training).  dh rows are dh[out_rows[i]][col:col+64].  Gradients are added
+ * to gw1[64][f_in], gb1, ggamma, gbeta, gw2[64][64], gb2.  scratch: 2 n 64 floats. */
+int tmpnn_input_bwd(const float *x, int ldx, int col0, int f_in, const int32_t *x_idx, const float *a,
+                    const float *mean, const float *var, const float *gamma, const float *beta, const float *b1,
+                    const float *w2, const float *dh, int ldh, int col, const int32_t *out_rows, int n,
+                    int n_edge_rows, int training, float *scratch, float *gw1, float *gb1, float *ggamma,
+                    float *gbeta, float *gw2, float *gb2, void *stream);
+
+/* create_targets (models/loss.py:8-44) on a single-slab graph with labels: targets[N] int32. */
+int tmpnn_loss_targets(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, int32_t *targets, void *stream);
+
+/* CELoss (models/loss.py:81-115): per detection and per past / future incidence segment holding a positive
+ * target, (logsumexp(logit[segment]) - logit[chosen positive]) / len.  seg_* have 2 cap_dets entries and
+ * are what tmpnn_loss_ce_bwd needs; loss[0] = the sum (deterministic order). */
+int tmpnn_loss_ce_fwd(const tmpnn_index *ix, int n_rows, const int32_t *targets, const float *logit, float *seg_lse,
+                      int32_t *seg_pos, float *seg_loss, float *loss, void *stream);
+int tmpnn_loss_ce_bwd(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, const float *seg_lse,
+                      const int32_t *seg_pos, const float *logit, const float *grad_out, float *dlogit, void *stream);
+
+/* FocalLoss(gamma=0, alpha=None, size_average=True) (models/loss.py:57-74): mean(-log(p_t + 1e-10)). */
+int tmpnn_loss_focal_fwd(int n, const float *p, const int64_t *targets, float *per_elem, float *loss, void *stream);
+int tmpnn_loss_focal_bwd(int n, const float *p, const int64_t *targets, const float *grad_out, float *dp, void *stream);
+
 /* ---- graph bookkeeping (utils/graph.py) ------------------------------------------------ */
 
 /* y_pred[N,3] int64 <-> ts/det/ass, scores[N,2] -> p, labels int64 -> int32 for ONE slab. */

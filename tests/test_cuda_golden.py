@@ -147,3 +147,62 @@ def test_train_forward(name):
     for k in gold.z.files:
         if k.startswith('w_after/'):
             np.testing.assert_allclose(sd[k[len('w_after/'):]].cpu().numpy(), gold.z[k], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', golden_names('train'))
+def test_train_backward(name):
+    """One BPTT chunk exactly as train.py:65-134 drives it, through the drop-in modules
+    (TrackMPNN.forward as an autograd Function, create_targets / CELoss / FocalLoss, loss.backward()):
+    targets bit-exact, per-step losses, the total loss and every parameter gradient against the
+    reference's own autograd."""
+    from golden_util import assert_grads_close
+    from trackmpnn_b200.utils.graph import initialize_graph, update_graph
+    from trackmpnn_b200.models.loss import create_targets, CELoss, FocalLoss
+    gold = Golden(name)
+    m = gold.meta
+    dev = torch.device('cuda:0')
+    model = _model(gold, dev, train=True)
+    X, y = torch.from_numpy(gold.X).to(dev), torch.from_numpy(gold.y).to(dev)
+    ce, focal_node, focal_edge = CELoss(), FocalLoss(gamma=0), FocalLoss(gamma=0)
+
+    def losses(scores, logits, y_pred, labels, node_adj, s):
+        idx_edge = torch.nonzero((y_pred[:, 0] == -1))[:, 0]
+        idx_node = torch.nonzero((y_pred[:, 0] != -1))[:, 0]
+        targets = create_targets(labels, node_adj, idx_node)
+        np.testing.assert_array_equal(targets.cpu().numpy(), gold.get(s, 'targets'), err_msg=f'targets step {s}')
+        loss_c = ce(logits, targets, node_adj, idx_node)
+        if m['tp_classifier']:
+            loss_f = focal_node(scores[idx_node, 0], targets[idx_node]) + focal_edge(scores[idx_edge, 0], targets[idx_edge])
+            scores = torch.cat((1 - scores, scores), dim=1)
+        else:
+            loss_f = focal_edge(scores[idx_edge, 0], targets[idx_edge])
+            scores = torch.cat((1 - scores, scores), dim=1)
+            scores[idx_node, 0] = 0
+            scores[idx_node, 1] = 1
+        np.testing.assert_allclose(loss_c.item(), gold.get(s, 'loss_c'), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(loss_f.item(), gold.get(s, 'loss_f'), rtol=1e-4, atol=1e-5)
+        return scores, loss_c, loss_f
+
+    y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, t_st=0, mode='train', cuda=True)
+    scores, logits, states, _ = model(feats, None, node_adj, edge_adj)
+    assert logits.requires_grad and states.requires_grad
+    s = 0
+    scores, loss_c, loss_f = losses(scores, logits, y_pred, labels, node_adj, s)
+    for t_cur in range(t_st, t_end):
+        s += 1
+        y_pred, feats, node_adj, edge_adj, labels = update_graph(
+            node_adj, labels, scores, y_pred, X, y, t_cur, use_hungraian=False, mode='train', cuda=True)
+        scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+        np.testing.assert_allclose(logits.detach().cpu().numpy(), gold.get(s, 'logits'), atol=TOL, rtol=0)
+        scores, lc, lf = losses(scores, logits, y_pred, labels, node_adj, s)
+        loss_c = loss_c + lc
+        loss_f = loss_f + lf
+    assert s + 1 == gold.n_steps
+    loss = loss_c + loss_f
+    np.testing.assert_allclose(loss.item(), float(gold.z['loss']), rtol=1e-4)
+    loss.backward()
+    got = {k: (torch.zeros_like(p) if p.grad is None else p.grad).cpu().numpy() for k, p in model.named_parameters()}
+    assert_grads_close(got, gold)
+    # an optimizer step on these gradients runs and changes the packed cells on the next forward
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
+    opt.step()

@@ -79,6 +79,17 @@ _PROTOS = {
     'tmpnn_gru_tc_pack_bytes': ([], C.c_size_t),
     'tmpnn_pack_gru_tc': ([_VP] * 8, _I),
     'tmpnn_mp_edge_fwd_tc': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP], _I),
+    'tmpnn_mp_step_fwd_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 16, _I),
+    'tmpnn_rows_times_w': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _VP], _I),
+    'tmpnn_rows_outer': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP], _I),
+    'tmpnn_scatter_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP], _I),
+    'tmpnn_input_bwd': ([_VP, _I, _I, _I] + [_VP] * 9 + [_I, _I, _VP, _I, _I, _I] + [_VP] * 8, _I),
+    'tmpnn_loss_targets': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP], _I),
+    'tmpnn_loss_ce_fwd': ([C.POINTER(Index), _I] + [_VP] * 7, _I),
+    'tmpnn_loss_ce_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I] + [_VP] * 6, _I),
+    'tmpnn_loss_focal_fwd': ([_I] + [_VP] * 5, _I),
+    'tmpnn_loss_focal_bwd': ([_I] + [_VP] * 5, _I),
     'tmpnn_ypred_unpack': ([_VP, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_ypred_pack': ([_VP, _VP, _VP, _I, _VP, _VP], _I),
     'tmpnn_coo_from_edges': ([_VP, _VP, _VP, _I, _I, _VP, _VP, C.c_int64, _VP, _VP], _I),
@@ -148,6 +159,9 @@ KERNELS_PER_CALL = {
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 2, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4,
+    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
+    'tmpnn_input_bwd': 1, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
+    'tmpnn_loss_focal_bwd': 1,
 }
 
 

@@ -333,7 +333,7 @@ __device__ __forceinline__ void load_pack(StepSmem<KX>& s, const float* __restri
 template <int KX>
 __device__ __forceinline__ void gru_tile(StepSmem<KX>& s, float* __restrict__ h_out, int ldh, int col,
                                          float* __restrict__ logit, float* __restrict__ score, bool first_group,
-                                         bool last_group) {
+                                         bool last_group, float* __restrict__ gates) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float ar[8][2], az[8][2], an[8][2], ahn[8][2];
 #pragma unroll
@@ -401,6 +401,13 @@ __device__ __forceinline__ void gru_tile(StepSmem<KX>& s, float* __restrict__ h_
     float dot = warp_sum_f(fmaf(o0, hw.x, o1 * hw.y));
     if (row >= 0) {
       *reinterpret_cast<float2*>(h_out + (size_t)row * ldh + col + 2 * tx) = make_float2(o0, o1);
+      if (gates) {  // training: keep r | z | n | (W_hn h + b_hn) for the backward pass
+        float* gr = gates + (size_t)row * 4 * H + 2 * tx;
+        *reinterpret_cast<float2*>(gr) = make_float2(r0, r1);
+        *reinterpret_cast<float2*>(gr + H) = make_float2(z0, z1);
+        *reinterpret_cast<float2*>(gr + 2 * H) = make_float2(n0, n1);
+        *reinterpret_cast<float2*>(gr + 3 * H) = make_float2(ahn[i][0] + bhn.x, ahn[i][1] + bhn.y);
+      }
       if (tx == 0) {
         const float lg = dot + (first_group ? hb : logit[row]);
         logit[row] = lg;
@@ -416,7 +423,8 @@ __global__ void __launch_bounds__(NT, 1)
 k_mp_edge(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
           const int32_t* __restrict__ n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
           int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const float* __restrict__ pack,
-          float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group) {
+          float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
+          float* __restrict__ gates) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<KX>& s = *reinterpret_cast<StepSmem<KX>*>(smem_raw);
   const int total = tile_ptr[num_seqs];
@@ -457,7 +465,7 @@ k_mp_edge(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, in
       if (l16 == 0) s.rowid[r] = a >= 0 ? (int)(base + lr) : -1;
     }
     __syncthreads();
-    gru_tile<KX>(s, h_out, ldh, col, logit, score, first_group != 0, last_group != 0);
+    gru_tile<KX>(s, h_out, ldh, col, logit, score, first_group != 0, last_group != 0, gates);
   }
 }
 
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
          const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows, const float* __restrict__ agg,
          const float* __restrict__ pack, float* __restrict__ logit, float* __restrict__ score, int first_group,
-         int last_group) {
+         int last_group, float* __restrict__ gates) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<H>& s = *reinterpret_cast<StepSmem<H>*>(smem_raw);
   const int nd = *n_dets;
@@ -492,7 +500,7 @@ k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int
       if (l16 == 0) s.rowid[r] = row;
     }
     __syncthreads();
-    gru_tile<H>(s, h_out, ldh, col, logit, score, first_group != 0, last_group != 0);
+    gru_tile<H>(s, h_out, ldh, col, logit, score, first_group != 0, last_group != 0, gates);
   }
 }
 
@@ -515,8 +523,8 @@ extern "C" int tmpnn_init(void) {
   return TMPNN_OK;
 }
 
-extern "C" int tmpnn_mp_edge_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
-                                 int group, int num_groups, int concat, const float* edge_pack, void* stream) {
+static int mp_edge_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
+                          int num_groups, int concat, const float* edge_pack, float* gates, void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_pack, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
@@ -527,26 +535,47 @@ extern "C" int tmpnn_mp_edge_fwd(const tmpnn_graph* g, const tmpnn_index* ix, co
   if (concat)
     k_mp_edge<2 * H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<2 * H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last);
+        g->score, first, last, gates);
   else
     k_mp_edge<H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last);
+        g->score, first, last, gates);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
 
-extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
-                                int group, int num_groups, const float* node_pack, const float* agg, void* stream) {
+static int mp_det_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
+                         int num_groups, const float* node_pack, const float* agg, float* gates, void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && node_pack && agg, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   if (!g_init_done) { int rc0 = tmpnn_init(); if (rc0) return rc0; }
   k_mp_det<<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, ix->n_dets, ix->det_rows, agg, node_pack, g->logit, g->score, group == 0,
-      group == num_groups - 1);
+      group == num_groups - 1, gates);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
+}
+
+extern "C" int tmpnn_mp_edge_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                 int group, int num_groups, int concat, const float* edge_pack, void* stream) {
+  return mp_edge_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, nullptr, stream);
+}
+
+extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                int group, int num_groups, const float* node_pack, const float* agg, void* stream) {
+  return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, nullptr, stream);
+}
+
+extern "C" int tmpnn_mp_step_fwd_train(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                       int group, int num_groups, int concat, const float* edge_pack,
+                                       const float* node_pack, float* agg, float* gates, void* stream) {
+  TMPNN_REQUIRE(gates, "null argument");
+  int rc = tmpnn_aggregate_dets(g, ix, h_in, ldh, group * H, agg, stream);
+  if (rc) return rc;
+  rc = mp_edge_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, gates, stream);
+  if (rc) return rc;
+  return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, gates, stream);
 }
 
 extern "C" int tmpnn_mp_step_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,

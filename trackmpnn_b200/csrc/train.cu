@@ -1,0 +1,574 @@
+// train.cu -- backward pass of the message-passing step and the training losses (fp32).
+//
+// Reference behaviour: the autograd graph torch builds for models/track_mpnn.py:54-75 +
+// models/layers.py:84-116 when train.py:65-134 calls loss.backward(), and models/loss.py:8-115
+// (create_targets, CELoss, FocalLoss with gamma = 0).  Restated on the edge list:
+//
+//   forward (per feature group, Jacobi):   x_e = h[src]-h[dst] | [h[src] | h[dst]],  x_d = agg[d]
+//                                          h' = GRUCell_type(x, h),  logit = w_type . h' + b_type
+//   backward, given dL/dh', dL/dlogit, dL/dscore:
+//     dh'   += dlogit_tot * w_type                         dlogit_tot = dlogit + dscore * p (1 - p)
+//     dn = dh' (1-z), dz = dh' (h - n), dh_self = dh' z
+//     dpn = dn (1 - n^2), dpz = dz z (1-z), dpr = dpn * hn_pre * r (1-r)
+//     dgi = [dpr, dpz, dpn], dgh = [dpr, dpz, dpn r]
+//     dx = dgi . W_ih,  dh_self += dgh . W_hh,  dW_ih += dgi^T x,  dW_hh += dgh^T h,  db_* += sum dg*
+//   and the transpose of the gather / segmented sum in GATHER form (no float atomics on the state):
+//     edge row e: dh_in[e] = dh_self[e] + dagg[src(e)] - dagg[dst(e)]
+//     det  row d: dh_in[d] = dh_self[d] + sum_{e: src=d} dx_e[0:64] -/+ sum_{e: dst=d} dx_e[0:64 | 64:128]
+//
+// The training graphs of the reference are small (<= 10^4 rows per step, BPTT over <= 10 steps), so
+// these kernels favour simple, checkable structure; weight-gradient partial sums are combined with
+// fp32 atomics (order-dependent in the last bits, well inside the gradient tolerance).
+#include "common.cuh"
+
+namespace {
+
+constexpr int H = TMPNN_HIDDEN;
+
+// ------------------------------------------------------------------------------------------
+// gate gradients: one thread per (row, hidden unit); block = 4 rows x 64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict__ gates,
+           const float* __restrict__ h_prev, const float* __restrict__ h_new, int ldh, int col,
+           const float* __restrict__ dh_out, const float* __restrict__ dlogits, const float* __restrict__ dscores,
+           const float* __restrict__ score, const float* __restrict__ hw_e, const float* __restrict__ hw_d,
+           float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dhself,
+           float* __restrict__ gb_e, float* __restrict__ gb_d,   // [2][192]: d bias_ih | d bias_hh
+           float* __restrict__ ghw_e, float* __restrict__ ghw_d, // [64] head weight slices
+           float* __restrict__ ghb_e, float* __restrict__ ghb_d) // [1] head biases (group 0 only, else null)
+{
+  __shared__ float red[4][H];
+  const int j = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  float acc[2][5] = {{0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f}};  // per type: dpr, dpz, dpn, dpnr, dhw
+  float accb[2] = {0.f, 0.f};
+  const float we = hw_e[j], wd = hw_d[j];
+  for (int row = blockIdx.x * 4 + rl; row < n_rows; row += gridDim.x * 4) {
+    const int t = src[row] >= 0 ? 0 : 1;  // 0 = edge row, 1 = detection row
+    const float p = score[row];
+    const float dl = (dlogits ? dlogits[row] : 0.f) + (dscores ? dscores[row] * p * (1.0f - p) : 0.f);
+    const float* gr = gates + (size_t)row * 4 * H;
+    const float r = gr[j], z = gr[H + j], n = gr[2 * H + j], hn = gr[3 * H + j];
+    const size_t o = (size_t)row * ldh + col + j;
+    const float h = h_prev[o];
+    const float dh = (dh_out ? dh_out[o] : 0.f) + dl * (t ? wd : we);
+    const float dn = dh * (1.0f - z), dz = dh * (h - n);
+    const float dpn = dn * (1.0f - n * n), dpz = dz * z * (1.0f - z), dpr = dpn * hn * r * (1.0f - r);
+    const float dpnr = dpn * r;
+    float* gi = dgi + (size_t)row * 3 * H;
+    float* gh = dgh + (size_t)row * 3 * H;
+    gi[j] = dpr; gi[H + j] = dpz; gi[2 * H + j] = dpn;
+    gh[j] = dpr; gh[H + j] = dpz; gh[2 * H + j] = dpnr;
+    dhself[(size_t)row * H + j] = dh * z;
+    acc[t][0] += dpr; acc[t][1] += dpz; acc[t][2] += dpn; acc[t][3] += dpnr; acc[t][4] += dl * h_new[o];
+    if (j == 0) accb[t] += dl;
+  }
+  for (int t = 0; t < 2; ++t) {
+    float* gb = t ? gb_d : gb_e;
+    float* ghw = t ? ghw_d : ghw_e;
+    for (int q = 0; q < 5; ++q) {
+      __syncthreads();
+      red[rl][j] = acc[t][q];
+      __syncthreads();
+      if (rl == 0) {
+        const float v = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+        if (v != 0.f) {
+          if (q < 3) atomicAdd(&gb[q * H + j], v);                  // d bias_ih
+          if (q < 2) atomicAdd(&gb[3 * H + q * H + j], v);          // d bias_hh (r, z)
+          if (q == 3) atomicAdd(&gb[3 * H + 2 * H + j], v);         // d bias_hh (n)
+          if (q == 4) atomicAdd(&ghw[j], v);
+        }
+      }
+    }
+    __syncthreads();
+    if (j == 0) red[rl][0] = accb[t];
+    __syncthreads();
+    float* ghb = t ? ghb_d : ghb_e;
+    if (threadIdx.x == 0 && ghb) {
+      const float v = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+      if (v != 0.f) atomicAdd(ghb, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// C[rc(i)][0:N] (+)= A[ra(i)][0:K] . W[K][N]      rows i < R with mask[ra(i)] >= 0
+// ------------------------------------------------------------------------------------------
+constexpr int GK = 192;
+template <int N>
+__global__ void __launch_bounds__(256)
+k_rows_times_w(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __restrict__ a_rows,
+               const int32_t* __restrict__ c_rows, const int32_t* __restrict__ mask, const float* __restrict__ A,
+               const float* __restrict__ W, float* __restrict__ C, int ldc, int accumulate) {
+  constexpr int RPB = 16;           // rows per block pass
+  constexpr int RPT = RPB * N / 256;  // rows per thread (N = 64 -> 4, N = 128 -> 8)
+  __shared__ float As[RPB][GK];
+  __shared__ int32_t rc_s[RPB];
+  const int R = r_dev ? *r_dev : r_host;
+  const int nn = threadIdx.x % N, rg = threadIdx.x / N;  // rg < 256 / N
+  for (int i0 = blockIdx.x * RPB; i0 < R; i0 += gridDim.x * RPB) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < RPB * GK; q += 256) {
+      const int ri = q / GK, k = q % GK, i = i0 + ri;
+      float v = 0.f;
+      if (i < R) {
+        const int ra = a_rows ? a_rows[i] : i;
+        if (!mask || mask[ra] >= 0) v = A[(size_t)ra * GK + k];
+      }
+      As[ri][k] = v;
+    }
+    if (threadIdx.x < RPB) {
+      const int i = i0 + threadIdx.x;
+      int rc = -1;
+      if (i < R) {
+        const int ra = a_rows ? a_rows[i] : i;
+        if (!mask || mask[ra] >= 0) rc = c_rows ? c_rows[i] : i;
+      }
+      rc_s[threadIdx.x] = rc;
+    }
+    __syncthreads();
+    float acc[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) acc[q] = 0.f;
+    for (int k = 0; k < GK; ++k) {
+      const float w = __ldg(W + (size_t)k * N + nn);
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) acc[q] = fmaf(As[rg * RPT + q][k], w, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int rc = rc_s[rg * RPT + q];
+      if (rc >= 0) {
+        float* c = C + (size_t)rc * ldc + nn;
+        *c = accumulate ? *c + acc[q] : acc[q];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// G[m][n] += sum_i A[ra(i)][m] * B[rb(i)][n]      m < 192, n < N, rows i < R with mask[ra(i)] >= 0
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256)
+k_rows_outer(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __restrict__ a_rows,
+             const int32_t* __restrict__ b_rows, const int32_t* __restrict__ mask, const float* __restrict__ A,
+             const float* __restrict__ B, int ldb, float* __restrict__ G) {
+  constexpr int RPB = 32;
+  __shared__ float As[RPB][GK];
+  __shared__ float Bs[RPB][N];
+  const int R = r_dev ? *r_dev : r_host;
+  constexpr int OPT = GK * N / 256;  // outputs per thread
+  float acc[OPT];
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) acc[q] = 0.f;
+  for (int i0 = blockIdx.x * RPB; i0 < R; i0 += gridDim.x * RPB) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < RPB * GK; q += 256) {
+      const int ri = q / GK, k = q % GK, i = i0 + ri;
+      float v = 0.f;
+      if (i < R) {
+        const int ra = a_rows ? a_rows[i] : i;
+        if (!mask || mask[ra] >= 0) v = A[(size_t)ra * GK + k];
+      }
+      As[ri][k] = v;
+    }
+    for (int q = threadIdx.x; q < RPB * N; q += 256) {
+      const int ri = q / N, k = q % N, i = i0 + ri;
+      float v = 0.f;
+      if (i < R) v = B[(size_t)(b_rows ? b_rows[i] : i) * ldb + k];
+      Bs[ri][k] = v;
+    }
+    __syncthreads();
+    // output o = threadIdx.x + 256 q -> (m, n) = (o / N, o % N): n is the fast index across a warp
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) {
+      const int o = threadIdx.x + 256 * q, m = o / N, n = o % N;
+      float a = acc[q];
+#pragma unroll 8
+      for (int ri = 0; ri < RPB; ++ri) a = fmaf(As[ri][m], Bs[ri][n], a);
+      acc[q] = a;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) {
+    const int o = threadIdx.x + 256 * q;
+    if (acc[q] != 0.f) atomicAdd(&G[o], acc[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// transpose of the gather / segmented sum
+// ------------------------------------------------------------------------------------------
+// edge rows: half-warp per row
+__global__ void __launch_bounds__(256)
+k_scatter_bwd_edges(int n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                    const int32_t* __restrict__ det_of_row, const float* __restrict__ dhself,
+                    const float* __restrict__ dagg, float* __restrict__ dh_in, int ldh, int col) {
+  const int l16 = threadIdx.x & 15;
+  for (int row = blockIdx.x * 16 + (threadIdx.x >> 4); row < n_rows; row += gridDim.x * 16) {
+    const int a = src[row];
+    if (a < 0) continue;
+    const int ka = det_of_row[a], kb = det_of_row[dst[row]];
+    const float4 s = ldg4(dhself + (size_t)row * H + 4 * l16);
+    const float4 pa = ldg4(dagg + (size_t)ka * H + 4 * l16), pb = ldg4(dagg + (size_t)kb * H + 4 * l16);
+    *reinterpret_cast<float4*>(dh_in + (size_t)row * ldh + col + 4 * l16) =
+        make_float4(s.x + pa.x - pb.x, s.y + pa.y - pb.y, s.z + pa.z - pb.z, s.w + pa.w - pb.w);
+  }
+}
+
+// detection rows: warp per detection over its incidence segments (ascending -> reproducible)
+__global__ void __launch_bounds__(256)
+k_scatter_bwd_dets(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows,
+                   const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ inc,
+                   const float* __restrict__ dhself, const float* __restrict__ dx, int kx,
+                   float* __restrict__ dh_in, int ldh, int col) {
+  const int nd = *n_dets;
+  const int lane = threadIdx.x & 31;
+  const int concat = kx == 2 * H;
+  for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nd; k += gridDim.x * 8) {
+    const int s0 = seg_ptr[2 * k], s1 = seg_ptr[2 * k + 1], s2 = seg_ptr[2 * k + 2];
+    const int row = det_rows[k];
+    float a0 = dhself[(size_t)row * H + lane], a1 = dhself[(size_t)row * H + lane + 32];
+    for (int i = s0; i < s1; ++i) {  // past edges: this detection is their dst
+      const float* d = dx + (size_t)inc[i] * kx + (concat ? H : 0);
+      if (concat) { a0 += d[lane]; a1 += d[lane + 32]; }
+      else { a0 -= d[lane]; a1 -= d[lane + 32]; }
+    }
+    for (int i = s1; i < s2; ++i) {  // future edges: this detection is their src
+      const float* d = dx + (size_t)inc[i] * kx;
+      a0 += d[lane]; a1 += d[lane + 32];
+    }
+    dh_in[(size_t)row * ldh + col + lane] = a0;
+    dh_in[(size_t)row * ldh + col + lane + 32] = a1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// input transform backward (Linear -> BatchNorm -> ReLU -> Linear), one CTA
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_input_bwd(const float* __restrict__ x, int ldx, int col0, int f_in, const int32_t* __restrict__ x_idx,
+            const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ var,
+            const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ b1,
+            const float* __restrict__ w2, const float* __restrict__ dh, int ldh, int col,
+            const int32_t* __restrict__ out_rows, int n, int n_edge, int training, float* __restrict__ scratch,
+            float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ ggamma, float* __restrict__ gbeta,
+            float* __restrict__ gw2, float* __restrict__ gb2) {
+  __shared__ float red[2][4][H];
+  __shared__ float m_s[2][H];
+  const int j = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  float* dbn = scratch;                   // [n][64], later da
+  float* act = scratch + (size_t)n * H;   // [n][64]
+  const float inv = 1.0f / sqrtf(var[j] + 1e-5f), mu = mean[j], gm = gamma[j], bt = beta[j];
+  const float ntot = (float)(n + n_edge);
+  // pass 1: d act = dh . W2, through the ReLU; channel sums
+  float s1 = 0.f, s2 = 0.f, sb2 = 0.f;
+  for (int i = rl; i < n; i += 4) {
+    const float* dr = dh + (size_t)out_rows[i] * ldh + col;
+    float d = 0.f;
+    for (int o = 0; o < H; ++o) d = fmaf(dr[o], w2[o * H + j], d);
+    const float xh = (a[(size_t)i * H + j] - mu) * inv;
+    const float bn = xh * gm + bt;
+    const float g = bn > 0.f ? d : 0.f;
+    dbn[(size_t)i * H + j] = g;
+    act[(size_t)i * H + j] = fmaxf(bn, 0.f);
+    s1 += g; s2 += g * xh; sb2 += dr[j];
+  }
+  red[0][rl][j] = s1; red[1][rl][j] = s2;
+  __syncthreads();
+  if (rl == 0) {
+    const float t1 = red[0][0][j] + red[0][1][j] + red[0][2][j] + red[0][3][j];
+    const float t2 = red[1][0][j] + red[1][1][j] + red[1][2][j] + red[1][3][j];
+    m_s[0][j] = t1; m_s[1][j] = t2;
+    gbeta[j] += t1;
+    ggamma[j] += t2;
+  }
+  __syncthreads();
+  red[0][rl][j] = sb2;
+  __syncthreads();
+  if (rl == 0) gb2[j] += red[0][0][j] + red[0][1][j] + red[0][2][j] + red[0][3][j];
+  const float m1 = training ? m_s[0][j] / ntot : 0.f, m2 = training ? m_s[1][j] / ntot : 0.f;
+  __syncthreads();
+  // d W2[o][j] += sum_i dh[i][o] act[i][j]
+  for (int q = threadIdx.x; q < H * H; q += 256) {
+    const int o = q / H, jj = q % H;
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = fmaf(dh[(size_t)out_rows[i] * ldh + col + o], act[(size_t)i * H + jj], s);
+    gw2[q] += s;
+  }
+  // pass 2: through the BatchNorm
+  float sda = 0.f;
+  for (int i = rl; i < n; i += 4) {
+    const float xh = (a[(size_t)i * H + j] - mu) * inv;
+    const float da = gm * inv * (dbn[(size_t)i * H + j] - m1 - xh * m2);
+    dbn[(size_t)i * H + j] = da;
+    sda += da;
+  }
+  __syncthreads();
+  red[0][rl][j] = sda;
+  __syncthreads();
+  if (rl == 0) {
+    float t = red[0][0][j] + red[0][1][j] + red[0][2][j] + red[0][3][j];
+    if (training) {  // the n_edge all-zero rows (value b1 after Linear1) sit in the batch statistics too
+      const float xe = (b1[j] - mu) * inv;
+      t += (float)n_edge * gm * inv * (-m1 - xe * m2);
+    }
+    gb1[j] += t;
+  }
+  __syncthreads();
+  // d W1[j][k] += sum_i da[i][j] x[i][k]
+  for (int q = threadIdx.x; q < H * f_in; q += 256) {
+    const int jj = q / f_in, k = q % f_in;
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = fmaf(dbn[(size_t)i * H + jj], x[(size_t)(x_idx ? x_idx[i] : i) * ldx + col0 + k], s);
+    gw1[q] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// losses (models/loss.py)
+// ------------------------------------------------------------------------------------------
+__global__ void k_targets_init(int n, const int32_t* __restrict__ ts, const int32_t* __restrict__ label,
+                               int32_t* __restrict__ targets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) targets[i] = ts[i] >= 0 ? label[i] : 0;
+}
+
+// per detection: latest positive past edge, earliest positive future edge (models/loss.py:26-43)
+__global__ void k_targets_mark(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ seg_ptr,
+                               const int32_t* __restrict__ inc, const int32_t* __restrict__ label,
+                               int32_t* __restrict__ targets) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *n_dets) return;
+  const int s0 = seg_ptr[2 * k], s1 = seg_ptr[2 * k + 1], s2 = seg_ptr[2 * k + 2];
+  for (int i = s1 - 1; i >= s0; --i)
+    if (label[inc[i]]) { targets[inc[i]] = 1; break; }
+  for (int i = s1; i < s2; ++i)
+    if (label[inc[i]]) { targets[inc[i]] = 1; break; }
+}
+
+// one warp per segment (2 per detection): log-sum-exp, the chosen positive, loss / len
+__global__ void __launch_bounds__(256)
+k_ce_fwd(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ inc,
+         const int32_t* __restrict__ targets, const float* __restrict__ logit, float* __restrict__ seg_lse,
+         int32_t* __restrict__ seg_pos, float* __restrict__ seg_loss) {
+  const int lane = threadIdx.x & 31;
+  const int nseg = 2 * (*n_dets);
+  for (int x = blockIdx.x * 8 + (threadIdx.x >> 5); x < nseg; x += gridDim.x * 8) {
+    const int s0 = seg_ptr[x], s1 = seg_ptr[x + 1];
+    const bool past = (x & 1) == 0;
+    // position of the chosen positive: last one for past segments, first one for future segments
+    int pos = past ? -1 : 0x7fffffff;
+    float mx = -INFINITY;
+    for (int i = s0 + lane; i < s1; i += 32) {
+      const int e = inc[i];
+      mx = fmaxf(mx, logit[e]);
+      if (targets[e]) pos = past ? max(pos, i) : min(pos, i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+      pos = past ? max(pos, p2) : min(pos, p2);
+    }
+    const bool has = past ? pos >= 0 : pos != 0x7fffffff;
+    float lse = 0.f, loss = 0.f;
+    int pe = -1;
+    if (has && s1 > s0) {
+      float sum = 0.f;
+      for (int i = s0 + lane; i < s1; i += 32) sum += expf(logit[inc[i]] - mx);
+      sum = warp_sum_f(sum);
+      lse = mx + logf(sum);
+      pe = inc[pos];
+      loss = (lse - logit[pe]) / (float)(s1 - s0);
+    }
+    if (lane == 0) { seg_lse[x] = lse; seg_pos[x] = pe; seg_loss[x] = loss; }
+  }
+}
+
+// deterministic sum of a float array with one CTA (double accumulation), out[0] (+)= scale * sum
+__global__ void __launch_bounds__(256) k_sum(const float* __restrict__ v, const int32_t* __restrict__ n_dev, int n_mul,
+                                             int n_host, float scale_by_n, float* __restrict__ out) {
+  __shared__ double red[256];
+  const int n = n_dev ? n_mul * (*n_dev) : n_host;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(scale_by_n != 0.f ? red[0] / (double)max(n, 1) : red[0]);
+}
+
+// d logit of every edge row from its two segments (past segment of dst, future segment of src)
+__global__ void k_ce_bwd(int n, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                         const int32_t* __restrict__ det_of_row, const int32_t* __restrict__ seg_ptr,
+                         const float* __restrict__ seg_lse, const int32_t* __restrict__ seg_pos,
+                         const float* __restrict__ logit, const float* __restrict__ gout, float* __restrict__ dlogit) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float d = 0.f;
+  const int a = src[e];
+  if (a >= 0) {
+    const float g = gout[0], lg = logit[e];
+    const int xs[2] = {2 * det_of_row[dst[e]], 2 * det_of_row[a] + 1};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int x = xs[q];
+      if (seg_pos[x] >= 0) {
+        const float len = (float)(seg_ptr[x + 1] - seg_ptr[x]);
+        d += g * (expf(lg - seg_lse[x]) - (seg_pos[x] == e ? 1.0f : 0.0f)) / len;
+      }
+    }
+  }
+  dlogit[e] = d;
+}
+
+// FocalLoss(gamma = 0): -log(p_t + 1e-10) per element (models/loss.py:57-74)
+__global__ void k_focal_fwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = -logf((t[i] == 1 ? p[i] : 1.0f - p[i]) + 1e-10f);
+}
+__global__ void k_focal_bwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t,
+                            const float* __restrict__ gout, float inv_n, float* __restrict__ dp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const bool pos = t[i] == 1;
+    const float pt = (pos ? p[i] : 1.0f - p[i]) + 1e-10f;
+    dp[i] = gout[0] * inv_n * (pos ? -1.0f : 1.0f) / pt;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int tmpnn_gate_bwd(int n_rows, const int32_t* src, const float* gates, const float* h_prev, const float* h_new,
+                              int ldh, int col, const float* dh_out, const float* dlogits, const float* dscores,
+                              const float* score, const float* head_w_edge, const float* head_w_node, float* dgi,
+                              float* dgh, float* dhself, float* gbias_edge, float* gbias_node, float* ghw_edge,
+                              float* ghw_node, float* ghb_edge, float* ghb_node, void* stream) {
+  TMPNN_REQUIRE(src && gates && h_prev && h_new && score && dgi && dgh && dhself, "null argument");
+  if (n_rows <= 0) return TMPNN_OK;
+  const int blocks = min(tmpnn_div_up(n_rows, 16), TMPNN_SM_COUNT * 2);
+  k_gate_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, src, gates, h_prev, h_new, ldh, col, dh_out, dlogits, dscores,
+                                                      score, head_w_edge, head_w_node, dgi, dgh, dhself, gbias_edge,
+                                                      gbias_node, ghw_edge, ghw_node, ghb_edge, ghb_node);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_rows_times_w(const int32_t* r_dev, int r_host, const int32_t* a_rows, const int32_t* c_rows,
+                                  const int32_t* mask, const float* A, const float* W, int n, float* C, int ldc,
+                                  int accumulate, void* stream) {
+  TMPNN_REQUIRE(A && W && C && (n == 64 || n == 128), "bad argument");
+  const int r_max = r_dev ? TMPNN_SM_COUNT * 16 * 4 : r_host;
+  if (r_max <= 0) return TMPNN_OK;
+  const int blocks = min(tmpnn_div_up(r_max, 16), TMPNN_SM_COUNT * 4);
+  if (n == 64)
+    k_rows_times_w<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(r_dev, r_host, a_rows, c_rows, mask, A, W, C, ldc, accumulate);
+  else
+    k_rows_times_w<128><<<blocks, 256, 0, (cudaStream_t)stream>>>(r_dev, r_host, a_rows, c_rows, mask, A, W, C, ldc, accumulate);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_rows_outer(const int32_t* r_dev, int r_host, const int32_t* a_rows, const int32_t* b_rows,
+                                const int32_t* mask, const float* A, const float* B, int ldb, int n, float* G,
+                                void* stream) {
+  TMPNN_REQUIRE(A && B && G && (n == 64 || n == 128), "bad argument");
+  const int r_max = r_dev ? TMPNN_SM_COUNT * 32 : r_host;
+  if (r_max <= 0) return TMPNN_OK;
+  const int blocks = min(tmpnn_div_up(r_max, 32), TMPNN_SM_COUNT);
+  if (n == 64)
+    k_rows_outer<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(r_dev, r_host, a_rows, b_rows, mask, A, B, ldb, G);
+  else
+    k_rows_outer<128><<<blocks, 256, 0, (cudaStream_t)stream>>>(r_dev, r_host, a_rows, b_rows, mask, A, B, ldb, G);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_scatter_bwd(const tmpnn_graph* g, const tmpnn_index* ix, int n_rows, const float* dhself,
+                                 const float* dx, int kx, const float* dagg, float* dh_in, int ldh, int col, void* stream) {
+  TMPNN_REQUIRE(g && ix && dhself && dx && dagg && dh_in && g->num_seqs == 1, "bad argument (single-slab graphs only)");
+  TMPNN_REQUIRE(kx == H || kx == 2 * H, "kx must be 64 or 128");
+  if (n_rows <= 0) return TMPNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_scatter_bwd_edges<<<min(tmpnn_div_up(n_rows, 16), TMPNN_SM_COUNT * 8), 256, 0, st>>>(n_rows, g->src, g->dst, ix->det_of_row,
+                                                                                        dhself, dagg, dh_in, ldh, col);
+  TMPNN_LAUNCH_CHECK();
+  k_scatter_bwd_dets<<<min(tmpnn_div_up(n_rows, 8), TMPNN_SM_COUNT * 4), 256, 0, st>>>(ix->n_dets, ix->det_rows, ix->seg_ptr,
+                                                                                      ix->inc, dhself, dx, kx, dh_in, ldh, col);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_input_bwd(const float* x, int ldx, int col0, int f_in, const int32_t* x_idx, const float* a,
+                               const float* mean, const float* var, const float* gamma, const float* beta,
+                               const float* b1, const float* w2, const float* dh, int ldh, int col,
+                               const int32_t* out_rows, int n, int n_edge_rows, int training, float* scratch,
+                               float* gw1, float* gb1, float* ggamma, float* gbeta, float* gw2, float* gb2, void* stream) {
+  TMPNN_REQUIRE(x && a && mean && var && gamma && beta && b1 && w2 && dh && out_rows && scratch, "null argument");
+  TMPNN_REQUIRE(gw1 && gb1 && ggamma && gbeta && gw2 && gb2, "null gradient buffer");
+  if (n <= 0) return TMPNN_OK;
+  k_input_bwd<<<1, 256, 0, (cudaStream_t)stream>>>(x, ldx, col0, f_in, x_idx, a, mean, var, gamma, beta, b1, w2, dh, ldh, col,
+                                                  out_rows, n, n_edge_rows, training, scratch, gw1, gb1, ggamma, gbeta, gw2,
+                                                  gb2);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_targets(const tmpnn_graph* g, const tmpnn_index* ix, int n_rows, int32_t* targets, void* stream) {
+  TMPNN_REQUIRE(g && ix && targets && g->label && g->num_seqs == 1, "bad argument (single-slab graph with labels)");
+  if (n_rows <= 0) return TMPNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_targets_init<<<tmpnn_div_up(n_rows, 256), 256, 0, st>>>(n_rows, g->ts, g->label, targets);
+  TMPNN_LAUNCH_CHECK();
+  k_targets_mark<<<tmpnn_div_up(n_rows, 128), 128, 0, st>>>(ix->n_dets, ix->seg_ptr, ix->inc, g->label, targets);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_ce_fwd(const tmpnn_index* ix, int n_rows, const int32_t* targets, const float* logit,
+                                 float* seg_lse, int32_t* seg_pos, float* seg_loss, float* loss, void* stream) {
+  TMPNN_REQUIRE(ix && targets && logit && seg_lse && seg_pos && seg_loss && loss, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_ce_fwd<<<max(1, min(tmpnn_div_up(n_rows, 8), TMPNN_SM_COUNT * 4)), 256, 0, st>>>(ix->n_dets, ix->seg_ptr, ix->inc, targets, logit,
+                                                                                    seg_lse, seg_pos, seg_loss);
+  TMPNN_LAUNCH_CHECK();
+  k_sum<<<1, 256, 0, st>>>(seg_loss, ix->n_dets, 2, 0, 0.f, loss);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_ce_bwd(const tmpnn_graph* g, const tmpnn_index* ix, int n_rows, const float* seg_lse,
+                                 const int32_t* seg_pos, const float* logit, const float* grad_out, float* dlogit,
+                                 void* stream) {
+  TMPNN_REQUIRE(g && ix && seg_lse && seg_pos && logit && grad_out && dlogit, "null argument");
+  if (n_rows <= 0) return TMPNN_OK;
+  k_ce_bwd<<<tmpnn_div_up(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(n_rows, g->src, g->dst, ix->det_of_row, ix->seg_ptr, seg_lse,
+                                                                       seg_pos, logit, grad_out, dlogit);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_focal_fwd(int n, const float* p, const int64_t* targets, float* per_elem, float* loss, void* stream) {
+  TMPNN_REQUIRE(p && targets && per_elem && loss && n > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_focal_fwd<<<tmpnn_div_up(n, 256), 256, 0, st>>>(n, p, targets, per_elem);
+  TMPNN_LAUNCH_CHECK();
+  k_sum<<<1, 256, 0, st>>>(per_elem, nullptr, 0, n, 1.0f, loss);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_focal_bwd(int n, const float* p, const int64_t* targets, const float* grad_out, float* dp, void* stream) {
+  TMPNN_REQUIRE(p && targets && grad_out && dp && n > 0, "bad argument");
+  k_focal_bwd<<<tmpnn_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, targets, grad_out, 1.0f / (float)n, dp);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}

@@ -128,11 +128,16 @@ def input_transform_rows(model, g, x, x_idx, n, n_edge_rows, h, ldh, out_rows, n
     L.call('tmpnn_input_bn_relu_linear2', L.ptr(a), L.ptr(mean), L.ptr(var), L.ptr(bn.weight.detach()),
            L.ptr(bn.bias.detach()), L.ptr(lin2.weight.detach()), L.ptr(lin2.bias.detach()), L.ptr(h), int(ldh), g * H,
            L.ptr(out_rows), L.ptr(n_dev), int(n), L.stream())
-    return a
+    return a, mean, var
 
 
 def track_mpnn_forward(model, x, h_in, node_adj, edge_adj):
     """``TrackMPNN.forward`` (reference ``models/track_mpnn.py:54-75``) on the CUDA library."""
+    if torch.is_grad_enabled() and (any(p.requires_grad for p in model.parameters())
+                                    or (h_in is not None and h_in.requires_grad)):
+        G = len(model.feature_idx)
+        scores, logits, h_out = _MPStepFn.apply(model, node_adj, x, h_in, *_param_list(model))
+        return scores, logits, h_out, tuple(None for _ in range(G))
     wg = window_graph_of(node_adj)
     dev = wg.device
     n_tot = wg.n
@@ -188,3 +193,143 @@ def mp_step_single_group(gru, h, node_adj):
     L.call('tmpnn_mp_step_fwd', wg.g.c, ix.c, L.ptr(h_in), L.ptr(h_out), H, 0, 1, int(gru.msg_type == 'concat'),
            L.ptr(packs[0]), L.ptr(packs[1]), L.ptr(agg), L.stream())
     return h_out
+
+
+# ---------------------------------------------------------------------------------------------
+# training: the step as a torch.autograd.Function (reference: loss.backward() in train.py:65-134)
+# ---------------------------------------------------------------------------------------------
+_PER_GROUP = 14  # lin1.w, lin1.b, bn.w, bn.b, lin2.w, lin2.b, edge_gru x4, node_gru x4
+
+
+def _param_list(model):
+    ps = []
+    for g in range(len(model.feature_idx)):
+        seq, gru = model.input_transforms[g], model.factor_grus[g]
+        ps += [seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias]
+        for cell in (gru.edge_gru, gru.node_gru):
+            ps += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+    ps += [model.output_transform_node.weight, model.output_transform_node.bias,
+           model.output_transform_edge.weight, model.output_transform_edge.bias]
+    return ps
+
+
+class _MPStepFn(torch.autograd.Function):
+    """One ``TrackMPNN.forward`` with everything its backward needs kept on the device: the state the
+    step consumed, the GRU gates of every row, the detection aggregates, Linear1 outputs and the
+    BatchNorm statistics of the new rows, and the (immutable) window graph + incidence index."""
+
+    @staticmethod
+    def forward(ctx, model, node_adj, x, h_in, *params):
+        wg = window_graph_of(node_adj)
+        dev = wg.device
+        n_tot = wg.n
+        G = len(model.feature_idx)
+        ldh = G * H
+        n_new = int(x.size()[0])
+        n_old = n_tot - n_new
+        if (0 if h_in is None else int(h_in.shape[0])) != n_old:
+            raise ValueError(f'h_in has {0 if h_in is None else int(h_in.shape[0])} rows, graph has {n_tot} rows of '
+                             f'which {n_new} are new')
+        h_cur = torch.zeros((n_tot, ldh), dtype=torch.float32, device=dev)
+        if n_old:
+            h_cur[:n_old].copy_(h_in.detach())
+        saved_in = None
+        if n_new > 0:
+            new_det = torch.nonzero(wg.g.ts[n_old:n_tot] >= 0)[:, 0].to(torch.int32)
+            nd = int(new_det.numel())
+            out_rows = (new_det + n_old).contiguous()
+            xd = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+            per_group = []
+            for g in range(G):
+                training = model.input_transforms[g][1].training
+                a, mean, var = input_transform_rows(model, g, xd, new_det, nd, n_new - nd, h_cur, ldh, out_rows)
+                per_group.append((a, mean.clone(), var.clone(), training))
+            saved_in = (xd, new_det, out_rows, nd, n_new - nd, per_group)
+        ix = wg.index()
+        h_out = torch.empty_like(h_cur)
+        packs = packed_cells(model)
+        gates, aggs = [], []
+        st = L.stream()
+        for g in range(G):
+            concat = int(model.factor_grus[g].msg_type == 'concat')
+            gt = torch.empty((n_tot, 4 * H), dtype=torch.float32, device=dev)
+            agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
+            L.call('tmpnn_mp_step_fwd_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat,
+                   L.ptr(packs[g][0]), L.ptr(packs[g][1]), L.ptr(agg), L.ptr(gt), st)
+            gates.append(gt)
+            aggs.append(agg)
+        logits = wg.g.logit[:n_tot].clone().unsqueeze(1)
+        scores = wg.g.score[:n_tot].clone().unsqueeze(1)
+        ctx.model, ctx.wg, ctx.ix = model, wg, ix
+        ctx.n_old, ctx.has_h_in = n_old, h_in is not None
+        ctx.saved_in, ctx.gates, ctx.aggs = saved_in, gates, aggs
+        ctx.h_cur, ctx.h_out, ctx.p = h_cur, h_out, scores
+        ctx.param_vals = [p.detach() for p in params]
+        return scores, logits, h_out
+
+    @staticmethod
+    def backward(ctx, dscores, dlogits, dh_out):
+        model, wg, ix = ctx.model, ctx.wg, ctx.ix
+        dev = wg.device
+        n, G = wg.n, len(model.feature_idx)
+        ldh = G * H
+        st = L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        P = ctx.param_vals
+        grads = [torch.zeros_like(p) for p in P]
+        cont = lambda t: None if t is None else t.detach().to(**f32).contiguous()
+        dscores, dlogits, dh_out = cont(dscores), cont(dlogits), cont(dh_out)
+        dh_cur = torch.zeros((n, ldh), **f32)
+        g_hw_node, g_hb_node, g_hw_edge, g_hb_edge = grads[-4], grads[-3], grads[-2], grads[-1]
+        hw_node, hw_edge = P[-4], P[-2]
+        h_cur, h_out = ctx.h_cur, ctx.h_out
+        for g in range(G):
+            col = g * H
+            b = g * _PER_GROUP
+            e_wih, e_whh, n_wih, n_whh = P[b + 6], P[b + 7], P[b + 10], P[b + 11]
+            kx = int(e_wih.shape[1])
+            concat = int(kx == 2 * H)
+            dgi = torch.empty((n, 3 * H), **f32)
+            dgh = torch.empty((n, 3 * H), **f32)
+            dhself = torch.empty((n, H), **f32)
+            gb_e = torch.zeros((2, 3 * H), **f32)
+            gb_d = torch.zeros((2, 3 * H), **f32)
+            L.call('tmpnn_gate_bwd', n, L.ptr(wg.g.src), L.ptr(ctx.gates[g]), L.ptr(h_cur), L.ptr(h_out), ldh, col,
+                   L.ptr(dh_out), L.ptr(dlogits), L.ptr(dscores), L.ptr(ctx.p), L.ptr(hw_edge) + 4 * col,
+                   L.ptr(hw_node) + 4 * col, L.ptr(dgi), L.ptr(dgh), L.ptr(dhself), L.ptr(gb_e), L.ptr(gb_d),
+                   L.ptr(g_hw_edge) + 4 * col, L.ptr(g_hw_node) + 4 * col,
+                   L.ptr(g_hb_edge) if g == 0 else None, L.ptr(g_hb_node) if g == 0 else None, st)
+            grads[b + 8] += gb_e[0]; grads[b + 9] += gb_e[1]
+            grads[b + 12] += gb_d[0]; grads[b + 13] += gb_d[1]
+            # edge cell: rows with src >= 0
+            dx = torch.empty((n, kx), **f32)
+            L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(e_wih), kx, L.ptr(dx), kx, 0, st)
+            L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(e_whh), H, L.ptr(dhself), H, 1, st)
+            xbuf = torch.empty((n, kx), **f32)
+            L.call('tmpnn_aggregate_edges', wg.g.c, ix.c, L.ptr(h_cur), ldh, col, concat, L.ptr(xbuf), st)
+            L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(xbuf), kx, kx, L.ptr(grads[b + 6]), st)
+            L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
+                   L.ptr(grads[b + 7]), st)
+            # node cell: the detection list
+            nd_dev, det_rows = L.ptr(ix.n_dets), L.ptr(ix.det_rows)
+            dagg = torch.zeros((ix.cap_dets, H), **f32)
+            L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(n_wih), H, L.ptr(dagg), H, 0, st)
+            L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(n_whh), H, L.ptr(dhself), H, 1, st)
+            L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(ctx.aggs[g]), H, H, L.ptr(grads[b + 10]), st)
+            L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
+                   L.ptr(grads[b + 11]), st)
+            # through the gather / segmented sum, into the state this step consumed
+            L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx, L.ptr(dagg), L.ptr(dh_cur), ldh, col, st)
+            # new detection rows: through the input transform
+            if ctx.saved_in is not None and ctx.saved_in[3] > 0:
+                xd, new_det, out_rows, nd, n_edge_new, per_group = ctx.saved_in
+                a, mean, var, training = per_group[g]
+                cols = model.feature_idx[g]
+                scratch = torch.empty((2 * nd, H), **f32)
+                L.call('tmpnn_input_bwd', L.ptr(xd), int(xd.shape[1]), int(cols[0]), len(cols), L.ptr(new_det), L.ptr(a),
+                       L.ptr(mean), L.ptr(var), L.ptr(P[b + 2]), L.ptr(P[b + 3]), L.ptr(P[b + 1]), L.ptr(P[b + 4]),
+                       L.ptr(dh_cur), ldh, col, L.ptr(out_rows), nd, n_edge_new, int(training), L.ptr(scratch),
+                       L.ptr(grads[b + 0]), L.ptr(grads[b + 1]), L.ptr(grads[b + 2]), L.ptr(grads[b + 3]),
+                       L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), st)
+        dh_in = dh_cur[:ctx.n_old] if ctx.has_h_in else None
+        return (None, None, None, dh_in) + tuple(grads)
