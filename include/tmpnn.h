@@ -289,6 +289,23 @@ typedef struct tmpnn_seq_state {
   int32_t *fresh;      /* [S] out: 1 if the graph was (re-)initialised this tick (states = None) */
 } tmpnn_seq_state;
 
+/* Hungarian association (utils/graph.py:33-93 driven by :247-249 / :433-435): resets ass, then for every
+ * timestep of each window solves the reference's cost matrix (scores[e,0] for existing edges, 100.0
+ * otherwise; cost == NULL means 1 - score) with scipy.optimize.linear_sum_assignment's algorithm
+ * (rectangular shortest augmenting path, same transposition and tie-breaking; csrc/hungarian.cu) and
+ * keeps pairs with cost <= threshold (0.5 in the drivers).  only_t != 0 runs the single timestep t without
+ * resetting ass (the stand-alone hungarian() of utils/graph.py:33).  max_dets bounds the detection rows
+ * of one window; scratch holds tmpnn_hungarian_scratch_bytes(num_seqs, max_dets) bytes. */
+size_t tmpnn_hungarian_scratch_bytes(int num_seqs, int max_dets);
+int tmpnn_graph_associate_hungarian(const tmpnn_graph *g, const tmpnn_index *ix, const float *cost,
+                                    const int32_t *active, int max_dets, int only_t, int t, float threshold,
+                                    void *scratch, void *stream);
+
+/* The assignment solver alone: `batch` independent nr x nc fp32 cost matrices -> col_of_row[batch][nr]
+ * (-1 for unassigned rows of a tall matrix); equals scipy.optimize.linear_sum_assignment(C). */
+size_t tmpnn_lsap_scratch_bytes(int batch, int nr, int nc);
+int tmpnn_lsap_solve(const float *cost, int nr, int nc, int batch, int32_t *col_of_row, void *scratch, void *stream);
+
 /* update_graph steps 2-4 (utils/graph.py:270-327) and initialize_graph (utils/graph.py:96-186)
  * for every sequence at timestep t = *t_dev.
  *  Append: active set (mode 0: detection && ass == -1 && p >= 0.5; mode 1 (train):

@@ -45,11 +45,11 @@ def _fix(scores, y_pred, tp):
     return scores
 
 
-NON_HUNG = [n for n in golden_names('infer') if 'hung' not in n]
+INFER = golden_names('infer')
 
 
 @pytest.mark.parametrize('tensor', [False, True], ids=['fma', 'tcgen05'])
-@pytest.mark.parametrize('name', NON_HUNG)
+@pytest.mark.parametrize('name', INFER)
 def test_infer_free_running(name, tensor):
     """tensor=False: fp32 FMA kernel; tensor=True: tcgen05 kernel (3-term fp16 split) -- same 1e-4 bar."""
     from trackmpnn_b200.utils.graph import initialize_graph, update_graph, prune_graph, decode_tracks
@@ -88,7 +88,7 @@ def test_infer_free_running(name, tensor):
                 states = None
             else:
                 y_pred, feats, node_adj, edge_adj, labels = update_graph(
-                    node_adj, labels, scores, y_pred, X, y, t_cur, use_hungraian=False, mode='test', cuda=True)
+                    node_adj, labels, scores, y_pred, X, y, t_cur, use_hungraian=m['hungarian'], mode='test', cuda=True)
             np.testing.assert_array_equal(y_pred.cpu().numpy(), gold.get(s, 'y_pred'), err_msg=f'step {s}')
             np.testing.assert_array_equal(feats.cpu().numpy(), gold.get(s, 'feats'))
             np.testing.assert_array_equal(_dense(node_adj), _ref_dense(gold, s))
@@ -107,7 +107,7 @@ def test_infer_free_running(name, tensor):
                 np.testing.assert_array_equal(labels.cpu().numpy(), gold.get(s, 'prune_labels'))
             t_upto = t_end if t_cur == t_end - 1 else t_cur - m['cur_win_size'] + 2
             y_pred, y_out, states, node_adj, labels, scores = decode_tracks(
-                states, node_adj, labels, scores, y_pred, y_out, t_upto, m['ret_win_size'], use_hungraian=False, cuda=True)
+                states, node_adj, labels, scores, y_pred, y_out, t_upto, m['ret_win_size'], use_hungraian=m['hungarian'], cuda=True)
             np.testing.assert_array_equal(y_pred.cpu().numpy(), gold.get(s, 'dec_y_pred'), err_msg=f'decode step {s}')
             np.testing.assert_array_equal(y_out, gold.get(s, 'y_out'), err_msg=f'y_out step {s}')
             np.testing.assert_array_equal(_dense(node_adj), _ref_dense(gold, s, 'dec_'))

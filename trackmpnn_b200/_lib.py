@@ -95,6 +95,10 @@ _PROTOS = {
     'tmpnn_coo_from_edges': ([_VP, _VP, _VP, _I, _I, _VP, _VP, C.c_int64, _VP, _VP], _I),
     'tmpnn_edges_from_coo': ([_VP, _VP, C.c_int64, _I, _VP, _VP, _VP], _I),
     'tmpnn_graph_associate': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP], _I),
+    'tmpnn_hungarian_scratch_bytes': ([_I, _I], C.c_size_t),
+    'tmpnn_graph_associate_hungarian': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, C.c_float, _VP, _VP], _I),
+    'tmpnn_lsap_scratch_bytes': ([_I, _I, _I], C.c_size_t),
+    'tmpnn_lsap_solve': ([_VP, _I, _I, _I, _VP, _VP, _VP], _I),
     'tmpnn_graph_append_scratch_ints': ([_I, _I], C.c_size_t),
     'tmpnn_graph_append': ([C.POINTER(Graph), C.POINTER(Frames), C.POINTER(SeqState), _VP, _I, _I, _I, _VP, _I,
                             _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
@@ -161,7 +165,7 @@ KERNELS_PER_CALL = {
     'tmpnn_graph_compact': 4,
     'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_input_bwd': 1, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
-    'tmpnn_loss_focal_bwd': 1,
+    'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }
 
 

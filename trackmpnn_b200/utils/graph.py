@@ -141,13 +141,26 @@ def update_graph(node_adj, labels, scores, y_pred, X, y, t, use_hungraian=True, 
             _place_adj(wg.adjacency(True), cuda), out_labels)
 
 
+def _hungarian(wg, scores, only_t=False, t=0, threshold=0.5):
+    """tmpnn_graph_associate_hungarian on a single-slab graph; the cost column is scores[:, 0] as the
+    reference reads it (utils/graph.py:81)."""
+    dev = wg.device
+    ix = wg.index()
+    nd = max(1, int(ix.n_dets.item()))
+    cost = scores.detach().to(device=dev, dtype=torch.float32)[:, 0].contiguous()
+    nbytes = int(L.lib().tmpnn_hungarian_scratch_bytes(1, nd))
+    scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+    L.call('tmpnn_graph_associate_hungarian', wg.g.c, ix.c, L.ptr(cost), None, nd, int(only_t), int(t), float(threshold),
+           L.ptr(scratch), L.stream())
+    wg.g.check_status()
+
+
 def _associate(wg, scores, use_hungarian, mode):
     if mode == 'train':
         L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 1, None, L.stream())
         wg.g.check_status()
     elif use_hungarian:
-        raise NotImplementedError('Hungarian association is not built yet (SURVEY.md section 8f-1); '
-                                  'pass use_hungraian=False (the drivers\' default, --hungarian off)')
+        _hungarian(wg, scores)
     else:
         L.call('tmpnn_graph_associate', wg.g.c, wg.index().c, 0, None, L.stream())
 
@@ -223,4 +236,11 @@ def decode_tracks(states, node_adj, labels, scores, y_pred, y_out, t_upto, ret_w
 
 
 def hungarian(node_adj, scores, y_pred, t, threshold=0.5):
-    raise NotImplementedError('Hungarian association is not built yet (SURVEY.md section 8f-1)')
+    """Reference ``utils/graph.py:33-93``: optimal assignment for the detections of timestep t only;
+    returns ``y_pred`` with the new associations written into column 2 (earlier ones are kept)."""
+    wg = WindowGraph.from_tensors(torch.as_tensor(y_pred), node_adj, None, None)
+    _hungarian(wg, torch.as_tensor(scores), only_t=True, t=int(t), threshold=threshold)
+    out = wg.y_pred()
+    if isinstance(y_pred, np.ndarray):
+        return out.cpu().numpy().astype(y_pred.dtype)
+    return out.to(device=y_pred.device, dtype=y_pred.dtype)
