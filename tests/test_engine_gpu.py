@@ -49,6 +49,8 @@ def _sequences(seeds, dataset='kitti', gap=()):
     dict(seeds=[71, 72], msg_type='diff', ret=0, graph=False, gap=(), stock=True),
     dict(seeds=[30, 34, 48, 58, 65], msg_type='diff', ret=0, graph=False, gap=(), tensor=True),
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True),
+    dict(seeds=[108, 84, 77, 100, 72, 32, 56], msg_type='diff', ret=0, graph=True, gap=(), hungarian=True),
+    dict(seeds=[84, 100, 48, 125, 56], msg_type='diff', ret=2, graph=False, gap=(), hungarian=True),
 ])
 def test_engine_matches_oracle(cfg):
     from trackmpnn_b200.engine import TrackEngine
@@ -58,12 +60,12 @@ def test_engine_matches_oracle(cfg):
     params = _params(model)
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],
-                      tensor_cores=cfg.get('tensor', False))
+                      tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False))
     outs, stats = eng.run().results()
     tot_e = tot_f = 0
     for (X, y), got in zip(seqs, outs):
         want, st = run_infer(params, X, y, msg_type=cfg['msg_type'], cur_win_size=5, ret_win_size=cfg['ret'],
-                             record_margin=True)
+                             record_margin=True, use_hungarian=cfg.get('hungarian', False))
         assert stock or st['margin'] > 1e-4, 'decision margin too small for a meaningful bit-exact comparison; change the seed'
         np.testing.assert_array_equal(got, want[:, 1])
         tot_e += st['edge_updates']; tot_f += st['frames']

@@ -35,7 +35,7 @@ def worst_case_rows(frame_counts, window):
 
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
-                 use_cuda_graph=True, tensor_cores='auto'):
+                 use_cuda_graph=True, tensor_cores='auto', use_hungarian=False):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays."""
         self.model = model
         self.dev = device if device is not None else next(model.parameters()).device
@@ -91,6 +91,13 @@ class TrackEngine:
         self.det_updates = torch.zeros(1, dtype=torch.int64, device=dev)
         self.frames_done = torch.zeros(1, dtype=torch.int64, device=dev)
         self.use_cuda_graph = use_cuda_graph
+        # --hungarian (infer.py:143): optimal assignment per timestep instead of the greedy arg-max
+        self.use_hungarian = bool(use_hungarian)
+        self.max_dets = max_dets
+        self.hung_scratch = None
+        if self.use_hungarian:
+            nbytes = int(L.lib().tmpnn_hungarian_scratch_bytes(self.S, max_dets))
+            self.hung_scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
         diff = all(g.msg_type == 'diff' for g in model.factor_grus)
         # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise
         self.tensor = diff and (self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
@@ -150,17 +157,29 @@ class TrackEngine:
         # update_graph re-associates from the previous scores before it appends (utils/graph.py:251-268).
         # Inside the loop that result is carried over from decode_tracks (same scores, and deletion
         # cannot change a survivor's association); after the initial forward it is computed here.
-        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), L.stream())
+        self._associate(g)
+
+    def _associate(self, g):
+        if self.use_hungarian:
+            L.call('tmpnn_graph_associate_hungarian', g.c, self.index.c, None, L.ptr(self.st['active']), self.max_dets, 0, 0,
+                   0.5, L.ptr(self.hung_scratch), L.stream())
+        else:
+            L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), L.stream())
 
     def _tick(self):
         """One iteration of infer.py:60-87 for every sequence at t = *t_dev, then t += 1."""
         g, go = self.ga, self.gb
         st = L.stream()
+        if self.use_hungarian:
+            # update_graph re-solves the assignment on the graph decode_tracks left behind (utils/graph.py:247-249);
+            # unlike the greedy choice it is not invariant under the deletion, so it is recomputed here
+            self.index.build(g, self.st['active'])
+            self._associate(g)
         L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
                L.ptr(self.h_cur), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
         self._forward(g, self.h_cur, self.h_alt)
-        L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), st)
+        self._associate(g)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
                L.ptr(self.keep), L.ptr(self.decode_scratch), st)
