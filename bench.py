@@ -231,7 +231,9 @@ def main():
     k_edges = sum(int(p[2].item()) for p in prof)
     hbm_peak, peak_src = measured_peaks()
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roof = {'kernel': 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)', 'bound': 'hbm',
+    kname = ('k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'
+             if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
+    roof = {'kernel': kname, 'bound': 'hbm',
             'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
             'peak_source': peak_src, 'launches_timed': len(prof), 'avg_launch_ms': k_ms / max(1, len(prof)),
             'share_of_step': k_ms / ms if ms > 0 else None,

@@ -57,6 +57,7 @@ typedef enum tmpnn_status {
 #define TMPNN_FLAG_MULTI_GT_EDGE 16 /* "More than one GT edge from same node!" (utils/graph.py:243) */
 #define TMPNN_FLAG_WALK_CAPACITY 32 /* more detection rows in one window than the decode walk holds */
 #define TMPNN_FLAG_TC_TIMEOUT 64    /* tensor-core kernel: an mbarrier wait timed out (results invalid) */
+#define TMPNN_FLAG_UNSTRUCTURED 256 /* tmpnn_index_build_structured: the window graph is not a chain of dense edge blocks */
 #define TMPNN_FLAG_TC_RANGE 128     /* tensor-core kernel: |value| > 6e4 would overflow the fp16 split; use the FMA path */
 
 typedef struct tmpnn_graph {
@@ -139,6 +140,15 @@ int tmpnn_input_bn_relu_linear2(const float *a, const float *mean, const float *
 size_t tmpnn_index_scratch_ints(int num_seqs, int cap_rows, int cap_dets);
 /* active (may be NULL): sequences with active[s] == 0 are indexed as empty (they sit out this tick). */
 int tmpnn_index_build(const tmpnn_graph *g, const tmpnn_index *ix, const int32_t *active, void *stream);
+
+/* Same index for window graphs that were only ever changed by tmpnn_graph_append and the deletion of
+ * tmpnn_graph_decode (the TrackEngine loop; never tmpnn_graph_prune_mask): every edge block is then a
+ * dense [sources x detections-of-the-next-frame] matrix and the incidence lists follow from the block
+ * boundaries -- no atomics, no sort, coalesced writes only (csrc/graph_index.cu).  A graph that breaks
+ * the structure raises TMPNN_FLAG_UNSTRUCTURED.  scratch2: tmpnn_index_structured_scratch_bytes(). */
+size_t tmpnn_index_structured_scratch_bytes(int num_seqs, int cap_dets);
+int tmpnn_index_build_structured(const tmpnn_graph *g, const tmpnn_index *ix, const int32_t *active, void *scratch2,
+                                 void *stream);
 
 /* ---- K1: aggregation (models/layers.py:90-95,103) -------------------------------------- */
 

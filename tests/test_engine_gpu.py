@@ -76,3 +76,32 @@ def test_engine_matches_oracle(cfg):
     for a, b in zip(outs, outs2):
         np.testing.assert_array_equal(a, b)
     assert stats2 == stats
+
+
+@pytest.mark.parametrize('ret', [0, 2])
+def test_structured_index_equals_general_index(ret):
+    """The engine's sort-free index (incidence lists derived from the block boundaries) is entry for
+    entry the general one (atomic fill + per-segment sort) on graphs in the middle of a run."""
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.device_graph import SlabIndex
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    seqs = _sequences([30, 34, 48, 58, 65, 72, 77], gap=(48,))
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=ret, use_cuda_graph=False)
+    for ticks in (1, 3, 6, 9):
+        eng.run(max_ticks=ticks)
+        torch.cuda.synchronize()
+        g = eng.ga
+        a = SlabIndex(g, eng.index.cap_dets, eng.index.cap_inc)
+        b = SlabIndex(g, eng.index.cap_dets, eng.index.cap_inc)
+        a.build(g, None, structured=False)
+        b.build(g, None, structured=True)
+        torch.cuda.synchronize()
+        g.check_status()
+        nd = int(a.n_dets.item())
+        assert nd == int(b.n_dets.item()) and nd > 0
+        np.testing.assert_array_equal(a.det_rows[:nd].cpu().numpy(), b.det_rows[:nd].cpu().numpy())
+        sa, sb = a.seg_ptr[:2 * nd + 1].cpu().numpy(), b.seg_ptr[:2 * nd + 1].cpu().numpy()
+        np.testing.assert_array_equal(sa, sb)
+        np.testing.assert_array_equal(a.inc[:sa[-1]].cpu().numpy(), b.inc[:sb[-1]].cpu().numpy())
+        assert sa[-1] == 2 * int(a.n_edges.item())

@@ -206,6 +206,139 @@ __global__ void __launch_bounds__(128) k_sort_segments(const int32_t* __restrict
   }
 }
 
+// ---- structured build: incidence CSR from the block structure, no atomics, no sort ----------
+// A window graph that only ever grew by tmpnn_graph_append and shrank by tmpnn_graph_decode's deletion
+// (whole prefixes, plus whole source runs of later edge blocks) is a chain of segments
+//   [dets f0] [edges -> f1] [dets f1] [edges -> f2] [dets f2] ...
+// where the edge segment in front of a detection segment of Nt rows is a dense [A x Nt] matrix:
+// row e0 + a Nt + j joins source a (constant along the run) to detection d0 + j (utils/graph.py:283-301;
+// Appendix A.4/A.5 of SURVEY.md).  Every incidence list is then a formula: the past edges of detection
+// d0 + j are e0 + a Nt + j (a ascending), the future edges of a source are its runs in ascending
+// segment order.  The builder finds the segment boundaries from ts, derives the counts, scans them and
+// writes inc with coalesced stores; it verifies the structure as it goes (TMPNN_FLAG_UNSTRUCTURED).
+constexpr int MAXSEG = 128;  // segments per slab (2 per frame in the window)
+constexpr int MAXE = 64;     // edge segments per slab
+
+struct SlabSegs {            // per slab, in global scratch
+  int32_t nseg;              // number of segments
+  int32_t start[MAXSEG + 1]; // slab-local first row of segment q; start[nseg] = n_rows
+  int32_t eord[MAXSEG];      // ordinal among the edge segments, -1 for detection segments
+};
+
+__global__ void __launch_bounds__(1024) k_block_segments(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                         const int32_t* __restrict__ ts, int cap_rows,
+                                                         SlabSegs* __restrict__ segs, int32_t* __restrict__ status) {
+  __shared__ int32_t bnd[MAXSEG + 2];
+  __shared__ int nb;
+  const int s = blockIdx.x;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  const int32_t* t = ts + (size_t)s * cap_rows;
+  if (threadIdx.x == 0) nb = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // a boundary in front of row i: first row, or the timestamp changes (edge rows all carry -1)
+    if (i == 0 || t[i] != t[i - 1]) {
+      const int k = atomicAdd(&nb, 1);
+      if (k < MAXSEG + 1) bnd[k] = i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SlabSegs& o = segs[s];
+    int m = nb;
+    if (m > MAXSEG) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
+    for (int a = 1; a < m; ++a) {  // insertion sort of <= 128 positions
+      const int v = bnd[a];
+      int b = a - 1;
+      while (b >= 0 && bnd[b] > v) { bnd[b + 1] = bnd[b]; --b; }
+      bnd[b + 1] = v;
+    }
+    int ne = 0;
+    for (int q = 0; q < m; ++q) {
+      o.start[q] = bnd[q];
+      const bool edge = t[bnd[q]] < 0;
+      o.eord[q] = edge ? ne : -1;
+      if (edge) ++ne;
+    }
+    if (ne > MAXE) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
+    o.nseg = m;
+    o.start[m] = n;
+  }
+}
+
+// counts: cnt[2k] = past edges, futlen[k][eord] = run length of detection k in edge segment eord
+__global__ void __launch_bounds__(256) k_block_degree(const SlabSegs* __restrict__ segs, const int32_t* __restrict__ src,
+                                                      int cap_rows, const int32_t* __restrict__ det_of_row,
+                                                      const int32_t* __restrict__ n_dets, int32_t* __restrict__ cnt,
+                                                      int32_t* __restrict__ futlen, int32_t* __restrict__ status) {
+  if (*n_dets == 0) return;
+  const int s = blockIdx.y;
+  const SlabSegs& sg = segs[s];
+  const size_t base = (size_t)s * cap_rows;
+  for (int q = 0; q < sg.nseg; ++q) {
+    if (sg.eord[q] < 0) continue;
+    const int e0 = sg.start[q], d0 = sg.start[q + 1], d1 = q + 2 <= sg.nseg ? sg.start[q + 2] : d0;
+    const int nt = d1 - d0;
+    if (nt <= 0 || q + 1 >= sg.nseg || sg.eord[q + 1] >= 0 || (d0 - e0) % nt != 0) {
+      if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, TMPNN_FLAG_UNSTRUCTURED);
+      continue;
+    }
+    const int A = (d0 - e0) / nt;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += gridDim.x * blockDim.x)
+      cnt[2 * det_of_row[base + d0 + j]] = A;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < A; a += gridDim.x * blockDim.x) {
+      const int d = src[base + e0 + (size_t)a * nt];
+      futlen[(size_t)det_of_row[base + d] * MAXE + sg.eord[q]] = nt;
+    }
+  }
+}
+
+// per detection: run lengths -> offsets inside its future list, total -> cnt[2k+1]
+__global__ void __launch_bounds__(256) k_block_futoff(const int32_t* __restrict__ n_dets, int32_t* __restrict__ futlen,
+                                                      int32_t* __restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *n_dets) return;
+  int32_t* f = futlen + (size_t)k * MAXE;
+  int acc = 0;
+  for (int b = 0; b < MAXE; ++b) {
+    const int v = f[b];
+    f[b] = acc;
+    acc += v;
+  }
+  cnt[2 * k + 1] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_block_fill(const SlabSegs* __restrict__ segs, const int32_t* __restrict__ src,
+                                                    const int32_t* __restrict__ dst, int cap_rows,
+                                                    const int32_t* __restrict__ det_of_row, const int32_t* __restrict__ n_dets,
+                                                    const int32_t* __restrict__ futoff, const int32_t* __restrict__ seg_ptr,
+                                                    int32_t* __restrict__ inc, int32_t* __restrict__ status) {
+  if (*n_dets == 0) return;
+  const int s = blockIdx.y;
+  const SlabSegs& sg = segs[s];
+  const size_t base = (size_t)s * cap_rows;
+  int bad = 0;
+  for (int q = 0; q + 1 < sg.nseg; ++q) {
+    if (sg.eord[q] < 0 || sg.eord[q + 1] >= 0) continue;
+    const int e0 = sg.start[q], d0 = sg.start[q + 1], nt = sg.start[q + 2] - d0;
+    if (nt <= 0 || (d0 - e0) % nt != 0) continue;
+    const int A = (d0 - e0) / nt, ne = d0 - e0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ne; p += gridDim.x * blockDim.x) {
+      // past lists, written detection-major (consecutive threads -> consecutive slots)
+      const int j = p / A, a = p % A;
+      inc[seg_ptr[2 * det_of_row[base + d0 + j]] + a] = (int32_t)(base + e0 + (size_t)a * nt + j);
+      // future lists, written in row order (a run is one contiguous stretch of its source's list)
+      const int ar = p / nt, jr = p % nt;
+      const size_t e = base + e0 + p;
+      const int sd = src[base + e0 + (size_t)ar * nt];
+      if (src[e] != sd || dst[e] != d0 + jr) bad = 1;
+      const int ks = det_of_row[base + sd];
+      inc[seg_ptr[2 * ks + 1] + futoff[(size_t)ks * MAXE + sg.eord[q]] + jr] = (int32_t)e;
+    }
+  }
+  if (bad) atomicOr(status, TMPNN_FLAG_UNSTRUCTURED);
+}
+
 }  // namespace
 
 extern "C" size_t tmpnn_index_scratch_ints(int num_seqs, int cap_rows, int cap_dets) {
@@ -242,6 +375,48 @@ extern "C" int tmpnn_index_build(const tmpnn_graph* g, const tmpnn_index* ix, co
                                  ix->inc);
   TMPNN_LAUNCH_CHECK();
   k_sort_segments<<<TMPNN_SM_COUNT * 8, 128, 0, st>>>(ix->n_dets, ix->seg_ptr, ix->inc, g->status);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" size_t tmpnn_index_structured_scratch_bytes(int num_seqs, int cap_dets) {
+  return (size_t)num_seqs * sizeof(SlabSegs) + (size_t)cap_dets * MAXE * sizeof(int32_t) + 64;
+}
+
+extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_index* ix, const int32_t* active,
+                                            void* scratch2, void* stream) {
+  TMPNN_REQUIRE(g && ix && ix->scratch && scratch2, "null argument");
+  TMPNN_REQUIRE(((uintptr_t)scratch2 & 3) == 0, "scratch must be 4-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = g->num_seqs;
+  const int nblk = tmpnn_div_up(g->cap_rows, ROWS_PER_BLOCK);
+  int32_t* blk = ix->scratch;
+  int32_t* cnt = blk + (size_t)S * nblk;
+  int32_t* sums = cnt + (2 * (size_t)ix->cap_dets + 4);
+  SlabSegs* segs = (SlabSegs*)scratch2;
+  int32_t* futlen = (int32_t*)((unsigned char*)scratch2 + (size_t)S * sizeof(SlabSegs));
+
+  dim3 grid_rows(nblk, S);
+  k_count_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk);
+  TMPNN_LAUNCH_CHECK();
+  k_scan_det_blocks<<<1, 1024, 0, st>>>(g->n_rows, active, S, nblk, blk, ix->seq_det_ptr, ix->tile_ptr, ix->tile128_ptr, ix->n_dets,
+                                        ix->n_edges, ix->cap_dets, ix->cap_inc, g->status);
+  TMPNN_LAUNCH_CHECK();
+  k_write_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk, ix->n_dets, ix->det_rows,
+                                          ix->det_of_row, cnt);
+  TMPNN_LAUNCH_CHECK();
+  k_block_segments<<<S, 1024, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, segs, g->status);
+  TMPNN_LAUNCH_CHECK();
+  TMPNN_CUDA_TRY(cudaMemsetAsync(futlen, 0, (size_t)ix->cap_dets * MAXE * sizeof(int32_t), st));
+  dim3 grid_d(4, S);
+  k_block_degree<<<grid_d, 256, 0, st>>>(segs, g->src, g->cap_rows, ix->det_of_row, ix->n_dets, cnt, futlen, g->status);
+  TMPNN_LAUNCH_CHECK();
+  k_block_futoff<<<tmpnn_div_up(ix->cap_dets, 256), 256, 0, st>>>(ix->n_dets, futlen, cnt);
+  TMPNN_LAUNCH_CHECK();
+  TMPNN_CUDA_TRY(scan_exclusive(cnt, ix->seg_ptr, ix->n_dets, 2, 0, 2 * (long long)ix->cap_dets, sums, st));
+  dim3 grid_e(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 8), 64)), S);
+  k_block_fill<<<grid_e, 256, 0, st>>>(segs, g->src, g->dst, g->cap_rows, ix->det_of_row, ix->n_dets, futlen, ix->seg_ptr, ix->inc,
+                                       g->status);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

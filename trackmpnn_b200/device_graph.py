@@ -72,8 +72,16 @@ class SlabIndex:
     def c(self):
         return C.byref(self._c)
 
-    def build(self, graph, active=None):
-        L.call('tmpnn_index_build', graph.c, self.c, L.ptr(active), L.stream())
+    def build(self, graph, active=None, structured=False):
+        """structured=True: the graph only ever changed through tmpnn_graph_append / tmpnn_graph_decode
+        (TrackEngine), so the incidence lists follow from the block boundaries (no atomics, no sort)."""
+        if structured:
+            if getattr(self, '_scratch2', None) is None:
+                nbytes = int(L.lib().tmpnn_index_structured_scratch_bytes(graph.num_seqs, self.cap_dets))
+                self._scratch2 = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=graph.device)
+            L.call('tmpnn_index_build_structured', graph.c, self.c, L.ptr(active), L.ptr(self._scratch2), L.stream())
+        else:
+            L.call('tmpnn_index_build', graph.c, self.c, L.ptr(active), L.stream())
 
 
 class FrameTable:

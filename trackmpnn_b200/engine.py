@@ -35,7 +35,7 @@ def worst_case_rows(frame_counts, window):
 
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
-                 use_cuda_graph=True, tensor_cores='auto', use_hungarian=False):
+                 use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays."""
         self.model = model
         self.dev = device if device is not None else next(model.parameters()).device
@@ -91,6 +91,8 @@ class TrackEngine:
         self.det_updates = torch.zeros(1, dtype=torch.int64, device=dev)
         self.frames_done = torch.zeros(1, dtype=torch.int64, device=dev)
         self.use_cuda_graph = use_cuda_graph
+        # the engine's graphs are chains of dense edge blocks: the index is derived from the block boundaries
+        self.structured_index = bool(structured_index)
         # --hungarian (infer.py:143): optimal assignment per timestep instead of the greedy arg-max
         self.use_hungarian = bool(use_hungarian)
         self.max_dets = max_dets
@@ -123,7 +125,7 @@ class TrackEngine:
                    L.ptr(bn.weight.detach()), L.ptr(bn.bias.detach()), L.ptr(lin2.weight.detach()),
                    L.ptr(lin2.bias.detach()), L.ptr(h_in), self.ldh, grp * H, L.ptr(self.new_rows),
                    L.ptr(self.n_new), 0, st)
-        self.index.build(g, self.st['active'])
+        self.index.build(g, self.st['active'], structured=self.structured_index)
         packs = F_.packed_cells(model)
         tc = F_.packed_cells_tc(model) if self.tensor else None
         for grp in range(self.G):
@@ -173,7 +175,7 @@ class TrackEngine:
         if self.use_hungarian:
             # update_graph re-solves the assignment on the graph decode_tracks left behind (utils/graph.py:247-249);
             # unlike the greedy choice it is not invariant under the deletion, so it is recomputed here
-            self.index.build(g, self.st['active'])
+            self.index.build(g, self.st['active'], structured=self.structured_index)
             self._associate(g)
         L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
                L.ptr(self.h_cur), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
