@@ -48,6 +48,9 @@ def parse():
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU-baseline sample (0 = auto)')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-train', action='store_true')
+    ap.add_argument('--train-chunks', type=int, default=6, help='BPTT chunks timed by the training leg')
+    ap.add_argument('--train-dets', type=int, default=40)
     return ap.parse_args()
 
 
@@ -156,6 +159,84 @@ def run_reference(a, rank):
            'e2e': {'value': val, 'unit': 'edge-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
     print(json.dumps(out), flush=True)
+
+
+# ---- training leg: BASELINE.json configs[1] (KITTI-shaped --category=All, ~40 dets/frame, forward + backward) ----
+def train_chunk_cuda(model, opt, X, y):
+    """One chunk of the reference's train.py:65-134 through the drop-in modules (tp_classifier on):
+    teacher-forced graph growth, TrackMPNN.forward per step (autograd Function), CE + BCE, backward, Adam."""
+    import torch
+    from trackmpnn_b200.utils.graph import initialize_graph, update_graph
+    from trackmpnn_b200.models.loss import create_targets, CELoss, FocalLoss
+    ce, fn, fe = CELoss(), FocalLoss(gamma=0), FocalLoss(gamma=0)
+    edges = 0
+
+    def losses(scores, logits, y_pred, labels, node_adj):
+        nonlocal edges
+        idx_edge = torch.nonzero((y_pred[:, 0] == -1))[:, 0]
+        idx_node = torch.nonzero((y_pred[:, 0] != -1))[:, 0]
+        edges += int(idx_edge.numel())
+        targets = create_targets(labels, node_adj, idx_node)
+        lc = ce(logits, targets, node_adj, idx_node)
+        lf = fn(scores[idx_node, 0], targets[idx_node]) + fe(scores[idx_edge, 0], targets[idx_edge])
+        return torch.cat((1 - scores, scores), dim=1), lc + lf
+
+    opt.zero_grad()
+    y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, t_st=0, mode='train', cuda=True)
+    scores, logits, states, _ = model(feats, None, node_adj, edge_adj)
+    scores, loss = losses(scores, logits, y_pred, labels, node_adj)
+    for t_cur in range(t_st, t_end):
+        y_pred, feats, node_adj, edge_adj, labels = update_graph(node_adj, labels, scores, y_pred, X, y, t_cur,
+                                                                 use_hungraian=False, mode='train', cuda=True)
+        scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+        scores, l = losses(scores, logits, y_pred, labels, node_adj)
+        loss = loss + l
+    loss.backward()
+    opt.step()
+    return edges, float(loss.item())
+
+
+def run_train_leg(a, dev):
+    import torch
+    from trackmpnn_b200 import synth
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories('kitti'), 64, 0, 'diff').to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)  # train.py:329
+
+    def chunk(seed):
+        ts = synth.train_chunk_timestamps(seed, 5, 2)
+        Xn, yn = synth.make_sequence(seed, None, a.train_dets, 'kitti', timestamps=ts)
+        return Xn, yn
+
+    data = [chunk(1000 + i) for i in range(a.train_chunks + 2)]
+    dd = [(torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)) for Xn, yn in data]
+    for X, y in dd[:2]:
+        train_chunk_cuda(model, opt, X, y)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    edges = 0
+    for X, y in dd[2:]:
+        e, _ = train_chunk_cuda(model, opt, X, y)
+        edges += e
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {'workload': f'C2 kitti-shaped training chunks (5 frames + 2 skip frames, ~Poisson({a.train_dets}) dets/frame, F=8, '
+                       f'tp_classifier, teacher forcing, BPTT over all steps, CE+BCE, Adam), drop-in modules, 1 chunk at a time',
+           'value': edges / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': a.train_chunks / dt,
+           'ms_per_chunk': 1e3 * dt / a.train_chunks, 'edge_rows_per_chunk': edges // max(1, a.train_chunks)}
+    if not a.skip_cpu:
+        from oracle import train_ref as T, trackmpnn_oracle as O
+        params = O.init_params('2d', 3, 64, 'diff', seed=5)
+        Xn, yn = data[2]
+        t0 = time.perf_counter()
+        r = T.train_chunk(params, Xn, yn)
+        dtc = time.perf_counter() - t0
+        ec = sum(int((g.ts < 0).sum()) for g in r['graphs'])
+        out['cpu_baseline'] = {'value': ec / dtc, 'unit': 'edge-updates/s', 'cores': os.cpu_count(), 'kind': 'port',
+                               'seconds': dtc, 'sample': '1 chunk of the workload (oracle/train_ref.py: torch fp32 ops on '
+                                                         'edge lists + autograd, no optimizer step)'}
+    return out
 
 
 def main():
@@ -277,6 +358,10 @@ def main():
                'sample': f'1 sequence of the workload, first {frames_cap} frames (oracle port: numpy BLAS threads for '
                          f'the GEMMs, one thread for graph bookkeeping)'}
 
+    train = None
+    if rank == 0 and world == 1 and not a.skip_train:
+        train = run_train_leg(a, dev)
+
     if rank == 0:
         sec = ms * 1e-3
         out = {'metric': 'edge_updates_per_s', 'value': tot_edges / sec, 'unit': 'edge-updates/s',
@@ -287,7 +372,7 @@ def main():
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
                           'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
-               'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk}
+               'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'train': train}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
