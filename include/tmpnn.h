@@ -163,6 +163,16 @@ int tmpnn_aggregate_dets(const tmpnn_graph *g, const tmpnn_index *ix, const floa
 int tmpnn_aggregate_edges(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
                           int concat, float *support, void *stream);
 
+/* Attention heads (models/layers.py:7-46, 105-112; --num-att-heads > 0), eval mode: for head `head` of
+ * `num_heads`, e_j = LeakyReLU_0.2(a . |W_att^T h[src_j] - W_att^T h[dst_j]|) per edge row, softmax over the
+ * edges incident to each detection, agg[k] (+)= (1/num_heads) sum_j alpha_j (+-1) h[j] -- the node GRU's input
+ * in place of tmpnn_aggregate_dets.  Call once per head with head = 0 first.  hatt: cap_dets*64 floats,
+ * escore: S*cap_rows floats (scratch); alpha (nullable): cap_inc floats, the attention weight of every
+ * incidence entry of this head (what the reference returns as a dense N x N matrix). */
+int tmpnn_gat_aggregate_dets(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
+                             const float *w_att, const float *a, int head, int num_heads, float *hatt,
+                             float *escore, float *agg, float *alpha, void *stream);
+
 /* ---- K2+K3: one message-passing step (models/layers.py:84-116 + track_mpnn.py:73-75) ---- */
 
 /* For feature group `group` (columns [64 group, 64 group + 64) of h): every edge row runs the

@@ -215,8 +215,56 @@ def aggregate(h, g, msg_type='diff'):
     return xs.astype(np.float32), agg[d].astype(np.float32), e, d
 
 
+def gat_heads(params, gi):
+    """Attention heads of feature group gi present in a state_dict (``factor_grus.gi.gat.k.{W_att,a}``)."""
+    k = 0
+    while f'factor_grus.{gi}.gat.{k}.W_att' in params:
+        k += 1
+    return k
+
+
+def gat_support(h, g, w_att, a, alpha=0.2):
+    """One ``GraphAttentionLayer.forward`` in eval mode (``models/layers.py:26-43``) on the edge list:
+    e_j = LeakyReLU(a . |W h[src_j] - W h[dst_j]|) per edge row, softmax over the edges incident to each
+    detection, h'_d = sum_j alpha_dj (+1 if d is the source of j else -1) h_j.
+    Returns (support for every row [N, H] -- zero off the detection rows --, e [N], per-detection
+    dict {row: (incident edge rows, alpha)})."""
+    n = g.n
+    h_att = (h @ w_att).astype(np.float32)
+    e_rows = np.nonzero(g.ts < 0)[0]
+    ev = np.zeros(n, np.float32)
+    if e_rows.size:
+        d = np.abs(h_att[g.src[e_rows]] - h_att[g.dst[e_rows]]).astype(np.float32)
+        v = (d @ a.reshape(-1)).astype(np.float32)
+        ev[e_rows] = np.where(v > 0, v, np.float32(alpha) * v)
+    past, fut = _segments(g)
+    out = np.zeros_like(h)
+    att = {}
+    for r in np.nonzero(g.ts >= 0)[0]:
+        inc = np.asarray(sorted(past.get(int(r), []) + fut.get(int(r), [])), np.int64)
+        if inc.size == 0:
+            continue
+        x = ev[inc]
+        w = np.exp(x - x.max(), dtype=np.float32)
+        w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+        sign = np.where(g.src[inc] == r, 1.0, -1.0).astype(np.float32)
+        out[r] = ((w * sign)[:, None] * h[inc]).sum(0, dtype=np.float32)
+        att[int(r)] = (inc, w)
+    return out, ev, att
+
+
+def dense_attention(att, n):
+    """The reference's dense [N, N] attention of one head: softmax rows of the detections, and the
+    uniform 1/N rows its masked softmax produces for rows without incident edges."""
+    A = np.full((n, n), np.float32(1.0) / np.float32(n), np.float32)
+    for r, (inc, w) in att.items():
+        A[r] = 0
+        A[r, inc] = w
+    return A
+
+
 def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, msg_type='diff',
-            training=False, update_running_stats=True):
+            training=False, update_running_stats=True, return_attention=False):
     """``TrackMPNN.forward`` (``models/track_mpnn.py:54-75``) for ``nattheads == 0``.
 
     x_new [N'-N, F] float32 (edge rows all-zero), h_in [N, G*H] or None, g has N' rows.
@@ -230,6 +278,7 @@ def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, ms
     assert n_old + n_new == n_tot, (n_old, n_new, n_tot)
     is_det = g.ts >= 0
     h_out = np.zeros((n_tot, G * H), np.float32)
+    attention = []
     for gi, (a, b) in enumerate(groups):
         if n_new > 0:
             new_det = is_det[n_old:]
@@ -247,6 +296,19 @@ def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, ms
             h = h_in[:, gi * H:(gi + 1) * H]
         h = np.ascontiguousarray(h, dtype=np.float32)
         xs, agg, e, d = aggregate(h, g, msg_type)
+        nheads = gat_heads(params, gi)
+        if nheads:  # attention-weighted edge_support instead of the plain signed sum (models/layers.py:105-112)
+            assert not training, 'the oracle restates the attention heads in eval mode only (dropout p=0.5 in training)'
+            acc = np.zeros_like(h)
+            heads = []
+            for k in range(nheads):
+                sup, _, att = gat_support(h, g, params[f'factor_grus.{gi}.gat.{k}.W_att'], params[f'factor_grus.{gi}.gat.{k}.a'])
+                acc = acc + sup
+                heads.append(att)
+            agg = (acc / np.float32(nheads)).astype(np.float32)[d]
+            attention.append(heads)
+        else:
+            attention.append(None)
         pre = f'factor_grus.{gi}.'
         hn = np.empty_like(h)
         hn[e] = gru_cell(xs, h[e], params[pre + 'edge_gru.weight_ih'], params[pre + 'edge_gru.weight_hh'],
@@ -257,6 +319,8 @@ def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, ms
     wn = params['output_transform_node.weight'][0]; bn = params['output_transform_node.bias'][0]
     we = params['output_transform_edge.weight'][0]; be = params['output_transform_edge.bias'][0]
     logits = np.where(is_det, h_out @ wn + bn, h_out @ we + be).astype(np.float32)[:, None]
+    if return_attention:
+        return _sigmoid(logits), logits, h_out, attention
     return _sigmoid(logits), logits, h_out
 
 

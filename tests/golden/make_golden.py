@@ -36,13 +36,13 @@ def coo(adj):
     return np.stack((r, c, a[r, c])).astype(np.int32)
 
 
-def make_model(features, ncat, msg_type, scale, edge_bias, seed=5):
+def make_model(features, ncat, msg_type, scale, edge_bias, seed=5, nattheads=0):
     torch.manual_seed(seed)
-    m = TrackMPNN(features=features, ncategories=ncat, nhidden=64, nattheads=0, msg_type=msg_type)
+    m = TrackMPNN(features=features, ncategories=ncat, nhidden=64, nattheads=nattheads, msg_type=msg_type)
     if scale != 1.0:
         with torch.no_grad():
-            for p in m.parameters():
-                if p.dim() >= 2:
+            for name, p in m.named_parameters():
+                if p.dim() >= 2 and '.gat.' not in name:  # attention parameters keep their xavier init
                     p.mul_(scale)
     if edge_bias is not None:
         with torch.no_grad():
@@ -64,16 +64,17 @@ def add_features(X, y, features):
 
 
 def run_infer(name, seed, frames, dets, dataset, features, msg_type, scale, edge_bias, hungarian,
-              ret_win, cur_win, tp_classifier, prune_at=None):
+              ret_win, cur_win, tp_classifier, prune_at=None, nattheads=0):
     Xn, yn = synth.make_sequence(seed, frames, dets, dataset)
     Xn = add_features(Xn, yn, features)
     ncat = synth.num_categories(dataset)
-    model = make_model(features, ncat, msg_type, scale, edge_bias)
+    model = make_model(features, ncat, msg_type, scale, edge_bias, nattheads=nattheads)
     model.eval()
     X = torch.from_numpy(Xn); y = torch.from_numpy(yn)
     out = {'X': Xn, 'y': yn}
     meta = dict(kind='infer', features=features, ncategories=ncat, msg_type=msg_type, hungarian=hungarian,
-                ret_win_size=ret_win, cur_win_size=cur_win, tp_classifier=tp_classifier, dataset=dataset)
+                ret_win_size=ret_win, cur_win_size=cur_win, tp_classifier=tp_classifier, dataset=dataset,
+                nattheads=nattheads)
     for k, v in model.state_dict().items():
         out['w/' + k] = v.detach().cpu().numpy().copy()
 
@@ -121,9 +122,11 @@ def run_infer(name, seed, frames, dets, dataset, features, msg_type, scale, edge
             out[f's{s}/t'] = np.array(t_cur)
             out[f's{s}/y_pred'] = y_pred.numpy(); out[f's{s}/feats'] = feats.numpy()
             out[f's{s}/adj'] = coo(node_adj); out[f's{s}/labels'] = labels.numpy()
-            scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+            scores, logits, states, att = model(feats, states, node_adj, edge_adj)
             scores = fix(scores, y_pred)
             out[f's{s}/scores'] = scores.numpy(); out[f's{s}/logits'] = logits.numpy(); out[f's{s}/h'] = states.numpy()
+            if nattheads > 0 and s in (1, 3):  # dense attention [groups, heads, N, N] of two small steps
+                out[f's{s}/att'] = np.stack([np.stack([a.numpy() for a in grp]) for grp in att])
             if prune_at is not None and t_cur == prune_at:
                 t_lo, t_hi = t_cur - 2, t_cur - 1
                 y_pred, states, node_adj, labels, scores = prune_graph(
@@ -221,7 +224,12 @@ def run_train(name, seed, dets, dataset, features, msg_type, scale, edge_bias, t
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gat':
+    # added after the first batch of fixtures: attention heads (--num-att-heads 2), eval mode
+    torch.set_num_threads(4)
+    run_infer('infer_gat2', 18, 10, 5, 'kitti', '2d', 'diff', 20.0, 0.0, False, 0, 5, True, nattheads=2)
+    run_infer('infer_gat3_concat', 19, 9, 4, 'kitti', '2d+temp', 'concat', 20.0, 0.0, False, 0, 4, True, nattheads=3)
+elif __name__ == '__main__':
     torch.set_num_threads(4)
     # stock init: no association is ever made (edge score ~ 0.01), every detection is its own track
     run_infer('infer_stock_kitti', 11, 10, 8, 'kitti', '2d', 'diff', 1.0, None, False, 0, 5, True)

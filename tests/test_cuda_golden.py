@@ -16,7 +16,7 @@ TOL = 1e-4
 def _model(gold, dev, train=False, tensor=False):
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     m = gold.meta
-    model = TrackMPNN(m['features'], m['ncategories'], 64, 0, m['msg_type'], use_tensor_cores=tensor)
+    model = TrackMPNN(m['features'], m['ncategories'], 64, m.get('nattheads', 0), m['msg_type'], use_tensor_cores=tensor)
     sd = {k: torch.from_numpy(v) for k, v in gold.params().items()}
     model.load_state_dict(sd, strict=True)
     model.to(dev)
@@ -71,7 +71,7 @@ def test_infer_free_running(name, tensor):
                                       + np.diag((gold.get(0, 'y_pred')[:, 0] == -1).astype(np.float32)))
         np.testing.assert_array_equal(labels.cpu().numpy(), gold.get(0, 'labels'))
         scores, logits, states, att = model(feats, None, node_adj, edge_adj)
-        assert att == (None,) * len(model.feature_idx)
+        assert len(att) == len(model.feature_idx) and all((a is None) == (m.get('nattheads', 0) == 0) for a in att)
         np.testing.assert_allclose(logits.cpu().numpy(), gold.get(0, 'logits'), atol=TOL, rtol=0)
         np.testing.assert_allclose(states.cpu().numpy(), gold.get(0, 'h'), atol=TOL, rtol=0)
         scores = _fix(scores, y_pred, m['tp_classifier'])
@@ -93,9 +93,14 @@ def test_infer_free_running(name, tensor):
             np.testing.assert_array_equal(feats.cpu().numpy(), gold.get(s, 'feats'))
             np.testing.assert_array_equal(_dense(node_adj), _ref_dense(gold, s))
             np.testing.assert_array_equal(labels.cpu().numpy(), gold.get(s, 'labels'))
-            scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+            scores, logits, states, att = model(feats, states, node_adj, edge_adj)
             np.testing.assert_allclose(logits.cpu().numpy(), gold.get(s, 'logits'), atol=TOL, rtol=0)
             np.testing.assert_allclose(states.cpu().numpy(), gold.get(s, 'h'), atol=TOL, rtol=0)
+            if gold.has(s, 'att'):  # the reference's dense attention [groups, heads, N, N]
+                want = gold.get(s, 'att')
+                for gi in range(want.shape[0]):
+                    for k in range(want.shape[1]):
+                        np.testing.assert_allclose(att[gi][k].to_dense().cpu().numpy(), want[gi, k], atol=1e-5, rtol=0)
             scores = _fix(scores, y_pred, m['tp_classifier'])
             if gold.has(s, 'prune_y_pred'):
                 t_lo, t_hi = gold.get(s, 'prune_t')

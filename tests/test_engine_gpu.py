@@ -11,13 +11,13 @@ from trackmpnn_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _model(dev, dataset='kitti', msg_type='diff', scale=20.0, edge_bias=0.0, seed=5):
+def _model(dev, dataset='kitti', msg_type='diff', scale=20.0, edge_bias=0.0, seed=5, heads=0):
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     torch.manual_seed(seed)
-    model = TrackMPNN('2d', synth.num_categories(dataset), 64, 0, msg_type)
+    model = TrackMPNN('2d', synth.num_categories(dataset), 64, heads, msg_type)
     with torch.no_grad():
-        for p in model.parameters():
-            if p.dim() >= 2:
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and '.gat.' not in name:
                 p.mul_(scale)
         if edge_bias is not None:
             model.output_transform_edge.bias.fill_(edge_bias)
@@ -40,6 +40,9 @@ def _sequences(seeds, dataset='kitti', gap=()):
     return seqs
 
 
+GAT_SEEDS = [108, 41, 52, 68, 49, 44, 105]
+
+
 @pytest.mark.parametrize('cfg', [
     # seeds chosen (on the oracle) so that no score is within 5e-4 of the 0.5 decision threshold
     dict(seeds=[30, 34, 48, 58, 65], msg_type='diff', ret=0, graph=False, gap=()),
@@ -50,13 +53,15 @@ def _sequences(seeds, dataset='kitti', gap=()):
     dict(seeds=[30, 34, 48, 58, 65], msg_type='diff', ret=0, graph=False, gap=(), tensor=True),
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True),
     dict(seeds=[108, 84, 77, 100, 72, 32, 56], msg_type='diff', ret=0, graph=True, gap=(), hungarian=True),
+    dict(seeds=GAT_SEEDS, msg_type='diff', ret=0, graph=True, gap=(), heads=2),
     dict(seeds=[84, 100, 48, 125, 56], msg_type='diff', ret=2, graph=False, gap=(), hungarian=True),
 ])
 def test_engine_matches_oracle(cfg):
     from trackmpnn_b200.engine import TrackEngine
     dev = torch.device('cuda:0')
     stock = cfg.get('stock', False)
-    model = _model(dev, msg_type=cfg['msg_type'], scale=1.0 if stock else 20.0, edge_bias=None if stock else 0.0)
+    model = _model(dev, msg_type=cfg['msg_type'], scale=1.0 if stock else 20.0, edge_bias=None if stock else 0.0,
+                   heads=cfg.get('heads', 0))
     params = _params(model)
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],

@@ -100,9 +100,17 @@ def test_infer_free_running(name):
             h = None
         else:
             g, feats = O.update_graph(g, scores, gold.X, gold.y, t_cur, use_hungarian=m['hungarian'], mode='test')
+        h_before = h
         scores, logits, h = _fwd(gold, params, feats, h, g)
         scores = fix(scores, g)
         np.testing.assert_allclose(h, gold.get(s, 'h'), atol=TOL, rtol=0)
+        if gold.has(s, 'att'):  # dense attention of every group / head at this step
+            _, _, _, att = O.forward(params, feats, h_before, g, features=m['features'], ncategories=m['ncategories'],
+                                     msg_type=m['msg_type'], return_attention=True)
+            want = gold.get(s, 'att')
+            for gi in range(want.shape[0]):
+                for k in range(want.shape[1]):
+                    np.testing.assert_allclose(O.dense_attention(att[gi][k], g.n), want[gi, k], atol=1e-5, rtol=0)
         if gold.has(s, 'prune_y_pred'):
             t_lo, t_hi = gold.get(s, 'prune_t')
             g, h, scores, _ = O.prune_graph(g, h, scores, int(t_lo), int(t_hi), 0.5)

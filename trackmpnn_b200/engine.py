@@ -103,6 +103,7 @@ class TrackEngine:
         diff = all(g.msg_type == 'diff' for g in model.factor_grus)
         # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise
         self.tensor = diff and (self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
+        self._gat_scratch = {}
         self.profile = None  # list of (start event, end event, n_edges tensor) per edge-kernel launch when enabled
         self._graph = None
         self.ticks = 0
@@ -130,7 +131,7 @@ class TrackEngine:
         tc = F_.packed_cells_tc(model) if self.tensor else None
         for grp in range(self.G):
             concat = int(model.factor_grus[grp].msg_type == 'concat')
-            L.call('tmpnn_aggregate_dets', g.c, self.index.c, L.ptr(h_in), self.ldh, grp * H, L.ptr(self.agg), st)
+            F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, self.agg, self._gat_scratch)
             if self.profile is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -85,20 +85,76 @@ def use_tensor_path(model, n_rows):
     return bool(mode)
 
 
-def mp_step(model, g_c, ix_c, h_in, h_out, ldh, agg, tensor):
-    """One message-passing step over all feature groups (K1-det, edge rows, detection rows)."""
+class SparseAttention:
+    """Attention of one head, one weight per incidence entry (detection, incident edge).  ``to_dense()``
+    gives the reference's [N, N] matrix (``models/layers.py:35-37``): softmax rows for the detections and
+    the uniform 1/N rows its masked softmax yields for rows without incident edges."""
+
+    def __init__(self, n, n_dets, det_rows, seg_ptr, inc, alpha):
+        self.n, self.n_dets, self.det_rows, self.seg_ptr, self.inc, self.alpha = n, n_dets, det_rows, seg_ptr, inc, alpha
+
+    def to_dense(self):
+        nd = int(self.n_dets.item())
+        A = torch.full((self.n, self.n), 1.0 / self.n, dtype=torch.float32, device=self.alpha.device)
+        seg = self.seg_ptr[:2 * nd + 1].long()
+        lens = seg[2::2] - seg[0:-1:2]           # incident edges per detection (past + future)
+        rows = self.det_rows[:nd].long()
+        A[rows[lens > 0]] = 0
+        tot = int(seg[-1].item())
+        owner = torch.repeat_interleave(rows, lens)
+        A[owner, self.inc[:tot].long()] = self.alpha[:tot]
+        return A
+
+
+def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, keep_attention=False):
+    """Input of the node GRU for the detection rows: the plain signed sum, or -- with attention heads --
+    the attention-weighted one (reference ``models/layers.py:101-112``).  Returns a list of per-head
+    ``alpha`` tensors when ``keep_attention`` (else None)."""
+    st = L.stream()
+    if gru.gat is None:
+        L.call('tmpnn_aggregate_dets', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(agg), st)
+        return None
+    if gru.training and torch.is_grad_enabled():
+        raise NotImplementedError('attention heads are built for inference (eval mode); their training path '
+                                  '(dropout on the attention + backward) is not')
+    dev = h_in.device
+    if scratch is None:
+        scratch = {}
+    hatt = scratch.get('hatt')
+    if hatt is None or hatt.shape[0] < index.cap_dets:
+        hatt = scratch['hatt'] = torch.empty((index.cap_dets, H), dtype=torch.float32, device=dev)
+    esc = scratch.get('escore')
+    n_all = graph.num_seqs * graph.cap_rows
+    if esc is None or esc.numel() < n_all:
+        esc = scratch['escore'] = torch.empty(n_all, dtype=torch.float32, device=dev)
+    alphas = []
+    nh = len(gru.gat)
+    for k, head in enumerate(gru.gat):
+        alpha = torch.empty(index.cap_inc, dtype=torch.float32, device=dev) if keep_attention else None
+        L.call('tmpnn_gat_aggregate_dets', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(head.W_att.detach().contiguous()),
+               L.ptr(head.a.detach().contiguous()), k, nh, L.ptr(hatt), L.ptr(esc), L.ptr(agg), L.ptr(alpha), st)
+        alphas.append(alpha)
+    return alphas if keep_attention else None
+
+
+def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
+    """One message-passing step over all feature groups (K1-det, edge rows, detection rows).
+    Returns the per-group attention (list of per-head alpha tensors, or None)."""
     G = len(model.feature_idx)
+    g_c, ix_c = graph.c, index.c
     packs = packed_cells(model)
     tc = packed_cells_tc(model) if tensor else None
     st = L.stream()
+    att = []
     for g in range(G):
         concat = int(model.factor_grus[g].msg_type == 'concat')
-        L.call('tmpnn_aggregate_dets', g_c, ix_c, L.ptr(h_in), ldh, g * H, L.ptr(agg), st)
+        att.append(aggregate_for_dets(model.factor_grus[g], graph, index, h_in, ldh, g * H, agg, None, keep_attention))
         if tensor:
             L.call('tmpnn_mp_edge_fwd_tc', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(tc[g]), st)
         else:
             L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
         L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
+    return att
 
 
 def input_transform_rows(model, g, x, x_idx, n, n_edge_rows, h, ldh, out_rows, n_dev=None):
@@ -162,17 +218,19 @@ def track_mpnn_forward(model, x, h_in, node_adj, edge_adj):
     h_out = torch.empty_like(h_cur)
     agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
     tensor = use_tensor_path(model, n_tot)
-    mp_step(model, wg.g.c, ix.c, h_cur, h_out, ldh, agg, tensor)
+    att = mp_step(model, wg.g, ix, h_cur, h_out, ldh, agg, tensor, keep_attention=True)
     if tensor:
         wg.g.check_status()
     logits = wg.g.logit[:n_tot].clone().unsqueeze(1)
     scores = wg.g.score[:n_tot].clone().unsqueeze(1)
-    return scores, logits, h_out, tuple(None for _ in range(G))
+    attention = tuple(None if a is None else [SparseAttention(n_tot, ix.n_dets, ix.det_rows, ix.seg_ptr, ix.inc, al) for al in a]
+                      for a in att)
+    return scores, logits, h_out, attention
 
 
 def mp_step_single_group(gru, h, node_adj):
-    """``FactorGraphGRU.forward`` (reference ``models/layers.py:84-116``) for one 64-wide group.
-    The heads are fused in the kernel; with no head attached here a zero head is packed."""
+    """``FactorGraphGRU.forward`` (reference ``models/layers.py:84-116``) for one 64-wide group ->
+    ``(h', attention)``.  The heads are fused in the kernel; with no head attached here a zero head is packed."""
     wg = window_graph_of(node_adj)
     dev = wg.device
     n = wg.n
@@ -190,9 +248,13 @@ def mp_step_single_group(gru, h, node_adj):
     h_in = h.detach().to(device=dev, dtype=torch.float32).contiguous()
     h_out = torch.empty_like(h_in)
     agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
-    L.call('tmpnn_mp_step_fwd', wg.g.c, ix.c, L.ptr(h_in), L.ptr(h_out), H, 0, 1, int(gru.msg_type == 'concat'),
-           L.ptr(packs[0]), L.ptr(packs[1]), L.ptr(agg), L.stream())
-    return h_out
+    st = L.stream()
+    alphas = aggregate_for_dets(gru, wg.g, ix, h_in, H, 0, agg, None, keep_attention=True)
+    L.call('tmpnn_mp_edge_fwd', wg.g.c, ix.c, L.ptr(h_in), L.ptr(h_out), H, 0, 1, int(gru.msg_type == 'concat'),
+           L.ptr(packs[0]), st)
+    L.call('tmpnn_mp_det_fwd', wg.g.c, ix.c, L.ptr(h_in), L.ptr(h_out), H, 0, 1, L.ptr(packs[1]), L.ptr(agg), st)
+    att = None if alphas is None else [SparseAttention(n, ix.n_dets, ix.det_rows, ix.seg_ptr, ix.inc, a) for a in alphas]
+    return h_out, att
 
 
 # ---------------------------------------------------------------------------------------------
@@ -220,6 +282,9 @@ class _MPStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, node_adj, x, h_in, *params):
+        if any(g.gat is not None for g in model.factor_grus):
+            raise NotImplementedError('training with attention heads (--num-att-heads > 0) is not built: the heads '
+                                      'run in inference only (call model.eval() under torch.no_grad())')
         wg = window_graph_of(node_adj)
         dev = wg.device
         n_tot = wg.n
