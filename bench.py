@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--dataset', default='bdd', choices=['bdd', 'kitti'])
     ap.add_argument('--win', type=int, default=5)
     ap.add_argument('--no-cuda-graph', action='store_true')
+    ap.add_argument('--no-deferred', action='store_true', help='move the hidden states in every window slide (A/B switch)')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU-baseline sample (0 = auto)')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
@@ -275,7 +276,8 @@ def main():
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff').to(dev).eval()
     seqs = make_sequences(a, rank)
-    eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph)
+    eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
+                      deferred_compaction=not a.no_deferred)
 
     # ---- warm-up -------------------------------------------------------------------------
     for _ in range(max(a.warmup, 1)):
@@ -370,7 +372,7 @@ def main():
                'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': workload_name(a), 'l2': 'inputs_larger_than_l2 (state >= 4 GB per GPU vs 126 MB L2)',
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
-                          'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows,
+                          'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
                'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'train': train}
         print(json.dumps(out), flush=True)

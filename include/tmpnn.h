@@ -73,6 +73,17 @@ typedef struct tmpnn_graph {
   float *score;       /* [S*cap_rows]  p = scores[:,1] */
   float *logit;       /* [S*cap_rows]  */
   int32_t *status;    /* [1] sticky TMPNN_FLAG_* bits */
+  /* Deferred compaction of h (all NULL = rows of h are the logical rows).  When set, the state the next
+   * message-passing step consumes is NOT stored at the logical rows: row i lives at GLOBAL row phys[i] of
+   * the step's input buffer, its endpoints at psrc[i] / pdst[i] (-1 for detection rows).  The step writes
+   * its output densely at the logical rows of the other buffer, so tmpnn_graph_compact only has to emit
+   * these maps (the positions before the deletion) instead of moving 512 B per surviving row, and
+   * tmpnn_graph_append points new edge rows at an all-zero row (slab-local row cap_rows-1, never written)
+   * instead of zero-filling them.  phys_end[s]: slab-local end of the dense part of the input buffer. */
+  int32_t *phys;      /* [S*cap_rows] */
+  int32_t *psrc;      /* [S*cap_rows] */
+  int32_t *pdst;      /* [S*cap_rows] */
+  int32_t *phys_end;  /* [S] */
 } tmpnn_graph;
 
 /* Per-step index over the slabs: detection-row list, per-detection incidence lists (CSR,
@@ -370,6 +381,10 @@ int tmpnn_graph_prune_mask(const tmpnn_graph *g, const tmpnn_index *ix, int t_st
  * new_of_old[row] = new slab-local row or -1.  Sequences with active[s] == 0 (they sat out the
  * message-passing step, so their current state is still in the step's input buffer) take h from
  * h_src_inactive instead of h_src. */
+/* Deferred-compaction graphs only: declares the state dense at the logical rows (phys = identity,
+ * psrc/pdst = src/dst, phys_end = n_rows), e.g. after the first step on a freshly initialised graph. */
+int tmpnn_graph_phys_identity(const tmpnn_graph *g, void *stream);
+
 int tmpnn_graph_compact(const tmpnn_graph *g_in, const tmpnn_graph *g_out, const uint8_t *keep,
                         const float *h_src, const float *h_src_inactive, const int32_t *active, float *h_dst,
                         int ldh, int32_t *new_of_old, int32_t *scratch, void *stream);

@@ -56,7 +56,8 @@ GAT_SEEDS = [108, 41, 52, 68, 49, 44, 105]
     dict(seeds=GAT_SEEDS, msg_type='diff', ret=0, graph=True, gap=(), heads=2),
     dict(seeds=[84, 100, 48, 125, 56], msg_type='diff', ret=2, graph=False, gap=(), hungarian=True),
 ])
-def test_engine_matches_oracle(cfg):
+@pytest.mark.parametrize('deferred', [False, True])
+def test_engine_matches_oracle(cfg, deferred):
     from trackmpnn_b200.engine import TrackEngine
     dev = torch.device('cuda:0')
     stock = cfg.get('stock', False)
@@ -65,7 +66,8 @@ def test_engine_matches_oracle(cfg):
     params = _params(model)
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],
-                      tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False))
+                      tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False),
+                      deferred_compaction=deferred)
     outs, stats = eng.run().results()
     tot_e = tot_f = 0
     for (X, y), got in zip(seqs, outs):
@@ -81,6 +83,37 @@ def test_engine_matches_oracle(cfg):
     for a, b in zip(outs, outs2):
         np.testing.assert_array_equal(a, b)
     assert stats2 == stats
+
+
+@pytest.mark.parametrize('tensor', [False, True])
+@pytest.mark.parametrize('ticks', [1, 2, 5, 8])
+def test_deferred_compaction_is_bit_identical(tensor, ticks):
+    """Skipping the physical move of the hidden states (the next step reads them through the position maps)
+    changes nothing: graphs, scores and logits after any number of frames equal the plain engine's bit for bit,
+    and so do the states once read through the maps."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    seqs = _sequences([30, 49, 34, 52, 54, 72, 77], gap=(49, 52))
+    a = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=1, use_cuda_graph=False, tensor_cores=tensor,
+                    deferred_compaction=False)
+    b = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=1, use_cuda_graph=False, tensor_cores=tensor,
+                    deferred_compaction=True)
+    a.run(max_ticks=ticks); b.run(max_ticks=ticks)
+    torch.cuda.synchronize()
+    a.ga.check_status(); b.ga.check_status()
+    na, nb = a.ga.n_rows.cpu().numpy(), b.ga.n_rows.cpu().numpy()
+    np.testing.assert_array_equal(na, nb)
+    assert na.sum() > 0
+    hb_buf = b.h_alt if (ticks & 1) else b.h_cur   # the buffer the last step wrote
+    for s in range(len(seqs)):
+        ra = slice(s * a.cap_rows, s * a.cap_rows + int(na[s]))
+        rb = slice(s * b.cap_rows, s * b.cap_rows + int(nb[s]))
+        for name in ('ts', 'det', 'ass', 'src', 'dst', 'score', 'logit'):
+            np.testing.assert_array_equal(getattr(a.ga, name)[ra].cpu().numpy(), getattr(b.ga, name)[rb].cpu().numpy(), err_msg=name)
+        ha = a.h_cur[ra].cpu().numpy()
+        hb = hb_buf[b.ga.phys[rb].long()].cpu().numpy()
+        np.testing.assert_array_equal(ha, hb)
 
 
 @pytest.mark.parametrize('ret', [0, 2])

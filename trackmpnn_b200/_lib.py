@@ -34,7 +34,8 @@ f32p = C.POINTER(C.c_float)
 class Graph(C.Structure):
     _fields_ = [('num_seqs', C.c_int32), ('cap_rows', C.c_int32), ('n_rows', C.c_void_p), ('ts', C.c_void_p),
                 ('det', C.c_void_p), ('ass', C.c_void_p), ('src', C.c_void_p), ('dst', C.c_void_p),
-                ('label', C.c_void_p), ('score', C.c_void_p), ('logit', C.c_void_p), ('status', C.c_void_p)]
+                ('label', C.c_void_p), ('score', C.c_void_p), ('logit', C.c_void_p), ('status', C.c_void_p),
+                ('phys', C.c_void_p), ('psrc', C.c_void_p), ('pdst', C.c_void_p), ('phys_end', C.c_void_p)]
 
 
 class Index(C.Structure):
@@ -109,6 +110,7 @@ _PROTOS = {
     'tmpnn_graph_decode': ([C.POINTER(Graph), C.POINTER(Index), C.POINTER(Frames), _VP, _VP, _VP, _I, _VP, _I,
                             _VP, _VP, _VP], _I),
     'tmpnn_graph_prune_mask': ([C.POINTER(Graph), C.POINTER(Index), _I, _I, C.c_float, _VP, _VP, _VP], _I),
+    'tmpnn_graph_phys_identity': ([C.POINTER(Graph), _VP], _I),
     'tmpnn_graph_compact_scratch_ints': ([_I, _I], C.c_size_t),
     'tmpnn_graph_compact': ([C.POINTER(Graph), C.POINTER(Graph), _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
 }
@@ -166,7 +168,7 @@ KERNELS_PER_CALL = {
     'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 11, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 2, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
-    'tmpnn_graph_compact': 4,
+    'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
     'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_input_bwd': 1, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,

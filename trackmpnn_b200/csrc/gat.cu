@@ -17,7 +17,8 @@ constexpr int H = TMPNN_HIDDEN;
 // h_att[k] = h[det_rows[k]] . W_att  (only detection rows are ever endpoints); one warp per detection
 __global__ void __launch_bounds__(256) k_gat_project(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows,
                                                      const float* __restrict__ h, int ldh, int col,
-                                                     const float* __restrict__ w_att, float* __restrict__ hatt) {
+                                                     const float* __restrict__ w_att, float* __restrict__ hatt,
+                                                     const int32_t* __restrict__ phys) {
   __shared__ float w[H * H];
   __shared__ float hr[8][H];
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) w[i] = w_att[i];
@@ -25,7 +26,8 @@ __global__ void __launch_bounds__(256) k_gat_project(const int32_t* __restrict__
   const int nd = *n_dets;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int k = blockIdx.x * 8 + wp; k < nd; k += gridDim.x * 8) {
-    const float* r = h + (size_t)det_rows[k] * ldh + col;
+    const int row = det_rows[k];
+    const float* r = h + (size_t)(phys ? phys[row] : row) * ldh + col;
     hr[wp][lane] = r[lane];
     hr[wp][lane + 32] = r[lane + 32];
     __syncwarp();
@@ -70,7 +72,8 @@ __global__ void __launch_bounds__(256) k_gat_edge_score(const int32_t* __restric
 __global__ void __launch_bounds__(256) k_gat_aggregate(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ seg_ptr,
                                                        const int32_t* __restrict__ inc, const float* __restrict__ escore,
                                                        const float* __restrict__ h, int ldh, int col, float scale,
-                                                       int accumulate, float* __restrict__ agg, float* __restrict__ alpha) {
+                                                       int accumulate, float* __restrict__ agg, float* __restrict__ alpha,
+                                                       const int32_t* __restrict__ phys) {
   const int nd = *n_dets;
   const int lane = threadIdx.x & 31;
   for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nd; k += gridDim.x * 8) {
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(256) k_gat_aggregate(const int32_t* __restrict
       const int e = inc[i];
       const float w = expf(escore[e] - mx) / sum;
       const float sw = i < s1 ? -w : w;
-      const float* r = h + (size_t)e * ldh + col;
+      const float* r = h + (size_t)(phys ? phys[e] : e) * ldh + col;
       a0 = fmaf(sw, r[lane], a0);
       a1 = fmaf(sw, r[lane + 32], a1);
       if (alpha && lane == 0) alpha[i] = w;
@@ -106,13 +109,13 @@ extern "C" int tmpnn_gat_aggregate_dets(const tmpnn_graph* g, const tmpnn_index*
   TMPNN_REQUIRE(g && ix && h && w_att && a && hatt && escore && agg, "null argument");
   TMPNN_REQUIRE(ldh % 4 == 0 && col % 4 == 0 && head >= 0 && head < num_heads, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  k_gat_project<<<TMPNN_SM_COUNT * 2, 256, 0, st>>>(ix->n_dets, ix->det_rows, h, ldh, col, w_att, hatt);
+  k_gat_project<<<TMPNN_SM_COUNT * 2, 256, 0, st>>>(ix->n_dets, ix->det_rows, h, ldh, col, w_att, hatt, g->phys);
   TMPNN_LAUNCH_CHECK();
   dim3 grid(max(1, min(tmpnn_div_up(g->cap_rows, 16), TMPNN_SM_COUNT * 8 / max(1, min(g->num_seqs, 8)))), g->num_seqs);
   k_gat_edge_score<<<grid, 256, 0, st>>>(g->n_rows, g->src, g->dst, g->cap_rows, ix->det_of_row, hatt, a, escore);
   TMPNN_LAUNCH_CHECK();
   k_gat_aggregate<<<TMPNN_SM_COUNT * 8, 256, 0, st>>>(ix->n_dets, ix->seg_ptr, ix->inc, escore, h, ldh, col,
-                                                     1.0f / (float)num_heads, head > 0, agg, alpha);
+                                                     1.0f / (float)num_heads, head > 0, agg, alpha, g->phys);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

@@ -210,7 +210,8 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
       const int n0 = fp[t + 1] - fp[t], n1 = fp[t1 + 1] - fp[t1];
       const long long total = (long long)n0 + (long long)n0 * n1 + n1;
       int slot = -1;
-      bool ok = total <= g.cap_rows;
+      // deferred compaction keeps the slab's last row as the shared all-zero row
+      bool ok = total <= g.cap_rows - (g.phys ? 1 : 0);
       if (ok) {
         slot = atomicAdd(&n_new[0], n0 + n1);
         if (slot + n0 + n1 > cap_new) ok = false;
@@ -269,6 +270,9 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
     const long long add = nt ? (long long)A * nt + nt : 0;
     int slot = -1;
     bool ok = n + add <= g.cap_rows;
+    // deferred compaction: the new detections' state goes behind the dense part of the step's input buffer,
+    // and the slab's last row stays the shared all-zero row
+    if (g.phys) ok = n + add <= g.cap_rows - 1 && (long long)g.phys_end[s] + nt <= g.cap_rows - 1;
     if (ok && nt) {
       slot = atomicAdd(&n_new[0], nt);
       if (slot + nt > cap_new) ok = false;
@@ -301,19 +305,31 @@ k_append_fill(tmpnn_graph g, tmpnn_frames fr, const int32_t* __restrict__ act, c
   const int n_edge = A * nt;
   const int total = lead + n_edge + nt;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // deferred compaction: new detections take the physical rows behind the dense part of the step's input
+  // buffer, new edge rows all alias the slab's zero row
+  const bool deferred = g.phys != nullptr;
+  const int p_det0 = deferred ? (kind == 2 ? lead : g.phys_end[s]) : 0;  // physical slab row of detection j of frame t
+  const int32_t zrow = (int32_t)(base + g.cap_rows - 1);
   for (int k = tid; k < total; k += nth) {
     const size_t row = base + n_old + k;
     int ts = -1, det = -1, sr = -1, ds = -1, lab = 0;
+    int32_t ph = (int32_t)row, ps = -1, pd = -1;
     if (k < lead) {  // detections of t0 (init only)
       det = fr.frame_dets[f0_off + k];
       ts = t0;
-      new_det_rows[slot + k] = (int32_t)row;
+      if (deferred) ph = (int32_t)(base + k);
+      new_det_rows[slot + k] = ph;
       new_det_x[slot + k] = dp + det;
       if (fr.det_track) lab = fr.det_track[dp + det] >= 0;
     } else if (k < lead + n_edge) {
       const int q = k - lead, a = q / nt, j = q % nt;
       sr = kind == 2 ? a : act[base + a];
       ds = n_old + lead + n_edge + j;
+      if (deferred) {
+        ph = zrow;
+        ps = kind == 2 ? (int32_t)(base + a) : g.phys[base + sr];
+        pd = (int32_t)(base + p_det0 + j);
+      }
       if (fr.det_track && g.label) {
         const int da = kind == 2 ? fr.frame_dets[f0_off + a] : g.det[base + sr];
         const int tr_a = fr.det_track[dp + da];
@@ -324,7 +340,8 @@ k_append_fill(tmpnn_graph g, tmpnn_frames fr, const int32_t* __restrict__ act, c
       const int j = k - lead - n_edge;
       det = fr.frame_dets[f_off + j];
       ts = tnew;
-      new_det_rows[slot + lead + j] = (int32_t)row;
+      if (deferred) ph = (int32_t)(base + p_det0 + j);
+      new_det_rows[slot + lead + j] = ph;
       new_det_x[slot + lead + j] = dp + det;
       if (fr.det_track) lab = fr.det_track[dp + det] >= 0;
     }
@@ -336,9 +353,10 @@ k_append_fill(tmpnn_graph g, tmpnn_frames fr, const int32_t* __restrict__ act, c
     if (g.label) g.label[row] = lab;
     g.score[row] = 0.f;
     g.logit[row] = 0.f;
+    if (deferred) { g.phys[row] = ph; g.psrc[row] = ps; g.pdst[row] = pd; }
   }
   // h = 0 for the new rows: one flat, fully coalesced range per sequence
-  if (h) {
+  if (h && !deferred) {
     float4* p = reinterpret_cast<float4*>(h + (base + n_old) * ldh);
     const size_t n4 = (size_t)total * ldh / 4;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -558,12 +576,30 @@ k_compact_move(tmpnn_graph gi, tmpnn_graph go, const int32_t* __restrict__ new_o
                int ldh) {
   const int s = blockIdx.y, n = gi.n_rows[s];
   const size_t base = (size_t)s * gi.cap_rows;
-  const float* hs = (seq_off(active, s) && h_src_inactive) ? h_src_inactive : h_src;
+  const bool off = seq_off(active, s);
+  const float* hs = (off && h_src_inactive) ? h_src_inactive : h_src;
   const int r_begin = blockIdx.x * ROWS_PER_BLOCK, r_end = min(n, r_begin + ROWS_PER_BLOCK);
+  // deferred compaction: the step left the state of an active sequence dense at the OLD logical rows of
+  // h_src; nothing is moved, the maps say where the survivors are.  A sequence that did not step this frame
+  // still lives in the previous buffer (through its own maps) and is copied over densely.
+  const bool deferred = go.phys != nullptr;
+  if (deferred && blockIdx.x == 0 && threadIdx.x == 0) go.phys_end[s] = off ? go.n_rows[s] : n;
   for (int r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const int nr = new_of_old[base + r];
     if (nr < 0) continue;
     const size_t o = base + nr, i = base + r;
+    if (deferred) {
+      const int a0 = gi.src[i];
+      if (off) {
+        go.phys[o] = (int32_t)o;
+        go.psrc[o] = a0 < 0 ? -1 : (int32_t)(base + new_of_old[base + a0]);
+        go.pdst[o] = a0 < 0 ? -1 : (int32_t)(base + new_of_old[base + gi.dst[i]]);
+      } else {
+        go.phys[o] = (int32_t)i;
+        go.psrc[o] = a0 < 0 ? -1 : (int32_t)(base + a0);
+        go.pdst[o] = a0 < 0 ? -1 : (int32_t)(base + gi.dst[i]);
+      }
+    }
     go.ts[o] = gi.ts[i];
     go.det[o] = gi.det[i];
     go.ass[o] = gi.ass[i];
@@ -574,15 +610,28 @@ k_compact_move(tmpnn_graph gi, tmpnn_graph go, const int32_t* __restrict__ new_o
     go.score[o] = gi.score[i];
     go.logit[o] = gi.logit[i];
   }
-  if (h_dst) {
+  if (h_dst && (!deferred || off)) {
     const int v4 = ldh / 4;
     const long long items = (long long)(r_end - r_begin) * v4;
     for (long long it = threadIdx.x; it < items; it += blockDim.x) {
       const int r = r_begin + (int)(it / v4), c = (int)(it % v4);
       const int nr = new_of_old[base + r];
       if (nr < 0) continue;
-      reinterpret_cast<float4*>(h_dst + (base + nr) * ldh)[c] = __ldg(reinterpret_cast<const float4*>(hs + (base + r) * ldh) + c);
+      const size_t from = deferred ? (size_t)gi.phys[base + r] : base + r;
+      reinterpret_cast<float4*>(h_dst + (base + nr) * ldh)[c] = __ldg(reinterpret_cast<const float4*>(hs + from * ldh) + c);
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_phys_identity(tmpnn_graph g) {
+  const int s = blockIdx.y, n = g.n_rows[s];
+  const size_t base = (size_t)s * g.cap_rows;
+  if (blockIdx.x == 0 && threadIdx.x == 0) g.phys_end[s] = n;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int a = g.src[base + r];
+    g.phys[base + r] = (int32_t)(base + r);
+    g.psrc[base + r] = a < 0 ? -1 : (int32_t)(base + a);
+    g.pdst[base + r] = a < 0 ? -1 : (int32_t)(base + g.dst[base + r]);
   }
 }
 
@@ -707,6 +756,13 @@ extern "C" int tmpnn_graph_prune_mask(const tmpnn_graph* g, const tmpnn_index* i
   return TMPNN_OK;
 }
 
+extern "C" int tmpnn_graph_phys_identity(const tmpnn_graph* g, void* stream) {
+  TMPNN_REQUIRE(g && g->phys && g->psrc && g->pdst && g->phys_end, "the graph has no deferred-compaction maps");
+  k_phys_identity<<<stride_grid(g), 256, 0, (cudaStream_t)stream>>>(*g);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
 extern "C" size_t tmpnn_graph_compact_scratch_ints(int num_seqs, int cap_rows) {
   return (size_t)num_seqs * tmpnn_div_up(cap_rows, ROWS_PER_BLOCK) + 16;
 }
@@ -715,7 +771,9 @@ extern "C" int tmpnn_graph_compact(const tmpnn_graph* g_in, const tmpnn_graph* g
                                    const float* h_src, const float* h_src_inactive, const int32_t* active, float* h_dst,
                                    int ldh, int32_t* new_of_old, int32_t* scratch, void* stream) {
   TMPNN_REQUIRE(g_in && g_out && keep && new_of_old && scratch, "null argument");
-  TMPNN_REQUIRE(g_in->ts != g_out->ts && (!h_dst || h_src != h_dst), "compaction is out of place");
+  TMPNN_REQUIRE(g_in->ts != g_out->ts && (!h_dst || h_src != h_dst || g_out->phys), "compaction is out of place");
+  TMPNN_REQUIRE(!g_out->phys || (g_in->phys && h_dst && h_src_inactive && h_src_inactive != h_dst),
+                "deferred compaction needs maps on both graphs and the two state buffers");
   TMPNN_REQUIRE(g_in->num_seqs == g_out->num_seqs && g_in->cap_rows == g_out->cap_rows, "slab shapes differ");
   TMPNN_REQUIRE(!h_dst || ldh % 4 == 0, "ldh must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;

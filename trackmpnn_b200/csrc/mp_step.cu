@@ -226,7 +226,8 @@ extern "C" int tmpnn_input_bn_relu_linear2(const float* a, const float* mean, co
 __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict__ h, int ldh, int col,
                                                         const int32_t* __restrict__ n_dets,
                                                         const int32_t* __restrict__ seg_ptr,
-                                                        const int32_t* __restrict__ inc, float* __restrict__ agg) {
+                                                        const int32_t* __restrict__ inc, float* __restrict__ agg,
+                                                        const int32_t* __restrict__ phys) {
   const int nd = *n_dets;
   const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int wpb = blockDim.x >> 5;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict_
     int i = s0 + half;
     for (; i + 6 < s2; i += 8) {
       int e0 = inc[i], e1 = inc[i + 2], e2 = inc[i + 4], e3 = inc[i + 6];
+      if (phys) { e0 = phys[e0]; e1 = phys[e1]; e2 = phys[e2]; e3 = phys[e3]; }  // deferred compaction: physical rows
       float4 v0 = ldg4(h + (size_t)e0 * ldh + col + 4 * l16);
       float4 v1 = ldg4(h + (size_t)e1 * ldh + col + 4 * l16);
       float4 v2 = ldg4(h + (size_t)e2 * ldh + col + 4 * l16);
@@ -248,7 +250,8 @@ __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict_
       acc.x = fmaf(g3, v3.x, acc.x); acc.y = fmaf(g3, v3.y, acc.y); acc.z = fmaf(g3, v3.z, acc.z); acc.w = fmaf(g3, v3.w, acc.w);
     }
     for (; i < s2; i += 2) {
-      float4 v = ldg4(h + (size_t)inc[i] * ldh + col + 4 * l16);
+      const int e = phys ? phys[inc[i]] : inc[i];
+      float4 v = ldg4(h + (size_t)e * ldh + col + 4 * l16);
       float g = (i < s1) ? -1.f : 1.f;
       acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y); acc.z = fmaf(g, v.z, acc.z); acc.w = fmaf(g, v.w, acc.w);
     }
@@ -264,7 +267,8 @@ extern "C" int tmpnn_aggregate_dets(const tmpnn_graph* g, const tmpnn_index* ix,
                                     float* agg, void* stream) {
   TMPNN_REQUIRE(g && ix && h && agg, "null argument");
   TMPNN_REQUIRE(ldh % 4 == 0 && col % 4 == 0, "h rows must be 16-byte aligned");
-  k_aggregate_dets<<<TMPNN_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(h, ldh, col, ix->n_dets, ix->seg_ptr, ix->inc, agg);
+  k_aggregate_dets<<<TMPNN_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(h, ldh, col, ix->n_dets, ix->seg_ptr, ix->inc, agg,
+                                                                         g->phys);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -424,7 +428,8 @@ k_mp_edge(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, in
           const int32_t* __restrict__ n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
           int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const float* __restrict__ pack,
           float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
-          float* __restrict__ gates) {
+          float* __restrict__ gates, const int32_t* __restrict__ phys, const int32_t* __restrict__ psrc,
+          const int32_t* __restrict__ pdst) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<KX>& s = *reinterpret_cast<StepSmem<KX>*>(smem_raw);
   const int total = tile_ptr[num_seqs];
@@ -451,9 +456,12 @@ k_mp_edge(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, in
       if (lr < n) { a = src[base + lr]; b = dst[base + lr]; }
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va, vh = va;
       if (a >= 0) {
-        va = ldg4(h_in + (base + a) * ldh + col + 4 * l16);
-        vb = ldg4(h_in + (base + b) * ldh + col + 4 * l16);
-        vh = ldg4(h_in + (base + lr) * ldh + col + 4 * l16);
+        // deferred compaction: the input state sits at physical (global) rows
+        const size_t ra = phys ? (size_t)psrc[base + lr] : base + a, rb = phys ? (size_t)pdst[base + lr] : base + b;
+        const size_t rh = phys ? (size_t)phys[base + lr] : base + lr;
+        va = ldg4(h_in + ra * ldh + col + 4 * l16);
+        vb = ldg4(h_in + rb * ldh + col + 4 * l16);
+        vh = ldg4(h_in + rh * ldh + col + 4 * l16);
       }
       if (KX == 2 * H) {
         *reinterpret_cast<float4*>(&s.X[r][4 * l16]) = va;
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
          const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows, const float* __restrict__ agg,
          const float* __restrict__ pack, float* __restrict__ logit, float* __restrict__ score, int first_group,
-         int last_group, float* __restrict__ gates) {
+         int last_group, float* __restrict__ gates, const int32_t* __restrict__ phys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<H>& s = *reinterpret_cast<StepSmem<H>*>(smem_raw);
   const int nd = *n_dets;
@@ -493,7 +501,7 @@ k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int
       if (k < nd) {
         row = det_rows[k];
         vx = ldg4(agg + (size_t)k * H + 4 * l16);
-        vh = ldg4(h_in + (size_t)row * ldh + col + 4 * l16);
+        vh = ldg4(h_in + (size_t)(phys ? phys[row] : row) * ldh + col + 4 * l16);
       }
       *reinterpret_cast<float4*>(&s.X[r][4 * l16]) = vx;
       *reinterpret_cast<float4*>(&s.Hp[r][4 * l16]) = vh;
@@ -535,11 +543,11 @@ static int mp_edge_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
   if (concat)
     k_mp_edge<2 * H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<2 * H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last, gates);
+        g->score, first, last, gates, g->phys, g->psrc, g->pdst);
   else
     k_mp_edge<H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last, gates);
+        g->score, first, last, gates, g->phys, g->psrc, g->pdst);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -552,7 +560,7 @@ static int mp_det_launch(const tmpnn_graph* g, const tmpnn_index* ix, const floa
   if (!g_init_done) { int rc0 = tmpnn_init(); if (rc0) return rc0; }
   k_mp_det<<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, ix->n_dets, ix->det_rows, agg, node_pack, g->logit, g->score, group == 0,
-      group == num_groups - 1, gates);
+      group == num_groups - 1, gates, g->phys);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

@@ -289,7 +289,8 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
              const int32_t* __restrict__ n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
              int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const unsigned char* __restrict__ image,
              float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
-             int32_t* __restrict__ status) {
+             int32_t* __restrict__ status, const int32_t* __restrict__ phys, const int32_t* __restrict__ psrc,
+             const int32_t* __restrict__ pdst) {
   extern __shared__ unsigned char smem_dyn[];
   const int total = tile_ptr[num_seqs];
   if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
@@ -337,7 +338,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     const float4* __restrict__ h4p = reinterpret_cast<const float4*>(h_in);
     const uint32_t ldh4 = (uint32_t)ldh >> 2, cl4 = ((uint32_t)col >> 2) + (uint32_t)l;
     // lane l < 8 of a group keeps src of row g + 16 l, lane l >= 8 keeps dst of row g + 16 (l - 8)
-    const int32_t* __restrict__ idx_arr = l < 8 ? src : dst;
+    // deferred compaction (phys != NULL): the input state sits at GLOBAL physical rows -- endpoints at
+    // psrc / pdst, the row itself at phys -- instead of slab base + logical row
+    const bool dfr = phys != nullptr;
+    const int32_t* __restrict__ idx_arr = dfr ? (l < 8 ? psrc : pdst) : (l < 8 ? src : dst);
     const int idx_row = g + 16 * (l & 7);
     int seq = 0;
     seek_seq(tile_ptr, num_seqs, blockIdx.x, seq);
@@ -345,20 +349,27 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     int r0 = (blockIdx.x - __ldg(tile_ptr + seq)) * TCM;                 // first slab row of the tile
     int nleft = __ldg(n_rows + seq) - r0;                                // rows of the slab from r0 on
     int idxv = idx_row < nleft ? __ldg(idx_arr + base + r0 + idx_row) : -1;
+    // physical row of this thread group's row (l & 7) of the tile (deferred compaction only)
+    int pownv = dfr ? __ldg(phys + base + r0 + min(idx_row, nleft - 1)) : 0;
     // Every load below is unconditional with a clamped (always valid) address: a predicated load
     // is compiled as load + predicated move, and the move would wait for the load right away,
     // which defeats the register pipeline.
     float4 own[8];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) own[p] = __ldg(h4p + (base + r0 + min(g + 16 * p, nleft - 1)) * ldh4 + cl4);
+    for (int p = 0; p < 8; ++p) {
+      const int sp = __shfl_sync(FULL, pownv, gl0 + p);
+      const uint32_t orow = dfr ? (uint32_t)sp : base + r0 + min(g + 16 * p, nleft - 1);
+      own[p] = __ldg(h4p + orow * ldh4 + cl4);
+    }
     float4 gs[2][2], gd[2][2];
     auto gather = [&](int buf, int round, uint32_t gbase, int iv) {
+      const uint32_t gb = dfr ? 0u : gbase;  // physical endpoints are global rows already
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int p = 2 * round + u;
         const int a = __shfl_sync(FULL, iv, gl0 + p), b = __shfl_sync(FULL, iv, gl0 + 8 + p);
-        gs[buf][u] = __ldg(h4p + (gbase + (uint32_t)max(a, 0)) * ldh4 + cl4);
-        gd[buf][u] = __ldg(h4p + (gbase + (uint32_t)max(b, 0)) * ldh4 + cl4);
+        gs[buf][u] = __ldg(h4p + (gb + (uint32_t)max(a, 0)) * ldh4 + cl4);
+        gd[buf][u] = __ldg(h4p + (gb + (uint32_t)max(b, 0)) * ldh4 + cl4);
       }
     };
     gather(0, 0, base, idxv);
@@ -369,7 +380,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
       // next tile (or this one again when it is the last: the loads are then simply unused)
       uint32_t nbase = base;
-      int nr0 = r0, nnleft = nleft, nidx = -1;
+      int nr0 = r0, nnleft = nleft, nidx = -1, npown = pownv;
       if (tile + stride < total) {
         seek_seq(tile_ptr, num_seqs, tile + stride, seq);
         nbase = (uint32_t)seq * (uint32_t)cap_rows;
@@ -377,8 +388,8 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         nnleft = __ldg(n_rows + seq) - nr0;
         // in flight for the whole tile; rows past the end of the slab repeat its last row (masked by the epilogue)
         nidx = __ldg(idx_arr + nbase + nr0 + min(idx_row, nnleft - 1));
+        if (dfr) npown = __ldg(phys + nbase + nr0 + min(idx_row, nnleft - 1));
       }
-      const uint32_t nown0 = (nbase + nr0) * ldh4 + cl4;
       float amax = 0.f;
       // x images first: they are free as soon as the previous tile of this stage left the tensor core
       mbar_wait(bar_xfree + 8 * stage, phase ^ 1u, status);
@@ -407,7 +418,9 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       for (int p = 0; p < 8; ++p) {
         const float4 h4 = own[p];
         // this row's slot of the next tile: HBM latency, one tile ahead
-        own[p] = __ldg(h4p + nown0 + (uint32_t)min(g + 16 * p, nnleft - 1) * ldh4);
+        const int sp = __shfl_sync(FULL, npown, gl0 + p);
+        const uint32_t orow = dfr ? (uint32_t)sp : nbase + nr0 + min(g + 16 * p, nnleft - 1);
+        own[p] = __ldg(h4p + orow * ldh4 + cl4);
         uint2 hh, hl;
         split4(h4, hh, hl, amax);
         const uint32_t off = sw128(g + 16 * p, l >> 1) + ((l & 1) << 3);
@@ -429,7 +442,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         }
       }
       __syncwarp();
-      base = nbase; r0 = nr0; nleft = nnleft; idxv = nidx;
+      base = nbase; r0 = nr0; nleft = nnleft; idxv = nidx; pownv = npown;
     }
   } else {
     // ================= epilogue =================
@@ -589,7 +602,8 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
   if (rc) return rc;
   k_mp_edge_tc<<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
-      (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status);
+      (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
+      g->psrc, g->pdst);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

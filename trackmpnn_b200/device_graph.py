@@ -14,7 +14,7 @@ from . import _lib as L
 
 
 class SlabGraph:
-    def __init__(self, num_seqs, cap_rows, device, with_labels=True, status=None):
+    def __init__(self, num_seqs, cap_rows, device, with_labels=True, status=None, deferred=False):
         self.num_seqs, self.cap_rows, self.device = int(num_seqs), int(cap_rows), device
         n = self.num_seqs * self.cap_rows
         i32 = dict(dtype=torch.int32, device=device)
@@ -28,6 +28,11 @@ class SlabGraph:
         self.score = torch.zeros(n, dtype=torch.float32, device=device)
         self.logit = torch.zeros(n, dtype=torch.float32, device=device)
         self.status = status if status is not None else torch.zeros(1, **i32)
+        # deferred compaction of h (TrackEngine): physical positions of every row and of its endpoints
+        self.phys = torch.zeros(n, **i32) if deferred else None
+        self.psrc = torch.zeros(n, **i32) if deferred else None
+        self.pdst = torch.zeros(n, **i32) if deferred else None
+        self.phys_end = torch.zeros(self.num_seqs, **i32) if deferred else None
         self._c = None
 
     @property
@@ -35,7 +40,8 @@ class SlabGraph:
         if self._c is None:
             self._c = L.Graph(self.num_seqs, self.cap_rows, L.ptr(self.n_rows), L.ptr(self.ts), L.ptr(self.det),
                               L.ptr(self.ass), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.label),
-                              L.ptr(self.score), L.ptr(self.logit), L.ptr(self.status))
+                              L.ptr(self.score), L.ptr(self.logit), L.ptr(self.status), L.ptr(self.phys),
+                              L.ptr(self.psrc), L.ptr(self.pdst), L.ptr(self.phys_end))
         return C.byref(self._c)
 
     def check_status(self):

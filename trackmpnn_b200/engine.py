@@ -35,8 +35,13 @@ def worst_case_rows(frame_counts, window):
 
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
-                 use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True):
-        """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays."""
+                 use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
+                 deferred_compaction=True):
+        """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
+
+        deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
+        through the position maps the compaction emits (tmpnn_graph.phys / psrc / pdst) and writes its output
+        densely, so the state only ever crosses HBM once per step in each direction."""
         self.model = model
         self.dev = device if device is not None else next(model.parameters()).device
         if self.dev.type != 'cuda':
@@ -55,14 +60,20 @@ class TrackEngine:
         self.t_hi = int(self.frames.t_max) + 1
         if cap_rows is None:
             cap_rows = max(worst_case_rows(counts[s], self.W + self.R) for s in range(self.S))
+            max_frame = int(counts.max()) if counts.size else 1
+            if deferred_compaction:
+                # a frame's detections are staged behind the previous (uncompacted) graph, and the slab's last
+                # row is the shared all-zero row the new association rows read
+                cap_rows += max_frame + 1
             cap_rows = max(64, (cap_rows + 63) // 64 * 64)
         self.cap_rows = int(cap_rows)
+        self.deferred = bool(deferred_compaction)
         max_frame = int(counts.max()) if counts.size else 1
         self.cap_new = max(1, 2 * self.S * max_frame)
         max_dets = int(max(worst_case_dets(counts[s], self.W + self.R) for s in range(self.S)))
         dev = self.dev
-        self.ga = SlabGraph(self.S, self.cap_rows, dev, with_labels=False)
-        self.gb = SlabGraph(self.S, self.cap_rows, dev, with_labels=False, status=self.ga.status)
+        self.ga = SlabGraph(self.S, self.cap_rows, dev, with_labels=False, deferred=self.deferred)
+        self.gb = SlabGraph(self.S, self.cap_rows, dev, with_labels=False, status=self.ga.status, deferred=self.deferred)
         self._g0, self._g1 = self.ga, self.gb
         n_all = self.S * self.cap_rows
         self.h_cur = torch.zeros((n_all, self.ldh), dtype=torch.float32, device=dev)
@@ -157,6 +168,8 @@ class TrackEngine:
                self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), L.stream())
         self._forward(g, self.h_alt, self.h_cur)
+        if self.deferred:  # the state now sits at the logical rows of h_cur
+            L.call('tmpnn_graph_phys_identity', g.c, L.stream())
         # update_graph re-associates from the previous scores before it appends (utils/graph.py:251-268).
         # Inside the loop that result is carried over from decode_tracks (same scores, and deletion
         # cannot change a survivor's association); after the initial forward it is computed here.
@@ -169,9 +182,11 @@ class TrackEngine:
         else:
             L.call('tmpnn_graph_associate', g.c, self.index.c, 0, L.ptr(self.st['active']), L.stream())
 
-    def _tick(self):
-        """One iteration of infer.py:60-87 for every sequence at t = *t_dev, then t += 1."""
+    def _tick(self, flip=False):
+        """One iteration of infer.py:60-87 for every sequence at t = *t_dev, then t += 1.  With deferred
+        compaction the state alternates between the two buffers (flip = odd tick: h_alt -> h_cur)."""
         g, go = self.ga, self.gb
+        h_in, h_out = (self.h_alt, self.h_cur) if (flip and self.deferred) else (self.h_cur, self.h_alt)
         st = L.stream()
         if self.use_hungarian:
             # update_graph re-solves the assignment on the graph decode_tracks left behind (utils/graph.py:247-249);
@@ -179,15 +194,17 @@ class TrackEngine:
             self.index.build(g, self.st['active'], structured=self.structured_index)
             self._associate(g)
         L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
-               L.ptr(self.h_cur), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
+               L.ptr(h_in), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
-        self._forward(g, self.h_cur, self.h_alt)
+        self._forward(g, h_in, h_out)
         self._associate(g)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
                L.ptr(self.keep), L.ptr(self.decode_scratch), st)
-        L.call('tmpnn_graph_compact', g.c, go.c, L.ptr(self.keep), L.ptr(self.h_alt), L.ptr(self.h_cur),
-               L.ptr(self.st['active']), L.ptr(self.h_cur), self.ldh, L.ptr(self.new_of_old),
+        # plain: move the survivors h_alt -> h_cur; deferred: emit the maps only (sequences that sat the step out
+        # are copied h_in -> h_out)
+        L.call('tmpnn_graph_compact', g.c, go.c, L.ptr(self.keep), L.ptr(h_out), L.ptr(h_in),
+               L.ptr(self.st['active']), L.ptr(h_out if self.deferred else h_in), self.ldh, L.ptr(self.new_of_old),
                L.ptr(self.compact_scratch), st)
         self.frames_done += self.st['active'].sum()
         self.t_dev += 1
@@ -224,7 +241,7 @@ class TrackEngine:
                 self._graph.replay()
                 t += 2
         while t < n_ticks:
-            self._tick()
+            self._tick(flip=bool(t & 1))
             self.ga, self.gb = self.gb, self.ga
             t += 1
         self.ticks = n_ticks
@@ -237,9 +254,9 @@ class TrackEngine:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._tick()
+            self._tick(flip=False)
             self.ga, self.gb = self.gb, self.ga
-            self._tick()
+            self._tick(flip=True)
             self.ga, self.gb = self.gb, self.ga
         self._graph = g
 

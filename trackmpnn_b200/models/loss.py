@@ -17,7 +17,7 @@ def _graph_with_labels(wg, labels):
     lab = labels.detach().to(device=wg.device, dtype=torch.int32).contiguous()
     g = wg.g
     c = L.Graph(g.num_seqs, g.cap_rows, L.ptr(g.n_rows), L.ptr(g.ts), L.ptr(g.det), L.ptr(g.ass), L.ptr(g.src),
-                L.ptr(g.dst), L.ptr(lab), L.ptr(g.score), L.ptr(g.logit), L.ptr(g.status))
+                L.ptr(g.dst), L.ptr(lab), L.ptr(g.score), L.ptr(g.logit), L.ptr(g.status), None, None, None, None)
     return c, lab
 
 
