@@ -209,9 +209,19 @@ int tmpnn_mp_det_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h
  * kernel to ~2e-6; sets TMPNN_FLAG_TC_RANGE if an activation exceeds the fp16 range. */
 size_t tmpnn_gru_tc_pack_bytes(void);
 int tmpnn_pack_gru_tc(const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh,
-                      const float *head_w, const float *head_b, void *packed, void *stream);
+                      const float *head_w, const float *head_b, int concat, void *packed, void *stream);
 int tmpnn_mp_edge_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                          int group, int num_groups, const void *edge_image, void *stream);
+/* Same step with the endpoints prepared once per DETECTION row instead of once per association row (both
+ * msg_types; edge_image packed with the same `concat`).  gi = h[src] W_s^T -+ h[dst] W_d^T is linear in the two
+ * endpoints: a first kernel writes every detection's fp16 hi/lo image into det_img (same geometry as h: S*cap_rows
+ * rows of ldh floats, indexed by logical row; scratch, any content) and its source-side gate contribution with the
+ * biases folded in into det_p [index cap_dets][192] (fp32 FMA); the step kernel then copies the far endpoint's
+ * image (cp.async), multiplies it on the tensor cores (negated for 'diff') and adds det_p[src] in the epilogue.
+ * w_ih / b_ih / b_hh: the edge GRUCell's parameters (weight_ih [192][64 or 128]). */
+int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                             int group, int num_groups, int concat, const void *edge_image, const float *w_ih,
+                             const float *b_ih, const float *b_hh, float *det_img, float *det_p, void *stream);
 
 /* ---- training: backward of the step and the losses (train.py:65-134, models/loss.py) ------- */
 

@@ -16,7 +16,9 @@ TOL = 1e-4
 def _model(gold, dev, train=False, tensor=False):
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     m = gold.meta
-    model = TrackMPNN(m['features'], m['ncategories'], 64, m.get('nattheads', 0), m['msg_type'], use_tensor_cores=tensor)
+    model = TrackMPNN(m['features'], m['ncategories'], 64, m.get('nattheads', 0), m['msg_type'], use_tensor_cores=bool(tensor))
+    if tensor:
+        model.tensor_core_kernel = tensor   # 'gather' | 'pre'
     sd = {k: torch.from_numpy(v) for k, v in gold.params().items()}
     model.load_state_dict(sd, strict=True)
     model.to(dev)
@@ -48,15 +50,16 @@ def _fix(scores, y_pred, tp):
 INFER = golden_names('infer')
 
 
-@pytest.mark.parametrize('tensor', [False, True], ids=['fma', 'tcgen05'])
+@pytest.mark.parametrize('tensor', [False, 'gather', 'pre'], ids=['fma', 'tcgen05', 'tcgen05-pre'])
 @pytest.mark.parametrize('name', INFER)
 def test_infer_free_running(name, tensor):
-    """tensor=False: fp32 FMA kernel; tensor=True: tcgen05 kernel (3-term fp16 split) -- same 1e-4 bar."""
+    """tensor=False: fp32 FMA kernel; 'gather' / 'pre': the tcgen05 kernels (3-term fp16 split; endpoints gathered
+    per association row, or prepared once per detection row) -- same 1e-4 bar."""
     from trackmpnn_b200.utils.graph import initialize_graph, update_graph, prune_graph, decode_tracks
     gold = Golden(name)
     m = gold.meta
-    if tensor and m['msg_type'] != 'diff':
-        pytest.skip('the tensor-core kernel covers msg_type diff')
+    if tensor == 'gather' and m['msg_type'] != 'diff':
+        pytest.skip('the gather-and-split tensor-core kernel covers msg_type diff')
     dev = torch.device('cuda:0')
     model = _model(gold, dev, tensor=tensor)
     X, y = torch.from_numpy(gold.X).to(dev), torch.from_numpy(gold.y).to(dev)

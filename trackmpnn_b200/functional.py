@@ -47,7 +47,7 @@ def packed_cells(model):
 
 
 def packed_cells_tc(model):
-    """fp16 hi/lo UMMA weight images of the edge cells (tensor-core path, msg_type 'diff' only)."""
+    """fp16 hi/lo UMMA weight images of the edge cells (tensor-core path)."""
     cache = model.__dict__.setdefault('_tmpnn_pack_cache_tc', _PackCache())
     params = []
     for gru in model.factor_grus:
@@ -60,14 +60,12 @@ def packed_cells_tc(model):
         nbytes = int(L.lib().tmpnn_gru_tc_pack_bytes())
         for g, gru in enumerate(model.factor_grus):
             cell, head = gru.edge_gru, model.output_transform_edge
-            if gru.msg_type != 'diff':
-                packs.append(None)
-                continue
             out = torch.empty(nbytes, dtype=torch.uint8, device=cell.weight_ih.device)
             hw = head.weight.detach()[0, g * H:(g + 1) * H]
+            # 'concat': the image holds the far-endpoint half W_ih[:, 64:128] (only tmpnn_mp_edge_fwd_tc_pre takes it)
             L.call('tmpnn_pack_gru_tc', L.ptr(cell.weight_ih.detach()), L.ptr(cell.weight_hh.detach()),
                    L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(hw), L.ptr(head.bias.detach()),
-                   L.ptr(out), L.stream())
+                   int(gru.msg_type == 'concat'), L.ptr(out), L.stream())
             packs.append(out)
         cache.key, cache.packs = key, packs
     return cache.packs
@@ -78,8 +76,6 @@ TENSOR_MIN_ROWS = 8192  # below this a window graph cannot fill the 148 x 128-ro
 
 def use_tensor_path(model, n_rows):
     mode = getattr(model, 'use_tensor_cores', 'auto')
-    if any(g.msg_type != 'diff' for g in model.factor_grus):
-        return False
     if mode == 'auto':
         return n_rows >= TENSOR_MIN_ROWS
     return bool(mode)
@@ -137,6 +133,30 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
     return alphas if keep_attention else None
 
 
+def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, pre=True):
+    """Edge rows of feature group g on the tensor cores.  pre: endpoints prepared once per detection row
+    (tmpnn_mp_edge_fwd_tc_pre; both msg_types); else the gather-and-split kernel ('diff' only)."""
+    gru = model.factor_grus[g]
+    concat = int(gru.msg_type == 'concat')
+    st = L.stream()
+    if not pre:
+        if concat:
+            raise L.TmpnnError("tmpnn_mp_edge_fwd_tc handles msg_type 'diff' only")
+        L.call('tmpnn_mp_edge_fwd_tc', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(image), st)
+        return
+    n_all = graph.num_seqs * graph.cap_rows
+    img = scratch.get('det_img')
+    if img is None or img.shape != (n_all, ldh):
+        img = scratch['det_img'] = torch.empty((n_all, ldh), dtype=torch.float32, device=h_in.device)
+    dp = scratch.get('det_p')
+    if dp is None or dp.shape[0] < index.cap_dets:
+        dp = scratch['det_p'] = torch.empty((index.cap_dets, 3 * H), dtype=torch.float32, device=h_in.device)
+    cell = gru.edge_gru
+    L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
+           L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
+           L.ptr(dp), st)
+
+
 def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
     """One message-passing step over all feature groups (K1-det, edge rows, detection rows).
     Returns the per-group attention (list of per-head alpha tensors, or None)."""
@@ -150,7 +170,9 @@ def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=F
         concat = int(model.factor_grus[g].msg_type == 'concat')
         att.append(aggregate_for_dets(model.factor_grus[g], graph, index, h_in, ldh, g * H, agg, None, keep_attention))
         if tensor:
-            L.call('tmpnn_mp_edge_fwd_tc', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(tc[g]), st)
+            scratch = model.__dict__.setdefault('_tmpnn_tc_scratch', {})
+            edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, tc[g], scratch,
+                         pre=getattr(model, 'tensor_core_kernel', 'pre') == 'pre')
         else:
             L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
         L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
