@@ -54,6 +54,7 @@ GAT_SEEDS = [108, 41, 52, 68, 49, 44, 105]
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True),
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True, kernel='gather'),
     dict(seeds=[35, 36, 40], msg_type='concat', ret=2, graph=True, gap=(), tensor=True),
+    dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True, kernel='pre'),
     dict(seeds=[108, 84, 77, 100, 72, 32, 56], msg_type='diff', ret=0, graph=True, gap=(), hungarian=True),
     dict(seeds=GAT_SEEDS, msg_type='diff', ret=0, graph=True, gap=(), heads=2),
     dict(seeds=[84, 100, 48, 125, 56], msg_type='diff', ret=2, graph=False, gap=(), hungarian=True),
@@ -69,7 +70,7 @@ def test_engine_matches_oracle(cfg, deferred):
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],
                       tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False),
-                      deferred_compaction=deferred, tensor_kernel=cfg.get('kernel', 'pre'))
+                      deferred_compaction=deferred, tensor_kernel=cfg.get('kernel', 'pre2'))
     outs, stats = eng.run().results()
     tot_e = tot_f = 0
     for (X, y), got in zip(seqs, outs):

@@ -29,202 +29,12 @@
 // are reusable), hfree[2] (epilogue -> producers: the stage's h images, which the epilogue reads the
 // previous state from and then re-uses as its transpose buffer, are reusable),
 // tfree[2] (epilogue -> MMA: accumulator stage drained).
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
-constexpr int H = TMPNN_HIDDEN;
-constexpr int TCM = 128;            // rows per tile == UMMA M
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
 constexpr int TC_THREADS = 32 * (EPI_WARPS + PROD_WARPS);  // 512 -> 128 registers per thread
-constexpr int B_BYTES = 192 * 128;  // one [192 x 64] fp16 weight image
-constexpr int OFF_BX_HI = 0, OFF_BX_LO = B_BYTES, OFF_BH_HI = 2 * B_BYTES, OFF_BH_LO = 3 * B_BYTES;
-constexpr int OFF_BIAS = 4 * B_BYTES;            // 4 x 64 floats: -log2e (b_ir+b_hr), -log2e (b_iz+b_hz), b_in, b_hn
-constexpr int OFF_HEADW = OFF_BIAS + 1024;       // 64 floats
-constexpr int OFF_HEADB = OFF_HEADW + 256;       // 1 float (+ pad)
-constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // what tmpnn_pack_gru_tc writes
-constexpr int OFF_BAR = IMAGE_BYTES;             // 10 mbarriers + tmem pointer, inside the alignment gap
-constexpr int OFF_DOT = OFF_BAR + 96;            // 128 floats: head partial sums of the upper column half
-constexpr int OFF_A = 98 * 1024;                 // first A stage (1024-aligned)
-constexpr int A_PART = TCM * 128;                // [128 rows x 64 fp16] = 16 KB
-constexpr int A_STAGE = 4 * A_PART;              // x_hi, x_lo, h_hi, h_lo
-constexpr int SMEM_BYTES = OFF_A + 2 * A_STAGE + 1024;  // + slack to 1024-align the base
-static_assert(OFF_DOT + 512 <= OFF_A, "barriers and head partials must fit in the gap");
-static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
-constexpr float LOG2E = 1.4426950408889634f;
-
-// ---- PTX helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug must never hang the GPU -- after 2 s the kernel flags an error
-// and runs to completion with garbage instead.  Failed polls back off with nanosleep so that a
-// waiting role does not steal issue slots from the roles doing work on the same SM sub-partition.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spin = 0;
-  unsigned long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
-    if ((++spin & 1023u) == 0) {
-      const unsigned long long t = globaltimer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) {
-        atomicOr(status, TMPNN_FLAG_TC_TIMEOUT);
-        return;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address            bits [0,14)
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset       bits [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version 1 (Blackwell)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128
-__device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// byte offset of 16-byte chunk c (8 fp16 along K) of row r inside a [rows x 128 B] swizzled image
-__device__ __forceinline__ uint32_t sw128(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-
-// 4 floats -> 4 fp16 "hi" (round to nearest) + 4 fp16 "lo" (the residual)
-__device__ __forceinline__ void split4(const float4 a, uint2& hi, uint2& lo, float& amax) {
-  amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
-  const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
-  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-  const __half2 l01 = __floats2half2_rn(a.x - f01.x, a.y - f01.y), l23 = __floats2half2_rn(a.z - f23.x, a.w - f23.y);
-  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): halves the issue slots of the gate math
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
-  return r;
-}
-__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
-  float a, b;
-  up2(v, a, b);
-  return pk2(ex2_approx(a), ex2_approx(b));
-}
-__device__ __forceinline__ f32x2 rcp_2(f32x2 v) {
-  float a, b;
-  up2(v, a, b);
-  return pk2(rcp_approx(a), rcp_approx(b));
-}
-__device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// first sequence whose tile range contains `tile`, advancing a cursor (tiles are visited in
-// increasing order, so this is 0-1 steps per call after the first)
-__device__ __forceinline__ void seek_seq(const int32_t* __restrict__ tile_ptr, int num_seqs, int tile, int& seq) {
-  while (seq + 1 < num_seqs && __ldg(tile_ptr + seq + 1) <= tile) ++seq;
-}
 
 // ---- weight image ----------------------------------------------------------------------------
 __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
@@ -253,37 +63,6 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
     float* hb = reinterpret_cast<float*>(img + OFF_HEADB);
     hb[0] = head_b[0]; hb[1] = hb[2] = hb[3] = 0.f;
   }
-}
-
-// ---- MMA issue for one 128-row tile (one thread) ------------------------------------------------
-__device__ __forceinline__ void issue_tile_mma(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags,
-                                               uint32_t bar_xfree) {
-  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
-  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-  // x part: columns [0,192) = r | z | i_n
-  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
-  const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
-  uint32_t acc = 0;
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, acc);
-      acc = 1;
-    }
-  umma_commit(bar_xfree);  // the x images are reusable once these MMAs retire
-  // h part: columns [0,128) += r | z, columns [192,256) = h_n
-  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
-  const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
-  uint32_t acc_n = 0;
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
-      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
-      acc_n = 1;
-    }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
@@ -720,68 +499,13 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   }
 }
 
-// ---- per-detection preparation for PRE -------------------------------------------------------------
-// One warp per detection row: (a) its fp16 hi/lo image, written at the row's LOGICAL position of det_img (geometry of
-// h: 64 hi halves then 64 lo halves in the row's 256 B), which is what the producers copy for the far endpoint of
-// an association row; (b) P'[k] = the row's source-side contribution to the input gates, fp32 FMA:
-//   P = h W_ih[:, 0:64]^T,  P'[0:128) = -log2e (P + b_ih + b_hh),  P'[128:192) = P + b_ih.
-constexpr int PREP_SMEM = (64 * 192 + 8 * 64 + 192) * 4;
-__global__ void __launch_bounds__(256)
-k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* __restrict__ n_dets,
-              const int32_t* __restrict__ det_rows, const int32_t* __restrict__ phys, const float* __restrict__ w_ih, int ldw,
-              const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ det_img,
-              float* __restrict__ det_p, int32_t* __restrict__ status) {
-  extern __shared__ float prep_sm[];
-  float* wt = prep_sm;             // [64][192]: W_ih^T (source half)
-  float* hr = prep_sm + 64 * 192;  // [8][64]
-  float* bs = hr + 8 * 64;         // [192]
-  const int nd = *n_dets;
-  if ((int)blockIdx.x * 8 >= nd) return;
-  for (int i = threadIdx.x; i < 192 * 64; i += blockDim.x) {
-    const int n = i % 192, c = i / 192;
-    wt[c * 192 + n] = w_ih[n * ldw + c];
-  }
-  for (int n = threadIdx.x; n < 192; n += blockDim.x) bs[n] = b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* hw = hr + w * 64;
-  for (int k = blockIdx.x * 8 + w; k < nd; k += gridDim.x * 8) {
-    const int row = det_rows[k];
-    const size_t pr = phys ? (size_t)phys[row] : (size_t)row;  // deferred compaction: the state sits at the physical row
-    const float2 v = *reinterpret_cast<const float2*>(h_in + pr * ldh + col + 2 * lane);
-    hw[2 * lane] = v.x;
-    hw[2 * lane + 1] = v.y;
-    const __half2 hi = __floats2half2_rn(v.x, v.y);
-    const float2 f = __half22float2(hi);
-    const __half2 lo = __floats2half2_rn(v.x - f.x, v.y - f.y);
-    uint32_t* ib = reinterpret_cast<uint32_t*>(det_img + (size_t)row * ldh + col);
-    ib[lane] = *reinterpret_cast<const uint32_t*>(&hi);
-    ib[32 + lane] = *reinterpret_cast<const uint32_t*>(&lo);
-    if (fmaxf(fabsf(v.x), fabsf(v.y)) > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
-    __syncwarp();
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int c = 0; c < 64; ++c) {
-      const float hv = hw[c];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) acc[q] = fmaf(hv, wt[c * 192 + lane + 32 * q], acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int n = lane + 32 * q;
-      const float val = acc[q] + bs[n];
-      det_p[(size_t)k * 192 + n] = q < 4 ? -LOG2E * val : val;
-    }
-    __syncwarp();
-  }
-}
-
 }  // namespace
 
 int tmpnn_init_tc() {
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_det_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
+  int rc = tmpnn_init_tc2();
+  if (rc) return rc;
   return TMPNN_OK;
 }
 
@@ -822,9 +546,8 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
   int rc = tmpnn_init();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  k_det_prepare<<<TMPNN_SM_COUNT * 2, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys, w_ih,
-                                                           concat ? 128 : 64, b_ih, b_hh, det_img, det_p, g->status);
-  TMPNN_LAUNCH_CHECK();
+  rc = tmpnn_det_prepare_launch(g, ix, h_in, ldh, group, concat, w_ih, b_ih, b_hh, det_img, det_p, st);
+  if (rc) return rc;
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc<true><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,

@@ -36,7 +36,7 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='pre'):
+                 deferred_compaction=True, tensor_kernel='pre2'):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
@@ -113,10 +113,10 @@ class TrackEngine:
             self.hung_scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
         diff = all(g.msg_type == 'diff' for g in model.factor_grus)
         # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise.
-        # tensor_kernel 'pre': endpoints prepared once per detection row (both msg_types); 'gather': the
+        # tensor_kernel 'pre2' / 'pre': endpoints prepared once per detection row (both msg_types); 'gather': the
         # gather-and-split kernel ('diff' only)
         self.tensor_kernel = tensor_kernel
-        self.tensor = (diff or tensor_kernel == 'pre') and (
+        self.tensor = (diff or tensor_kernel != 'gather') and (
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self._tc_scratch = {}
         self._gat_scratch = {}
@@ -153,7 +153,7 @@ class TrackEngine:
                 e0.record()
             if self.tensor:
                 F_.edge_step_tc(model, g, self.index, h_in, h_out, self.ldh, grp, self.G, tc[grp], self._tc_scratch,
-                                pre=self.tensor_kernel == 'pre')
+                                kernel=self.tensor_kernel)
             else:
                 L.call('tmpnn_mp_edge_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G, concat,
                        L.ptr(packs[grp][0]), st)

@@ -133,13 +133,16 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
     return alphas if keep_attention else None
 
 
-def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, pre=True):
-    """Edge rows of feature group g on the tensor cores.  pre: endpoints prepared once per detection row
-    (tmpnn_mp_edge_fwd_tc_pre; both msg_types); else the gather-and-split kernel ('diff' only)."""
+def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, kernel='pre2'):
+    """Edge rows of feature group g on the tensor cores.  kernel 'pre2' / 'pre': endpoints prepared once per
+    detection row (tmpnn_mp_edge_fwd_tc2 / tmpnn_mp_edge_fwd_tc_pre; both msg_types); 'gather': the gather-and-split
+    kernel ('diff' only)."""
     gru = model.factor_grus[g]
     concat = int(gru.msg_type == 'concat')
     st = L.stream()
-    if not pre:
+    if kernel not in ('pre2', 'pre', 'gather'):
+        raise ValueError(f'unknown tensor-core kernel {kernel!r}')
+    if kernel == 'gather':
         if concat:
             raise L.TmpnnError("tmpnn_mp_edge_fwd_tc handles msg_type 'diff' only")
         L.call('tmpnn_mp_edge_fwd_tc', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(image), st)
@@ -152,9 +155,18 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, pr
     if dp is None or dp.shape[0] < index.cap_dets:
         dp = scratch['det_p'] = torch.empty((index.cap_dets, 3 * H), dtype=torch.float32, device=h_in.device)
     cell = gru.edge_gru
-    L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
+    if kernel == 'pre':
+        L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
+               L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
+               L.ptr(dp), st)
+        return
+    nb = int(L.lib().tmpnn_tc_tile_table_bytes(graph.num_seqs, graph.cap_rows))
+    tab = scratch.get('tile_tab')
+    if tab is None or tab.numel() * 16 < nb:
+        tab = scratch['tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
+    L.call('tmpnn_mp_edge_fwd_tc2', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
            L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
-           L.ptr(dp), st)
+           L.ptr(dp), L.ptr(tab), st)
 
 
 def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
@@ -172,7 +184,7 @@ def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=F
         if tensor:
             scratch = model.__dict__.setdefault('_tmpnn_tc_scratch', {})
             edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, tc[g], scratch,
-                         pre=getattr(model, 'tensor_core_kernel', 'pre') == 'pre')
+                         kernel=getattr(model, 'tensor_core_kernel', 'pre2'))
         else:
             L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
         L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
