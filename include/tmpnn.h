@@ -222,14 +222,6 @@ int tmpnn_mp_edge_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const floa
 int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                              int group, int num_groups, int concat, const void *edge_image, const float *w_ih,
                              const float *b_ih, const float *b_hh, float *det_img, float *det_p, void *stream);
-/* Second generation of the same step (csrc/mp_step_tc2.cu): 16 epilogue + 4 producer warps, tiles located through
- * a table {slab's first row, tile's first slab row, rows left} that the call rebuilds into tile_table
- * (tmpnn_tc_tile_table_bytes(), 16-byte aligned scratch) when group == 0.  Same arguments and results otherwise. */
-size_t tmpnn_tc_tile_table_bytes(int num_seqs, int cap_rows);
-int tmpnn_mp_edge_fwd_tc2(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
-                          int group, int num_groups, int concat, const void *edge_image, const float *w_ih,
-                          const float *b_ih, const float *b_hh, float *det_img, float *det_p, void *tile_table,
-                          void *stream);
 
 /* ---- training: backward of the step and the losses (train.py:65-134, models/loss.py) ------- */
 

@@ -18,7 +18,7 @@ def _model(gold, dev, train=False, tensor=False):
     m = gold.meta
     model = TrackMPNN(m['features'], m['ncategories'], 64, m.get('nattheads', 0), m['msg_type'], use_tensor_cores=bool(tensor))
     if tensor:
-        model.tensor_core_kernel = tensor   # 'gather' | 'pre' | 'pre2'
+        model.tensor_core_kernel = tensor   # 'gather' | 'pre'
     sd = {k: torch.from_numpy(v) for k, v in gold.params().items()}
     model.load_state_dict(sd, strict=True)
     model.to(dev)
@@ -50,7 +50,7 @@ def _fix(scores, y_pred, tp):
 INFER = golden_names('infer')
 
 
-@pytest.mark.parametrize('tensor', [False, 'gather', 'pre', 'pre2'], ids=['fma', 'tcgen05', 'tcgen05-pre', 'tcgen05-pre2'])
+@pytest.mark.parametrize('tensor', [False, 'gather', 'pre'], ids=['fma', 'tcgen05', 'tcgen05-pre'])
 @pytest.mark.parametrize('name', INFER)
 def test_infer_free_running(name, tensor):
     """tensor=False: fp32 FMA kernel; 'gather' / 'pre': the tcgen05 kernels (3-term fp16 split; endpoints gathered

@@ -70,7 +70,7 @@ def test_engine_matches_oracle(cfg, deferred):
     seqs = _sequences(cfg['seeds'], gap=cfg['gap'])
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=cfg['ret'], use_cuda_graph=cfg['graph'],
                       tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False),
-                      deferred_compaction=deferred, tensor_kernel=cfg.get('kernel', 'pre2'))
+                      deferred_compaction=deferred, tensor_kernel=cfg.get('kernel', 'auto'))
     outs, stats = eng.run().results()
     tot_e = tot_f = 0
     for (X, y), got in zip(seqs, outs):

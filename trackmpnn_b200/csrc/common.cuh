@@ -9,11 +9,6 @@
 #define TMPNN_SM_COUNT 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of it
 
 int tmpnn_set_error(int code, const char* fmt, ...);
-int tmpnn_init_tc2();
-// per-detection fp16 hi/lo images + source-side gate contributions for the 'pre' tensor-core kernels (mp_step_tc2.cu)
-int tmpnn_det_prepare_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, int ldh, int group, int concat,
-                             const float* w_ih, const float* b_ih, const float* b_hh, float* det_img, float* det_p,
-                             cudaStream_t st);
 
 #define TMPNN_CUDA_TRY(expr)                                                                   \
   do {                                                                                         \

@@ -499,13 +499,68 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   }
 }
 
+// ---- per-detection preparation -------------------------------------------------------------------------
+// One warp per detection row: (a) its fp16 hi/lo image, written at the row's LOGICAL position of det_img (geometry of
+// h: 64 hi halves then 64 lo halves in the row's 256 B), which is what the producers copy for the far endpoint of
+// an association row; (b) P'[k] = the row's source-side contribution to the input gates, fp32 FMA:
+//   P = h W_ih[:, 0:64]^T,  P'[0:128) = -log2e (P + b_ih + b_hh),  P'[128:192) = P + b_ih.
+constexpr int PREP_SMEM = (64 * 192 + 8 * 64 + 192) * 4;
+__global__ void __launch_bounds__(256)
+k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* __restrict__ n_dets,
+              const int32_t* __restrict__ det_rows, const int32_t* __restrict__ phys, const float* __restrict__ w_ih, int ldw,
+              const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ det_img,
+              float* __restrict__ det_p, int32_t* __restrict__ status) {
+  extern __shared__ float prep_sm[];
+  float* wt = prep_sm;             // [64][192]: W_ih^T (source half)
+  float* hr = prep_sm + 64 * 192;  // [8][64]
+  float* bs = hr + 8 * 64;         // [192]
+  const int nd = *n_dets;
+  if ((int)blockIdx.x * 8 >= nd) return;
+  for (int i = threadIdx.x; i < 192 * 64; i += blockDim.x) {
+    const int n = i % 192, c = i / 192;
+    wt[c * 192 + n] = w_ih[n * ldw + c];
+  }
+  for (int n = threadIdx.x; n < 192; n += blockDim.x) bs[n] = b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* hw = hr + w * 64;
+  for (int k = blockIdx.x * 8 + w; k < nd; k += gridDim.x * 8) {
+    const int row = det_rows[k];
+    const size_t pr = phys ? (size_t)phys[row] : (size_t)row;  // deferred compaction: the state sits at the physical row
+    const float2 v = *reinterpret_cast<const float2*>(h_in + pr * ldh + col + 2 * lane);
+    hw[2 * lane] = v.x;
+    hw[2 * lane + 1] = v.y;
+    const __half2 hi = __floats2half2_rn(v.x, v.y);
+    const float2 f = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(v.x - f.x, v.y - f.y);
+    uint32_t* ib = reinterpret_cast<uint32_t*>(det_img + (size_t)row * ldh + col);
+    ib[lane] = *reinterpret_cast<const uint32_t*>(&hi);
+    ib[32 + lane] = *reinterpret_cast<const uint32_t*>(&lo);
+    if (fmaxf(fabsf(v.x), fabsf(v.y)) > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
+    __syncwarp();
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float hv = hw[c];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[q] = fmaf(hv, wt[c * 192 + lane + 32 * q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int n = lane + 32 * q;
+      const float val = acc[q] + bs[n];
+      det_p[(size_t)k * 192 + n] = q < 4 ? -LOG2E * val : val;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 int tmpnn_init_tc() {
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  int rc = tmpnn_init_tc2();
-  if (rc) return rc;
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_det_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
   return TMPNN_OK;
 }
 
@@ -546,8 +601,9 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
   int rc = tmpnn_init();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = tmpnn_det_prepare_launch(g, ix, h_in, ldh, group, concat, w_ih, b_ih, b_hh, det_img, det_p, st);
-  if (rc) return rc;
+  k_det_prepare<<<TMPNN_SM_COUNT * 2, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys, w_ih,
+                                                           concat ? 128 : 64, b_ih, b_hh, det_img, det_p, g->status);
+  TMPNN_LAUNCH_CHECK();
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc<true><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,

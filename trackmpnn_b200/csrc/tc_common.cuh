@@ -1,4 +1,4 @@
-// tc_common.cuh -- shared pieces of the tcgen05 edge-step kernels (mp_step_tc.cu, mp_step_tc2.cu):
+// tc_common.cuh -- shared pieces of the tcgen05 edge-step kernels (mp_step_tc.cu):
 // shared-memory layout, PTX wrappers (mbarrier, tcgen05.mma / ld / commit, descriptors), the fp16 hi/lo
 // split and the MMA issue sequence of one 128-row tile.
 #pragma once

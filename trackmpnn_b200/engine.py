@@ -36,7 +36,7 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='pre2'):
+                 deferred_compaction=True, tensor_kernel='auto'):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
@@ -113,8 +113,8 @@ class TrackEngine:
             self.hung_scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
         diff = all(g.msg_type == 'diff' for g in model.factor_grus)
         # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise.
-        # tensor_kernel 'pre2' / 'pre': endpoints prepared once per detection row (both msg_types); 'gather': the
-        # gather-and-split kernel ('diff' only)
+        # tensor_kernel 'gather': endpoints gathered and split per association row ('diff' only); 'pre': prepared
+        # once per detection row (both msg_types); 'auto': gather for diff, pre for concat
         self.tensor_kernel = tensor_kernel
         self.tensor = (diff or tensor_kernel != 'gather') and (
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))

@@ -133,14 +133,16 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
     return alphas if keep_attention else None
 
 
-def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, kernel='pre2'):
-    """Edge rows of feature group g on the tensor cores.  kernel 'pre2' / 'pre': endpoints prepared once per
-    detection row (tmpnn_mp_edge_fwd_tc2 / tmpnn_mp_edge_fwd_tc_pre; both msg_types); 'gather': the gather-and-split
-    kernel ('diff' only)."""
+def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, kernel='auto'):
+    """Edge rows of feature group g on the tensor cores.  kernel 'gather': endpoints gathered, subtracted and split
+    per association row (tmpnn_mp_edge_fwd_tc, msg_type 'diff' only; the faster one today); 'pre': endpoints prepared
+    once per detection row (tmpnn_mp_edge_fwd_tc_pre; both msg_types); 'auto': gather for diff, pre for concat."""
     gru = model.factor_grus[g]
     concat = int(gru.msg_type == 'concat')
     st = L.stream()
-    if kernel not in ('pre2', 'pre', 'gather'):
+    if kernel == 'auto':
+        kernel = 'pre' if concat else 'gather'
+    if kernel not in ('pre', 'gather'):
         raise ValueError(f'unknown tensor-core kernel {kernel!r}')
     if kernel == 'gather':
         if concat:
@@ -155,18 +157,9 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
     if dp is None or dp.shape[0] < index.cap_dets:
         dp = scratch['det_p'] = torch.empty((index.cap_dets, 3 * H), dtype=torch.float32, device=h_in.device)
     cell = gru.edge_gru
-    if kernel == 'pre':
-        L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
-               L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
-               L.ptr(dp), st)
-        return
-    nb = int(L.lib().tmpnn_tc_tile_table_bytes(graph.num_seqs, graph.cap_rows))
-    tab = scratch.get('tile_tab')
-    if tab is None or tab.numel() * 16 < nb:
-        tab = scratch['tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
-    L.call('tmpnn_mp_edge_fwd_tc2', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
+    L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
            L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
-           L.ptr(dp), L.ptr(tab), st)
+           L.ptr(dp), st)
 
 
 def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
@@ -184,7 +177,7 @@ def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=F
         if tensor:
             scratch = model.__dict__.setdefault('_tmpnn_tc_scratch', {})
             edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, tc[g], scratch,
-                         kernel=getattr(model, 'tensor_core_kernel', 'pre2'))
+                         kernel=getattr(model, 'tensor_core_kernel', 'auto'))
         else:
             L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
         L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
