@@ -69,6 +69,16 @@ def make_sequences(a, rank):
     return seqs
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per association row of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json)."""
+    p = os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)[kernel]['dram_bytes_per_edge_row'])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -316,8 +326,24 @@ def main():
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     kname = ('k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'
              if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
+    # detection aggregation (K1): every association row's state is read for its two endpoints; compulsory bytes
+    # = one read of each row + one 256 B sum per detection (SURVEY.md 8d "K1")
+    a_ms = sum(p[3].elapsed_time(p[4]) for p in prof)
+    agg_bytes = 256.0 * k_edges + 256.0 * dets
+    agg = {'kernel': 'k_aggregate_dets (CSR segmented signed sum of incident association rows, CTA per detection)',
+           'bound': 'hbm', 'achieved': agg_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0, 'peak': hbm_peak, 'unit': 'GB/s',
+           'frac': agg_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak if a_ms > 0 else 0.0, 'avg_launch_ms': a_ms / max(1, len(prof)),
+           'share_of_step': a_ms / ms if ms > 0 else None, 'algorithmic_bytes': '256 B per association row + 256 B per detection',
+           'traffic': None}
+    n_l = max(1, len(prof))
+    tr_e, tr_a = (measured_traffic('k_mp_edge_tc') if eng.tensor else None), measured_traffic('k_aggregate_dets')
+    agg['traffic'] = tr_a * k_edges / n_l if tr_a else None
+    agg['traffic_source'] = 'profiles/r01_dram_traffic.json (ncu dram bytes per association row x rows per launch)'
     roof = {'kernel': kname, 'bound': 'hbm',
-            'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+            'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            'traffic': tr_e * k_edges / n_l if tr_e else None,
+            'traffic_source': 'profiles/r01_dram_traffic.json (ncu dram bytes per association row x rows per launch)',
+            'algorithmic_bytes_per_launch': BYTES_PER_EDGE_UPDATE * k_edges / n_l,
             'peak_source': peak_src, 'launches_timed': len(prof), 'avg_launch_ms': k_ms / max(1, len(prof)),
             'share_of_step': k_ms / ms if ms > 0 else None,
             'fp32_tflops': FLOP_PER_ROW_UPDATE * k_edges / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
@@ -374,7 +400,7 @@ def main():
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
                           'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
-               'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'train': train}
+               'roofline': roof, 'roofline_aggregation': agg, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'train': train}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

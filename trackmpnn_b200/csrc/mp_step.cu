@@ -220,46 +220,55 @@ extern "C" int tmpnn_input_bn_relu_linear2(const float* a, const float* mean, co
 // ------------------------------------------------------------------------------------------
 // K1: aggregation
 // ------------------------------------------------------------------------------------------
-// One warp per detection: the two half-warps stream alternate incident rows (16 lanes x
-// float4 = one 256 B row per half-warp per load, 4 rows in flight per half-warp), past
-// edges subtract, future edges add.  Fixed traversal order -> bit-reproducible sums.
+// One CTA per detection: its 16 half-warps stream the incident rows round-robin (16 lanes x float4 = one 256 B
+// row per half-warp per load, 4 rows in flight per half-warp), past edges subtract, future edges add; the 16
+// partial sums are combined in a fixed order -> bit-reproducible.  A CTA (not a warp) per detection keeps the
+// detections in flight at any time within ~3 sequences (~50 MB of state), so the second read of every
+// association row -- each is incident to two detections -- hits the 126 MB L2 instead of HBM.
 __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict__ h, int ldh, int col,
                                                         const int32_t* __restrict__ n_dets,
                                                         const int32_t* __restrict__ seg_ptr,
                                                         const int32_t* __restrict__ inc, float* __restrict__ agg,
                                                         const int32_t* __restrict__ phys) {
+  __shared__ float4 part[16][16];
   const int nd = *n_dets;
-  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
-  const int wpb = blockDim.x >> 5;
-  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < nd; k += gridDim.x * wpb) {
+  const int q = threadIdx.x >> 4, l16 = threadIdx.x & 15;  // half-warp, float4 within the row
+  for (int k = blockIdx.x; k < nd; k += gridDim.x) {
     const int s0 = seg_ptr[2 * k], s1 = seg_ptr[2 * k + 1], s2 = seg_ptr[2 * k + 2];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = s0 + half;
-    for (; i + 6 < s2; i += 8) {
-      int e0 = inc[i], e1 = inc[i + 2], e2 = inc[i + 4], e3 = inc[i + 6];
+    int i = s0 + q;
+    for (; i + 48 < s2; i += 64) {
+      int e0 = inc[i], e1 = inc[i + 16], e2 = inc[i + 32], e3 = inc[i + 48];
       if (phys) { e0 = phys[e0]; e1 = phys[e1]; e2 = phys[e2]; e3 = phys[e3]; }  // deferred compaction: physical rows
       float4 v0 = ldg4(h + (size_t)e0 * ldh + col + 4 * l16);
       float4 v1 = ldg4(h + (size_t)e1 * ldh + col + 4 * l16);
       float4 v2 = ldg4(h + (size_t)e2 * ldh + col + 4 * l16);
       float4 v3 = ldg4(h + (size_t)e3 * ldh + col + 4 * l16);
-      float g0 = (i < s1) ? -1.f : 1.f, g1 = (i + 2 < s1) ? -1.f : 1.f;
-      float g2 = (i + 4 < s1) ? -1.f : 1.f, g3 = (i + 6 < s1) ? -1.f : 1.f;
+      float g0 = (i < s1) ? -1.f : 1.f, g1 = (i + 16 < s1) ? -1.f : 1.f;
+      float g2 = (i + 32 < s1) ? -1.f : 1.f, g3 = (i + 48 < s1) ? -1.f : 1.f;
       acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
       acc.x = fmaf(g1, v1.x, acc.x); acc.y = fmaf(g1, v1.y, acc.y); acc.z = fmaf(g1, v1.z, acc.z); acc.w = fmaf(g1, v1.w, acc.w);
       acc.x = fmaf(g2, v2.x, acc.x); acc.y = fmaf(g2, v2.y, acc.y); acc.z = fmaf(g2, v2.z, acc.z); acc.w = fmaf(g2, v2.w, acc.w);
       acc.x = fmaf(g3, v3.x, acc.x); acc.y = fmaf(g3, v3.y, acc.y); acc.z = fmaf(g3, v3.z, acc.z); acc.w = fmaf(g3, v3.w, acc.w);
     }
-    for (; i < s2; i += 2) {
+    for (; i < s2; i += 16) {
       const int e = phys ? phys[inc[i]] : inc[i];
       float4 v = ldg4(h + (size_t)e * ldh + col + 4 * l16);
       float g = (i < s1) ? -1.f : 1.f;
       acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y); acc.z = fmaf(g, v.z, acc.z); acc.w = fmaf(g, v.w, acc.w);
     }
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-    if (half == 0) *reinterpret_cast<float4*>(agg + (size_t)k * H + 4 * l16) = acc;
+    part[q][l16] = acc;
+    __syncthreads();
+    if (q == 0) {
+      float4 t = part[0][l16];
+#pragma unroll
+      for (int w = 1; w < 16; ++w) {
+        const float4 u = part[w][l16];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      *reinterpret_cast<float4*>(agg + (size_t)k * H + 4 * l16) = t;
+    }
+    __syncthreads();
   }
 }
 

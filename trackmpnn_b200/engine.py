@@ -120,7 +120,7 @@ class TrackEngine:
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self._tc_scratch = {}
         self._gat_scratch = {}
-        self.profile = None  # list of (start event, end event, n_edges tensor) per edge-kernel launch when enabled
+        self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end) per step
         self._graph = None
         self.ticks = 0
 
@@ -147,8 +147,12 @@ class TrackEngine:
         tc = F_.packed_cells_tc(model) if self.tensor else None
         for grp in range(self.G):
             concat = int(model.factor_grus[grp].msg_type == 'concat')
+            if self.profile is not None:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
             F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, self.agg, self._gat_scratch)
             if self.profile is not None:
+                a1.record()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if self.tensor:
@@ -159,7 +163,7 @@ class TrackEngine:
                        L.ptr(packs[grp][0]), st)
             if self.profile is not None:
                 e1.record()
-                self.profile.append((e0, e1, self.index.n_edges.clone()))
+                self.profile.append((e0, e1, self.index.n_edges.clone(), a0, a1))
             L.call('tmpnn_mp_det_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
                    L.ptr(packs[grp][1]), L.ptr(self.agg), st)
         self.edge_updates += self.index.n_edges
