@@ -125,7 +125,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise TmpnnError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; '
                              f'g.build()"` (nvcc, sm_100a).  trackmpnn_b200 has no CPU or PyTorch fallback path.')
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(os.environ.get('TMPNN_LIB', LIB_PATH))  # TMPNN_LIB: a debug build (profiles/trace_tc.py)
         l.tmpnn_last_error.restype = C.c_char_p
         for name, (args, res) in _PROTOS.items():
             f = getattr(l, name)

@@ -31,6 +31,24 @@
 // tfree[2] (epilogue -> MMA: accumulator stage drained).
 #include "tc_common.cuh"
 
+// Debug build only (-DTMPNN_TC_TRACE, profiles/trace_tc.py): CTA 0 stamps clock64() at the hand-over points of
+// its three roles into g_tc_trace[iteration][16]; compiled out of the shipped library.
+#ifdef TMPNN_TC_TRACE
+__device__ long long* g_tc_trace = nullptr;
+__device__ int g_tc_trace_cap = 0;
+#define TC_TRACE(it_, slot_, cond_)                                                                 \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (cond_) && g_tc_trace && (it_) < g_tc_trace_cap) g_tc_trace[(it_) * 16 + (slot_)] = clock64(); \
+  } while (0)
+extern "C" int tmpnn_debug_set_tc_trace(long long* buf, int cap) {
+  cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf));
+  cudaMemcpyToSymbol(g_tc_trace_cap, &cap, sizeof(cap));
+  return 0;
+}
+#else
+#define TC_TRACE(it_, slot_, cond_) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
@@ -287,8 +305,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         if (dfr) npown = __ldg(phys + nbase + nr0 + min(idx_row, nnleft - 1));
       }
       float amax = 0.f;
+      TC_TRACE(it, 0, threadIdx.x == 32 * EPI_WARPS);
       // x images first: they are free as soon as the previous tile of this stage left the tensor core
       mbar_wait(bar_xfree + 8 * stage, phase ^ 1u, status);
+      TC_TRACE(it, 1, threadIdx.x == 32 * EPI_WARPS);
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         // endpoint rows of the following round (or of round 0 of the next tile): L2 hits, one round ahead
@@ -308,8 +328,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
           *reinterpret_cast<uint2*>(a_stage + A_PART + off) = xl;
         }
       }
+      TC_TRACE(it, 2, threadIdx.x == 32 * EPI_WARPS);
       // h images: released by the epilogue of the previous tile of this stage
       mbar_wait(bar_hfree + 8 * stage, phase ^ 1u, status);
+      TC_TRACE(it, 3, threadIdx.x == 32 * EPI_WARPS);
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const float4 h4 = own[p];
@@ -326,14 +348,18 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
       fence_proxy_async();
       __syncwarp();
+      TC_TRACE(it, 4, threadIdx.x == 32 * EPI_WARPS);
       if (lane == 0) {
         mbar_arrive(bar_full + 8 * stage);
         if (warp - EPI_WARPS == (it & (PROD_WARPS - 1))) {  // this tile's MMA issuer
           mbar_wait(bar_tfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained
+          TC_TRACE(it, 5, true);
           mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows
+          TC_TRACE(it, 6, true);
           tc_fence_after();
           issue_tile_mma(sm_u, tmem_base, stage, 0u, bar_xfree + 8 * stage);
           umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
+          TC_TRACE(it, 7, true);
         }
       }
       __syncwarp();
@@ -384,8 +410,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         coords(tile + 2 * stride, row2, nrem2, lr2);
         srcv2 = ld_src(row2, nrem2, lr2);
       }
+      TC_TRACE(it, 8, threadIdx.x == 0);
       mbar_wait(bar_done + 8 * stage, phase, status);
       tc_fence_after();
+      TC_TRACE(it, 9, threadIdx.x == 0);
       // previous state of this row's 32 columns = hi + lo of the stage's h images; once every epilogue
       // warp holds its part in registers the A stage goes back to the producers (before the gate math)
       f32x2 hp[16];
@@ -405,6 +433,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       // the pair of warps sharing this row quadrant has read both h images of its rows: from here on
       // they are this warp's transpose buffer ([32 rows x 32 floats], 16 B chunks XOR-swizzled by row)
       named_bar_sync(1 + quad, 64);
+      TC_TRACE(it, 10, threadIdx.x == 0);
       const bool valid = nrem_cur > 0 && src_cur >= 0;
       unsigned char* tbuf = a_stage + 2 * A_PART + warp * 4096;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
@@ -465,6 +494,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tfree + 8 * stage);  // accumulator stage drained
+      TC_TRACE(it, 11, threadIdx.x == 0);
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
       {
         float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
@@ -477,6 +507,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // the h images may be refilled
+      TC_TRACE(it, 12, threadIdx.x == 0);
       // head: the two column halves of a row live in warps quad and quad + 4
       if (half == 1) dot_part[r] = dot;
       named_bar_sync(1 + quad, 64);
@@ -486,6 +517,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
       }
       named_bar_sync(1 + quad, 64);
+      TC_TRACE(it, 13, threadIdx.x == 0);
       row = row1; nrem = nrem1; lr = lr1; srcv = srcv1; ks = ks1;
       row1 = row2; nrem1 = nrem2; lr1 = lr2; srcv1 = srcv2;
     }

@@ -52,14 +52,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 // Bounded wait: a protocol bug must never hang the GPU -- after 2 s the kernel flags an error
-// and runs to completion with garbage instead.  Failed polls back off with nanosleep so that a
-// waiting role does not steal issue slots from the roles doing work on the same SM sub-partition.
+// and runs to completion with garbage instead.  mbarrier.try_wait is itself a suspending wait (the
+// thread sleeps in hardware until the phase completes or a time limit expires), so the loop simply
+// re-issues it; TMPNN_TC_SLEEP_NS > 0 adds a nanosleep back-off between polls.
+#ifndef TMPNN_TC_SLEEP_NS
+#define TMPNN_TC_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* status) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spin = 0;
   unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
+    if (TMPNN_TC_SLEEP_NS > 0) __nanosleep(TMPNN_TC_SLEEP_NS);
     if ((++spin & 1023u) == 0) {
       const unsigned long long t = globaltimer_ns();
       if (t0 == 0) t0 = t;
