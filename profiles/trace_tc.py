@@ -37,12 +37,47 @@ def run():
     eng.run(max_ticks=8); torch.cuda.synchronize()
     cap = 2048
     buf = torch.zeros((cap, 16), dtype=torch.int64, device=dev)
-    f = L.lib().tmpnn_debug_set_tc_trace
+    kern = os.environ.get('TC_KERNEL', 'pre3')
+    eng.tensor_kernel = kern
+    f = getattr(L.lib(), 'tmpnn_debug_set_tc3_trace' if kern == 'pre3' else 'tmpnn_debug_set_tc_trace')
     f.argtypes = [C.c_void_p, C.c_int]; f(buf.data_ptr(), cap)
     eng._tick(flip=False); torch.cuda.synchronize()   # one more frame, traced (later launches overwrite earlier ones)
     f(None, 0)
     np.save(os.path.join(ROOT, 'gpurun_out', 'tc_trace.npy'), buf.cpu().numpy())
     print('saved', int((buf[:, 0] != 0).sum()), 'iterations')
+
+
+def show3(path):
+    """Timeline of the re-staged kernel (mp_step_tc3.cu): producer 2 loop top, 3 h images free, 4 h part written
+    (-> arrive full), 0 before / 1 after the wait for the other stage's x images; issuer 5-7; epilogue teams 8-13."""
+    import numpy as np
+    t = np.load(path).astype(np.float64)
+    n = int((t[:, 9] != 0).sum())
+    t = t[:n]
+    lo, hi = n // 4, 3 * n // 4
+    seg = t[lo:hi]
+    print(f'{n} tiles; steady-state cycles per tile {(seg[-1, 9] - seg[0, 9]) / (len(seg) - 1):.0f}')
+    def d(a, b, shift=0):
+        x = seg[:, b] - seg[:, a] if shift == 0 else seg[shift:, b] - seg[:-shift, a]
+        return f'{np.mean(x):7.0f} (p10 {np.percentile(x, 10):6.0f} p90 {np.percentile(x, 90):6.0f})'
+    print('producer: wait h free (gates of tile-2) ', d(2, 3))
+    print('producer: h part + cp.async wait + fence', d(3, 4))
+    print('producer: wait x free (stores of tile-1)', d(0, 1))
+    print('producer: issue x copies -> next top    ', d(1, 2, 1))
+    print('issuer  : wait tmem free                ', d(7, 5, 1))
+    print('issuer  : wait full                     ', d(5, 6))
+    print('issuer  : issue 36 MMA                  ', d(6, 7))
+    print('full arrive -> issuer sees              ', d(4, 6))
+    print('MMA     : issued -> epilogue sees done  ', d(7, 9))
+    print('epilogue: wait done                     ', d(8, 9))
+    print('epilogue: gates (4 chunks)              ', d(9, 11))
+    print('epilogue: stores                        ', d(11, 12))
+    print('epilogue: head                          ', d(12, 13))
+    print('epilogue: team tile -> next team tile   ', d(8, 8, 2))
+    print('gfree -> producer sees (tile+2)         ', d(11, 3, 2))
+    t0 = t[lo, 2]
+    for i in range(lo, lo + 6):
+        print(i, ' '.join(f'{(v - t0):8.0f}' for v in t[i, :14]))
 
 
 def show(path):
@@ -78,4 +113,4 @@ def show(path):
 
 
 if __name__ == '__main__':
-    {'build': build, 'run': run}.get(sys.argv[1], lambda: show(sys.argv[2]))()
+    {'build': build, 'run': run, 'show3': lambda: show3(sys.argv[2])}.get(sys.argv[1], lambda: show(sys.argv[2]))()

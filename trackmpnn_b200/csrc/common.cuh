@@ -9,6 +9,10 @@
 #define TMPNN_SM_COUNT 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of it
 
 int tmpnn_set_error(int code, const char* fmt, ...);
+// mp_step_tc3.cu: tile table + the re-staged tcgen05 edge kernel (endpoints already prepared by k_det_prepare)
+int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
+                          int num_groups, int concat, const void* edge_image, const float* det_img, const float* det_p,
+                          void* tile_table, cudaStream_t st);
 
 #define TMPNN_CUDA_TRY(expr)                                                                   \
   do {                                                                                         \

@@ -625,7 +625,8 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
 
 extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
                                         int group, int num_groups, int concat, const void* edge_image, const float* w_ih,
-                                        const float* b_ih, const float* b_hh, float* det_img, float* det_p, void* stream) {
+                                        const float* b_ih, const float* b_hh, float* det_img, float* det_p, void* tile_table,
+                                        void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_image && ix->tile128_ptr && ix->det_of_row && ix->det_rows, "null argument");
   TMPNN_REQUIRE(w_ih && b_ih && b_hh && det_img && det_p, "null argument");
   TMPNN_REQUIRE(h_in != h_out && det_img != h_in && det_img != h_out, "h_in, h_out and det_img must be distinct buffers");
@@ -636,6 +637,10 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
   k_det_prepare<<<TMPNN_SM_COUNT * 2, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys, w_ih,
                                                            concat ? 128 : 64, b_ih, b_hh, det_img, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
+  if (tile_table) {  // re-staged kernel (mp_step_tc3.cu)
+    TMPNN_REQUIRE(((uintptr_t)tile_table & 15) == 0, "tile_table must be 16-byte aligned");
+    return tmpnn_edge_tc3_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_image, det_img, det_p, tile_table, st);
+  }
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc<true><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,

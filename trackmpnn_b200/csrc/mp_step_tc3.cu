@@ -1,0 +1,356 @@
+// mp_step_tc3.cu -- the edge-row message-passing step on tcgen05, re-staged after the role timeline of
+// mp_step_tc.cu (profiles/r01_tc_trace_gather_v9.txt: 8.6 k cycles per 128-row tile, of which the epilogue is
+// busy 6.2 k, the MMA issue blocks a producer warp 2.8 k, and the MUFU pipe -- the real floor of the gate math,
+// 3.1 k -- idles while all eight epilogue warps store / exchange / read in lock step).
+//
+// Same math (reference models/layers.py:84-116, heads of models/track_mpnn.py:73-75), same endpoint preparation
+// as tmpnn_mp_edge_fwd_tc_pre (k_det_prepare: fp16 hi/lo image + source-side gate contribution P' per detection
+// row), same shared-memory images and TMEM accumulators.  Roles, 25 warps / 800 threads / 80 registers:
+//   warps 0-15   two epilogue TEAMS of 8 warps; team t owns accumulator stage t and A stage t, i.e. every other
+//                tile, so one team's loads / stores / head overlap the other team's MUFU-bound gate math.  The
+//                previous state is read from the h images chunk by chunk (8 registers instead of 32) because the
+//                transpose buffer now lives in the stage's x images, dead since the MMAs retired
+//   warps 16-23  producers: far-endpoint images by cp.async (no registers), own rows loaded one tile ahead,
+//                split to fp16 hi/lo and stored into the swizzled h images
+//   warp 24      MMA issuer: one thread waits for the stage, issues the 36 tcgen05.mma and commits; producers
+//                never block behind the tensor pipe any more
+// mbarriers per stage: full (8 producer warps), done (tcgen05.commit), gfree (8 team warps: gates done ->
+// accumulators drained and h images read), xfree (8 team warps: stores done -> x images / transpose buffer free).
+// Tiles are located through a table {slab's first global row, tile's first slab row, rows left} (k_tile_table).
+#include "tc_common.cuh"
+
+#ifdef TMPNN_TC_TRACE
+__device__ long long* g_tc3_trace = nullptr;
+__device__ int g_tc3_trace_cap = 0;
+#define TC3_TRACE(it_, slot_, cond_)                                                                \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (cond_) && g_tc3_trace && (it_) < g_tc3_trace_cap) g_tc3_trace[(it_) * 16 + (slot_)] = clock64(); \
+  } while (0)
+extern "C" int tmpnn_debug_set_tc3_trace(long long* buf, int cap) {
+  cudaMemcpyToSymbol(g_tc3_trace, &buf, sizeof(buf));
+  cudaMemcpyToSymbol(g_tc3_trace_cap, &cap, sizeof(cap));
+  return 0;
+}
+#else
+#define TC3_TRACE(it_, slot_, cond_) do { } while (0)
+#endif
+
+namespace {
+
+constexpr int EPI3 = 16, PROD3 = 8;
+constexpr int ISSUER3 = EPI3 + PROD3;              // warp 24
+constexpr int TC3_THREADS = 32 * (EPI3 + PROD3 + 1);  // 800 -> 80 registers per thread
+// barriers (8 bytes each, two stages): full, done, gfree, xfree; then the TMEM pointer
+// head partial sums: team 0 in the r | z bias slots of the image (unused here: folded into P'), team 1 at OFF_DOT
+
+__global__ void __launch_bounds__(256)
+k_tile_table(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ tile128_ptr, int cap_rows,
+             int4* __restrict__ tab) {
+  const int s = blockIdx.y;
+  const int t0 = tile128_ptr[s], nt = tile128_ptr[s + 1] - t0, n = n_rows[s];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += gridDim.x * blockDim.x)
+    tab[t0 + j] = make_int4(s * cap_rows, j * TCM, n - j * TCM, 0);
+}
+
+__global__ void __launch_bounds__(TC3_THREADS, 1)
+k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
+              const int32_t* __restrict__ src, const int32_t* __restrict__ dst, const int32_t* __restrict__ n_tiles,
+              const int4* __restrict__ tab, const unsigned char* __restrict__ image, float* __restrict__ logit,
+              float* __restrict__ score, int first_group, int last_group, int32_t* __restrict__ status,
+              const int32_t* __restrict__ phys, const float* __restrict__ det_img, const float* __restrict__ det_p,
+              const int32_t* __restrict__ det_of_row, uint32_t xflags) {
+  extern __shared__ unsigned char smem_dyn[];
+  const int total = *n_tiles;
+  if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
+  unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sm_u = smem_u32(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = sm_u + OFF_BAR, bar_done = bar_full + 16, bar_gfree = bar_full + 32, bar_xfree = bar_full + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 80);
+
+  // resident weight image (generic-proxy stores, made visible to the async proxy below)
+  {
+    const uint4* gsrc = reinterpret_cast<const uint4*>(image);
+    uint4* sdst = reinterpret_cast<uint4*>(sm);
+    for (int i = threadIdx.x; i < IMAGE_BYTES / 16; i += TC3_THREADS) sdst[i] = __ldg(gsrc + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, PROD3);  // one arrive per producer warp
+      mbar_init(bar_done + 8 * s, 1);      // tcgen05.commit
+      mbar_init(bar_gfree + 8 * s, 8);     // one arrive per warp of the stage's team
+      mbar_init(bar_xfree + 8 * s, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int stride = gridDim.x;
+  // tiles past the end repeat the last one (their loads are simply unused)
+  auto ldtab = [&](int tile) { return __ldg(tab + min(tile, total - 1)); };
+
+  if (warp == ISSUER3) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
+        TC3_TRACE(it, 5, true);
+        mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows
+        TC3_TRACE(it, 6, true);
+        tc_fence_after();
+        issue_tile_mma(sm_u, tmem_base, stage, xflags, 0u);
+        umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
+        TC3_TRACE(it, 7, true);
+      }
+    }
+  } else if (warp >= EPI3) {
+    // ================= producers: 8 warps, 16 lanes per row, rows g + 16 p =================
+    const int pt = threadIdx.x - 32 * EPI3;
+    const int g = pt >> 4, l = pt & 15, gl0 = lane & 16;
+    const uint32_t FULL = 0xffffffffu;
+    const bool tr = pt == 0;
+    // all addressing in units of float4 from h_in: (global row) * ldh4 + col4 + l fits 32 bits (checked on the host)
+    const float4* __restrict__ h4p = reinterpret_cast<const float4*>(h_in);
+    const uint32_t ldh4 = (uint32_t)ldh >> 2, cl4 = ((uint32_t)col >> 2) + (uint32_t)l;
+    const bool dfr = phys != nullptr;      // deferred compaction: own rows at GLOBAL physical rows
+    const int idx_row = g + 16 * (l & 7);  // lanes l and l + 8 of a group keep the far endpoint / physical row of tile row g + 16 (l & 7)
+    // detection images have the geometry of h: chunk l of the 256 B image of row R sits at
+    // (R * ldh + col) * 4 + 16 l; chunks 0-7 are the hi halves (K order), 8-15 the lo halves
+    const unsigned char* __restrict__ imgb = reinterpret_cast<const unsigned char*>(det_img) + (size_t)col * 4 + 16 * l;
+    const size_t row_bytes = (size_t)ldh * 4;
+    const uint32_t x_dst0 = sm_u + OFF_A + (uint32_t)(l >> 3) * A_PART + sw128(g, l & 7);  // + 2048 p: row g + 16 p
+    const uint32_t h_off0 = sw128(g, l >> 1) + ((l & 1) << 3);
+    // rows past the end of the slab repeat its last row; everything they produce is masked by the epilogue
+    auto ld_idx = [&](const int4 T) { return __ldg(dst + T.x + T.y + min(idx_row, T.z - 1)); };
+    auto ld_phys = [&](const int4 T) { return dfr ? __ldg(phys + T.x + T.y + min(idx_row, T.z - 1)) : 0; };
+    auto issue_x = [&](int st, uint32_t b, int iv) {
+      const uint32_t s0 = x_dst0 + (uint32_t)st * A_STAGE;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int d = __shfl_sync(FULL, iv, gl0 + p);  // -1 for detection rows inside the tile: any valid row will do
+        const unsigned char* sp = imgb + (size_t)(b + (uint32_t)max(d, 0)) * row_bytes;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2048u * p), "l"(sp) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride), T2 = ldtab(blockIdx.x + 2 * stride);
+    const int i0 = ld_idx(T0), pw0 = ld_phys(T0);
+    int i1 = ld_idx(T1), pw1 = ld_phys(T1);
+    float4 own[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int sp = __shfl_sync(FULL, pw0, gl0 + p);
+      const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T0.x + T0.y + min(g + 16 * p, T0.z - 1));
+      own[p] = __ldg(h4p + orow * ldh4 + cl4);
+    }
+    issue_x(0, (uint32_t)T0.x, i0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+      unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+      const int4 T3 = ldtab(tile + 3 * stride);      // in flight for a whole tile
+      const int i2 = ld_idx(T2), pw2 = ld_phys(T2);  // T2 landed a tile ago; these are consumed a tile from now
+      float amax = 0.f;
+      TC3_TRACE(it, 2, tr);
+      // h images: read (chunk by chunk) by the epilogue of the tile two back until its gates were done
+      mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);
+      TC3_TRACE(it, 3, tr);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const float4 h4 = own[p];
+        // this row's slot of the next tile: HBM latency, one tile ahead (unconditional, clamped address)
+        const int sp = __shfl_sync(FULL, pw1, gl0 + p);
+        const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T1.x + T1.y + min(g + 16 * p, T1.z - 1));
+        own[p] = __ldg(h4p + orow * ldh4 + cl4);
+        uint2 hh, hl;
+        split4(h4, hh, hl, amax);
+        const uint32_t off = h_off0 + 2048u * p;
+        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh;
+        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl;
+      }
+      if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's x images (issued one tile ago) have landed
+      fence_proxy_async();
+      __syncwarp();
+      TC3_TRACE(it, 4, tr);
+      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+      if (tile + stride < total) {
+        // the other stage's x images double as the transpose buffer of the tile before this one
+        TC3_TRACE(it, 0, tr);
+        mbar_wait(bar_xfree + 8 * (stage ^ 1), ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u, status);
+        TC3_TRACE(it, 1, tr);
+        issue_x(stage ^ 1, (uint32_t)T1.x, i1);
+      }
+      T0 = T1; T1 = T2; T2 = T3; i1 = i2; pw1 = pw2;
+    }
+  } else {
+    // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
+    const int team = warp >> 3, w8 = warp & 7;
+    const int quad = w8 & 3, half = w8 >> 2;  // quad == warp % 4: the TMEM lane quadrant this warp may read
+    const int r = quad * 32 + lane;           // row of the tile == TMEM lane
+    const int c0 = 32 * half;                 // this warp's columns of every gate: [c0, c0 + 32)
+    const int stage = team;
+    const bool tr = threadIdx.x == 0 || threadIdx.x == 256;
+    unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+    const float* bias = reinterpret_cast<const float*>(sm + OFF_BIAS);
+    const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
+    const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
+    float* dot_part = reinterpret_cast<float*>(sm + (team ? OFF_DOT : OFF_BIAS));
+    const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
+    const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+    unsigned char* tbuf = a_stage + w8 * 4096;  // [32 rows x 32 floats], 16 B chunks XOR-swizzled by row, in the x images
+    const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
+    const int bar_id = 1 + team * 4 + quad;
+    auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
+    const int first = blockIdx.x + team * stride, step2 = 2 * stride;
+    int4 T0 = ldtab(first), T1 = ldtab(first + step2);
+    int srcv = ld_src(T0);
+    uint32_t n = 0;  // tiles this team has done
+    for (int tile = first; tile < total; tile += step2, ++n) {
+      const uint32_t phase = n & 1u;
+      const int it = 2 * (int)n + team;
+      const size_t row_cur = (size_t)T0.x + T0.y + r;
+      const bool valid = T0.z - r > 0 && srcv >= 0;
+      const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
+      const int4 T2 = ldtab(tile + 2 * step2);
+      const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the team's next tile
+      TC3_TRACE(it, 8, tr);
+      mbar_wait(bar_done + 8 * stage, phase, status);
+      tc_fence_after();
+      TC3_TRACE(it, 9, tr);
+      const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      f32x2 dot2 = 0ull;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t ar[8], az[8], an[8], ahn[8];
+        tmem_ld8u(t0 + ch * 8, ar);
+        tmem_ld8u(t0 + 64 + ch * 8, az);
+        tmem_ld8u(t0 + 128 + ch * 8, an);
+        tmem_ld8u(t0 + 192 + ch * 8, ahn);
+        const int j0 = c0 + ch * 8;
+        // previous state of these 8 columns = hi + lo of the stage's h images (still intact: the transpose buffer
+        // lives in the x images)
+        f32x2 hp[4];
+        {
+          const uint32_t off = sw128(r, 4 * half + ch);
+          const uint4 vh = *reinterpret_cast<const uint4*>(a_stage + 2 * A_PART + off);
+          const uint4 vl = *reinterpret_cast<const uint4*>(a_stage + 3 * A_PART + off);
+          const __half2* ph = reinterpret_cast<const __half2*>(&vh);
+          const __half2* pl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
+            hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          // additive terms of the three input gates: the source's P' row, which already holds
+          // -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
+          const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
+          const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
+          const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+          const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
+          const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
+          f32x2 o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 4 * v + 2 * e;  // columns j0 + i, j0 + i + 1
+            // r, z = 1 / (1 + 2^(-log2e (acc + P + b)))   (2^x -> inf gives exactly 0, no clamp needed)
+            const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(ar[i], ar[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
+            const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(az[i], az[i + 1]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
+            // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + P_n + b_in + r (h_n + b_hn)
+            const f32x2 u = fma2(rg, add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), add2(pk2u(an[i], an[i + 1]), e ? bi.y : bi.x));
+            const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
+            const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
+            o[e] = ov;
+            dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+          }
+          *reinterpret_cast<ulonglong2*>(tbuf + lane * 128 + (((2 * ch + v) ^ (lane & 7)) << 4)) = make_ulonglong2(o[0], o[1]);
+        }
+      }
+      float dot;
+      {
+        float d0, d1;
+        up2(dot2, d0, d1);
+        dot = d0 + d1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained, h images read
+      TC3_TRACE(it, 11, tr);
+      // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
+      {
+        float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = 4 * k + (lane >> 3), cc = lane & 7;
+          const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_xfree + 8 * stage);  // the x images may be refilled
+      TC3_TRACE(it, 12, tr);
+      // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
+      if (half == 1) dot_part[r] = dot;
+      named_bar_sync(bar_id, 64);
+      if (half == 0 && valid) {
+        const float lg = dot + dot_part[r] + (first_group ? headb : logit[row_cur]);
+        logit[row_cur] = lg;
+        if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
+      }
+      named_bar_sync(bar_id, 64);
+      TC3_TRACE(it, 13, tr);
+      T0 = T1; T1 = T2; srcv = srcv1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+int tmpnn_init_tc3() {
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return TMPNN_OK;
+}
+
+extern "C" size_t tmpnn_tc_tile_table_bytes(int num_seqs, int cap_rows) {
+  return (size_t)num_seqs * (size_t)tmpnn_div_up(cap_rows, TCM) * sizeof(int4) + sizeof(int4);
+}
+
+int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
+                          int num_groups, int concat, const void* edge_image, const float* det_img, const float* det_p,
+                          void* tile_table, cudaStream_t st) {
+  if (group == 0) {
+    dim3 grid(max(1, min(tmpnn_div_up(tmpnn_div_up(g->cap_rows, TCM), 256), 8)), g->num_seqs);
+    k_tile_table<<<grid, 256, 0, st>>>(g->n_rows, ix->tile128_ptr, g->cap_rows, (int4*)tile_table);
+    TMPNN_LAUNCH_CHECK();
+  }
+  // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
+  k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
+      h_in, h_out, ldh, group * H, g->src, g->dst, ix->tile128_ptr + g->num_seqs, (const int4*)tile_table,
+      (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys, det_img,
+      det_p, ix->det_of_row, concat ? 0u : (1u << 13));
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}

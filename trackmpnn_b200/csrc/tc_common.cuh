@@ -217,7 +217,7 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t sm_u, uint32_t tmem_base
       umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, acc);
       acc = 1;
     }
-  umma_commit(bar_xfree);  // the x images are reusable once these MMAs retire
+  if (bar_xfree) umma_commit(bar_xfree);  // the x images are reusable once these MMAs retire (0: released by the epilogue)
   // h part: columns [0,128) += r | z, columns [192,256) = h_n
   const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
   const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
