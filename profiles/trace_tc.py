@@ -70,11 +70,10 @@ def show3(path):
     print('full arrive -> issuer sees              ', d(4, 6))
     print('MMA     : issued -> epilogue sees done  ', d(7, 9))
     print('epilogue: wait done                     ', d(8, 9))
-    print('epilogue: gates (4 chunks)              ', d(9, 11))
-    print('epilogue: stores                        ', d(11, 12))
+    print('epilogue: gates + stores (4 chunks)     ', d(9, 12))
     print('epilogue: head                          ', d(12, 13))
     print('epilogue: team tile -> next team tile   ', d(8, 8, 2))
-    print('gfree -> producer sees (tile+2)         ', d(11, 3, 2))
+    print('hfree -> producer sees (tile+2)         ', d(12, 3, 2))
     t0 = t[lo, 2]
     for i in range(lo, lo + 6):
         print(i, ' '.join(f'{(v - t0):8.0f}' for v in t[i, :14]))

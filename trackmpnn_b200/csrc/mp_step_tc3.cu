@@ -65,7 +65,8 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = sm_u + OFF_BAR, bar_done = bar_full + 16, bar_gfree = bar_full + 32, bar_xfree = bar_full + 48;
+  const uint32_t bar_hfull = sm_u + OFF_BAR, bar_xfull = bar_hfull + 16, bar_done = bar_hfull + 32, bar_gfree = bar_hfull + 48,
+                 bar_xfree = bar_hfull + 64;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 80);
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
@@ -76,7 +77,8 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, PROD3);  // one arrive per producer warp
+      mbar_init(bar_hfull + 8 * s, PROD3);  // one arrive per producer warp: own rows written
+      mbar_init(bar_xfull + 8 * s, 32 * PROD3);  // one arrive per producer THREAD: its far-endpoint copies landed
       mbar_init(bar_done + 8 * s, 1);      // tcgen05.commit
       mbar_init(bar_gfree + 8 * s, 8);     // one arrive per warp of the stage's team
       mbar_init(bar_xfree + 8 * s, 8);
@@ -93,6 +95,12 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int stride = gridDim.x;
+  // the far-endpoint MMAs only ever accumulate: the i_n columns of both accumulator stages start at zero (each
+  // epilogue warp owns the 32 lanes x 32 columns it will later drain and re-zero)
+  if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 128 + 32 * ((warp & 7) >> 2)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   // tiles past the end repeat the last one (their loads are simply unused)
   auto ldtab = [&](int tile) { return __ldg(tab + min(tile, total - 1)); };
 
@@ -105,10 +113,17 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         const uint32_t phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
         TC3_TRACE(it, 5, true);
-        mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows
+        mbar_wait(bar_hfull + 8 * stage, phase, status);       // own rows written
         TC3_TRACE(it, 6, true);
         tc_fence_after();
-        issue_tile_mma(sm_u, tmem_base, stage, xflags, 0u);
+        issue_tile_mma_h_first(sm_u, tmem_base, stage);
+        // the far-endpoint images arrive last: they share the stage's x images with the transpose buffer of the
+        // tile two back, which the epilogue holds until its stores are out
+        mbar_wait(bar_xfull + 8 * stage, phase, status);
+        TC3_TRACE(it, 10, true);
+        fence_proxy_async();  // the copies were generic-proxy writes of other threads, observed through the barrier
+        tc_fence_after();
+        issue_tile_mma_x_second(sm_u, tmem_base, stage, xflags);
         umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
         TC3_TRACE(it, 7, true);
       }
@@ -144,8 +159,8 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride), T2 = ldtab(blockIdx.x + 2 * stride);
-    const int i0 = ld_idx(T0), pw0 = ld_phys(T0);
-    int i1 = ld_idx(T1), pw1 = ld_phys(T1);
+    int i0 = ld_idx(T0), i1 = ld_idx(T1), pw1 = ld_phys(T1);
+    const int pw0 = ld_phys(T0);
     float4 own[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -153,7 +168,6 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T0.x + T0.y + min(g + 16 * p, T0.z - 1));
       own[p] = __ldg(h4p + orow * ldh4 + cl4);
     }
-    issue_x(0, (uint32_t)T0.x, i0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
       const int stage = it & 1;
@@ -180,19 +194,19 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl;
       }
       if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
-      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's x images (issued one tile ago) have landed
       fence_proxy_async();
       __syncwarp();
       TC3_TRACE(it, 4, tr);
-      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-      if (tile + stride < total) {
-        // the other stage's x images double as the transpose buffer of the tile before this one
-        TC3_TRACE(it, 0, tr);
-        mbar_wait(bar_xfree + 8 * (stage ^ 1), ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u, status);
-        TC3_TRACE(it, 1, tr);
-        issue_x(stage ^ 1, (uint32_t)T1.x, i1);
-      }
-      T0 = T1; T1 = T2; T2 = T3; i1 = i2; pw1 = pw2;
+      if (lane == 0) mbar_arrive(bar_hfull + 8 * stage);
+      // far-endpoint images: this stage's x images double as the transpose buffer of the tile two back
+      TC3_TRACE(it, 0, tr);
+      mbar_wait(bar_xfree + 8 * stage, phase ^ 1u, status);
+      TC3_TRACE(it, 1, tr);
+      issue_x(stage, (uint32_t)T0.x, i0);
+      // completion is signalled by the copy engine itself (one arrival per thread once its copies have landed), so
+      // the producers go straight on to the next tile's own rows; the issuer fences the proxies after its wait
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_xfull + 8 * stage) : "memory");
+      T0 = T1; T1 = T2; T2 = T3; i0 = i1; i1 = i2; pw1 = pw2;
     }
   } else {
     // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
@@ -231,6 +245,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       TC3_TRACE(it, 9, tr);
       const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
       f32x2 dot2 = 0ull;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -288,22 +303,21 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         up2(dot2, d0, d1);
         dot = d0 + d1;
       }
+      // accumulator stage drained: re-zero this warp's i_n columns for the accumulate-only far-endpoint MMAs
+      tmem_zero32(t0 + 128);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained, h images read
       TC3_TRACE(it, 11, tr);
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
-      {
-        float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int rr = 4 * k + (lane >> 3), cc = lane & 7;
-          const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const int rr = 4 * k + (lane >> 3), cc = lane & 7;
+        const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xfree + 8 * stage);  // the x images may be refilled
+      if (lane == 0) mbar_arrive(bar_xfree + 8 * stage);  // transpose buffer (the x images) read back: may be refilled
       TC3_TRACE(it, 12, tr);
       // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
       if (half == 1) dot_part[r] = dot;

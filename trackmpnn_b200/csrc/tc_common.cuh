@@ -201,6 +201,45 @@ __device__ __forceinline__ void seek_seq(const int32_t* __restrict__ tile_ptr, i
   while (seq + 1 < num_seqs && __ldg(tile_ptr + seq + 1) <= tile) ++seq;
 }
 
+// ---- the two halves of the MMA issue, h part FIRST (mp_step_tc3.cu) -----------------------------------
+// own-row part: columns [0,128) = r | z and [192,256) = h_n are (re)initialised here
+__device__ __forceinline__ void issue_tile_mma_h_first(uint32_t sm_u, uint32_t tmem_base, int stage) {
+  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
+  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
+  const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), acc);
+      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc);
+      acc = 1;
+    }
+}
+// far-endpoint part: accumulates into r | z | i_n; the i_n columns [128,192) were zeroed by the epilogue
+// (tcgen05.st) when it drained the stage, so this is 12 instructions on the critical path instead of 24
+__device__ __forceinline__ void issue_tile_mma_x_second(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags) {
+  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
+  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
+  const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, 1);
+}
+// 32 zero columns for this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- MMA issue for one 128-row tile (one thread) ------------------------------------------------
 __device__ __forceinline__ void issue_tile_mma(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags,
                                                uint32_t bar_xfree) {
