@@ -84,8 +84,7 @@ _PROTOS = {
     'tmpnn_gru_tc_pack_bytes': ([], C.c_size_t),
     'tmpnn_pack_gru_tc': ([_VP] * 6 + [_I, _VP, _VP], _I),
     'tmpnn_tc_tile_table_bytes': ([_I, _I], C.c_size_t),
-    'tmpnn_mp_edge_fwd_tc_pre': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP,
-                                  _VP, _VP, _VP], _I),
+    'tmpnn_mp_edge_fwd_tc_pre': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_edge_fwd_tc': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_mp_step_fwd_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 16, _I),

@@ -77,6 +77,15 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
   }
   float* hw = reinterpret_cast<float*>(img + OFF_HEADW);
   for (int i = tid; i < H; i += nth) hw[i] = head_w[i];
+  // k_det_prepare's operands: the source-side half of W_ih transposed ([c][n]: lanes read consecutive n) and
+  // b_ih (+ b_hh for r, z)
+  float* wt = reinterpret_cast<float*>(img + OFF_WT);
+  for (int i = tid; i < 64 * 192; i += nth) {
+    const int c = i / 192, n = i % 192;
+    wt[i] = w_ih[n * ldw + c];
+  }
+  float* bs = reinterpret_cast<float*>(img + OFF_BS);
+  for (int n = tid; n < 192; n += nth) bs[n] = b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f);
   if (tid == 0) {
     float* hb = reinterpret_cast<float*>(img + OFF_HEADB);
     hb[0] = head_b[0]; hb[1] = hb[2] = hb[3] = 0.f;
@@ -539,20 +548,20 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
 constexpr int PREP_SMEM = (64 * 192 + 8 * 64 + 192) * 4;
 __global__ void __launch_bounds__(256)
 k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* __restrict__ n_dets,
-              const int32_t* __restrict__ det_rows, const int32_t* __restrict__ phys, const float* __restrict__ w_ih, int ldw,
-              const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ det_img,
-              float* __restrict__ det_p, int32_t* __restrict__ status) {
+              const int32_t* __restrict__ det_rows, const int32_t* __restrict__ phys, const unsigned char* __restrict__ image,
+              float* __restrict__ det_img, float* __restrict__ det_p, int32_t* __restrict__ status) {
   extern __shared__ float prep_sm[];
   float* wt = prep_sm;             // [64][192]: W_ih^T (source half)
   float* hr = prep_sm + 64 * 192;  // [8][64]
   float* bs = hr + 8 * 64;         // [192]
   const int nd = *n_dets;
   if ((int)blockIdx.x * 8 >= nd) return;
-  for (int i = threadIdx.x; i < 192 * 64; i += blockDim.x) {
-    const int n = i % 192, c = i / 192;
-    wt[c * 192 + n] = w_ih[n * ldw + c];
+  {
+    const float4* gw = reinterpret_cast<const float4*>(image + OFF_WT);
+    for (int i = threadIdx.x; i < 64 * 192 / 4; i += blockDim.x) reinterpret_cast<float4*>(wt)[i] = __ldg(gw + i);
+    const float* gb = reinterpret_cast<const float*>(image + OFF_BS);
+    for (int n = threadIdx.x; n < 192; n += blockDim.x) bs[n] = gb[n];
   }
-  for (int n = threadIdx.x; n < 192; n += blockDim.x) bs[n] = b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* hw = hr + w * 64;
@@ -596,7 +605,7 @@ int tmpnn_init_tc() {
   return TMPNN_OK;
 }
 
-extern "C" size_t tmpnn_gru_tc_pack_bytes(void) { return (size_t)IMAGE_BYTES; }
+extern "C" size_t tmpnn_gru_tc_pack_bytes(void) { return (size_t)IMAGE_TOTAL_BYTES; }
 
 extern "C" int tmpnn_pack_gru_tc(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                                  const float* head_w, const float* head_b, int concat, void* packed, void* stream) {
@@ -624,18 +633,17 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
 }
 
 extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
-                                        int group, int num_groups, int concat, const void* edge_image, const float* w_ih,
-                                        const float* b_ih, const float* b_hh, float* det_img, float* det_p, void* tile_table,
-                                        void* stream) {
+                                        int group, int num_groups, int concat, const void* edge_image, float* det_img,
+                                        float* det_p, void* tile_table, void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_image && ix->tile128_ptr && ix->det_of_row && ix->det_rows, "null argument");
-  TMPNN_REQUIRE(w_ih && b_ih && b_hh && det_img && det_p, "null argument");
+  TMPNN_REQUIRE(det_img && det_p, "null argument");
   TMPNN_REQUIRE(h_in != h_out && det_img != h_in && det_img != h_out, "h_in, h_out and det_img must be distinct buffers");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   int rc = tmpnn_init();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  k_det_prepare<<<TMPNN_SM_COUNT * 2, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys, w_ih,
-                                                           concat ? 128 : 64, b_ih, b_hh, det_img, det_p, g->status);
+  k_det_prepare<<<TMPNN_SM_COUNT, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys,
+                                                       (const unsigned char*)edge_image, det_img, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
   if (tile_table) {  // re-staged kernel (mp_step_tc3.cu)
     TMPNN_REQUIRE(((uintptr_t)tile_table & 15) == 0, "tile_table must be 16-byte aligned");

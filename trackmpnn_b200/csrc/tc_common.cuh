@@ -15,7 +15,11 @@ constexpr int OFF_BX_HI = 0, OFF_BX_LO = B_BYTES, OFF_BH_HI = 2 * B_BYTES, OFF_B
 constexpr int OFF_BIAS = 4 * B_BYTES;            // 4 x 64 floats: -log2e (b_ir+b_hr), -log2e (b_iz+b_hz), b_in, b_hn
 constexpr int OFF_HEADW = OFF_BIAS + 1024;       // 64 floats
 constexpr int OFF_HEADB = OFF_HEADW + 256;       // 1 float (+ pad)
-constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // what tmpnn_pack_gru_tc writes
+constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // the part of the packed image the step kernels keep in shared memory
+// behind it, for k_det_prepare: the source-side W_ih^T as fp32 [64][192] and the folded bias [192]
+constexpr int OFF_WT = IMAGE_BYTES;
+constexpr int OFF_BS = OFF_WT + 64 * 192 * 4;
+constexpr int IMAGE_TOTAL_BYTES = OFF_BS + 192 * 4;
 constexpr int OFF_BAR = IMAGE_BYTES;             // 10 mbarriers + tmem pointer, inside the alignment gap
 constexpr int OFF_DOT = OFF_BAR + 96;            // 128 floats: head partial sums of the upper column half
 constexpr int OFF_A = 98 * 1024;                 // first A stage (1024-aligned)

@@ -157,7 +157,6 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
     dp = scratch.get('det_p')
     if dp is None or dp.shape[0] < index.cap_dets:
         dp = scratch['det_p'] = torch.empty((index.cap_dets, 3 * H), dtype=torch.float32, device=h_in.device)
-    cell = gru.edge_gru
     tab = None
     if kernel == 'pre3':
         nb = int(L.lib().tmpnn_tc_tile_table_bytes(graph.num_seqs, graph.cap_rows))
@@ -165,8 +164,7 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
         if tab is None or tab.numel() * 4 < nb:
             tab = scratch['tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
     L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
-           L.ptr(cell.weight_ih.detach()), L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(img),
-           L.ptr(dp), L.ptr(tab), st)
+           L.ptr(img), L.ptr(dp), L.ptr(tab), st)
 
 
 def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
