@@ -10,7 +10,7 @@ from . import trackmpnn_oracle as O
 
 
 def run_infer(params, X, y, features='2d', ncategories=3, msg_type='diff', cur_win_size=5, ret_win_size=0,
-              use_hungarian=False, tp_classifier=True, max_frames=None, record_margin=False):
+              use_hungarian=False, tp_classifier=True, max_frames=None, record_margin=False, keep_state=False):
     X = np.asarray(X, np.float32); y = np.asarray(y, np.float32)
     if X.ndim == 2:
         X = X[None]; y = y[None]
@@ -57,4 +57,6 @@ def run_infer(params, X, y, features='2d', ncategories=3, msg_type='diff', cur_w
         t_upto = t_end if t_cur == t_end - 1 else t_cur - cur_win_size + 2
         g, y_out, h, scores, _ = O.decode_tracks(g, h, scores, y_out, t_upto, ret_win_size, use_hungarian=use_hungarian)
         stats['frames'] += 1
+    if keep_state:  # the window graph, states and scores the loop stopped with (tests compare them with the engine's)
+        stats['state'] = dict(g=g, h=h, scores=scores)
     return y_out, stats

@@ -146,3 +146,38 @@ def test_structured_index_equals_general_index(ret):
         np.testing.assert_array_equal(sa, sb)
         np.testing.assert_array_equal(a.inc[:sa[-1]].cpu().numpy(), b.inc[:sb[-1]].cpu().numpy())
         assert sa[-1] == 2 * int(a.n_edges.item())
+
+
+@pytest.mark.parametrize('kernel', ['fma', 'gather', 'pre', 'pre3'])
+def test_engine_state_at_workload_size(kernel):
+    """BDD-shaped sequences at the bench workload's size (~80 detections / frame, ~60 k association rows per
+    window, hundreds of 128-row tiles per launch, so every pipeline stage / barrier phase of the tensor-core
+    kernels wraps many times): after 7 tracked frames the engine's window graphs equal the oracle's bit for bit and the
+    scores / hidden states (read through the deferred-compaction maps) agree within 1e-4."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev, dataset='bdd', scale=1.0, edge_bias=None)   # stock init: BASELINE configs
+    params = _params(model)
+    seqs = []
+    for sd in (11, 12, 13):
+        X, y = synth.make_sequence(sd, 12, 80, 'bdd')
+        seqs.append((X[0], y[0]))
+    frames = 7
+    ticks = 2 + frames   # engine ticks are absolute timesteps; the first two frames are consumed by the initialisation
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=kernel != 'fma',
+                      tensor_kernel=kernel if kernel != 'fma' else 'auto')
+    eng.run(max_ticks=ticks)
+    torch.cuda.synchronize()
+    eng.ga.check_status()
+    n_rows = eng.ga.n_rows.cpu().numpy()
+    hb = eng.h_alt if (ticks & 1) else eng.h_cur   # the buffer the last step wrote
+    for s, (X, y) in enumerate(seqs):
+        _, st = run_infer(params, X, y, ncategories=synth.num_categories('bdd'), cur_win_size=5, max_frames=frames,
+                          keep_state=True)
+        g, h, sc = st['state']['g'], st['state']['h'], st['state']['scores']
+        assert g.n > 20000 and int(n_rows[s]) == g.n
+        rows = slice(s * eng.cap_rows, s * eng.cap_rows + g.n)
+        for name in ('ts', 'det', 'ass', 'src', 'dst'):
+            np.testing.assert_array_equal(getattr(eng.ga, name)[rows].cpu().numpy(), getattr(g, name), err_msg=name)
+        np.testing.assert_allclose(eng.ga.score[rows].cpu().numpy(), sc[:, 1], atol=1e-4, rtol=0)
+        np.testing.assert_allclose(hb[eng.ga.phys[rows].long()].cpu().numpy(), h, atol=1e-4, rtol=0)

@@ -642,7 +642,7 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
   int rc = tmpnn_init();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  k_det_prepare<<<TMPNN_SM_COUNT, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys,
+  k_det_prepare<<<TMPNN_SM_COUNT * 4, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys,
                                                        (const unsigned char*)edge_image, det_img, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
   if (tile_table) {  // re-staged kernel (mp_step_tc3.cu)
