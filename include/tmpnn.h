@@ -156,7 +156,8 @@ int tmpnn_index_build(const tmpnn_graph *g, const tmpnn_index *ix, const int32_t
  * tmpnn_graph_decode (the TrackEngine loop; never tmpnn_graph_prune_mask): every edge block is then a
  * dense [sources x detections-of-the-next-frame] matrix and the incidence lists follow from the block
  * boundaries -- no atomics, no sort, coalesced writes only (csrc/graph_index.cu).  A graph that breaks
- * the structure raises TMPNN_FLAG_UNSTRUCTURED.  scratch2: tmpnn_index_structured_scratch_bytes(). */
+ * the structure raises TMPNN_FLAG_UNSTRUCTURED.  scratch2: tmpnn_index_structured_scratch_bytes(), zero-filled
+ * before its first use (the per-slab boundary counters live there and are left at zero by every call). */
 size_t tmpnn_index_structured_scratch_bytes(int num_seqs, int cap_dets);
 int tmpnn_index_build_structured(const tmpnn_graph *g, const tmpnn_index *ix, const int32_t *active, void *scratch2,
                                  void *stream);

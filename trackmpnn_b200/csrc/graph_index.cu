@@ -225,45 +225,51 @@ struct SlabSegs {            // per slab, in global scratch
   int32_t eord[MAXSEG];      // ordinal among the edge segments, -1 for detection segments
 };
 
-__global__ void __launch_bounds__(1024) k_block_segments(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
-                                                         const int32_t* __restrict__ ts, int cap_rows,
-                                                         SlabSegs* __restrict__ segs, int32_t* __restrict__ status) {
-  __shared__ int32_t bnd[MAXSEG + 2];
-  __shared__ int nb;
-  const int s = blockIdx.x;
+// Segment boundaries: a boundary sits in front of row i when i is the first row or the timestamp changes (edge rows all
+// carry -1).  Found by a grid over the rows (a window of W = 20 frames x 200 detections has millions of rows per
+// slab; one CTA per slab took 22 % of a frame there), collected per slab, then sorted by one thread (<= 128 of them).
+constexpr int BND_STRIDE = MAXSEG + 4;  // [0] = count, [1 ..] = positions
+__global__ void __launch_bounds__(256) k_segment_bounds(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                        const int32_t* __restrict__ ts, int cap_rows, int32_t* __restrict__ bnd) {
+  const int s = blockIdx.y;
   const int n = (active && !active[s]) ? 0 : n_rows[s];
   const int32_t* t = ts + (size_t)s * cap_rows;
-  if (threadIdx.x == 0) nb = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    // a boundary in front of row i: first row, or the timestamp changes (edge rows all carry -1)
+  int32_t* o = bnd + (size_t)s * BND_STRIDE;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (i == 0 || t[i] != t[i - 1]) {
-      const int k = atomicAdd(&nb, 1);
-      if (k < MAXSEG + 1) bnd[k] = i;
+      const int k = atomicAdd(&o[0], 1);
+      if (k < MAXSEG + 1) o[1 + k] = i;
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    SlabSegs& o = segs[s];
-    int m = nb;
-    if (m > MAXSEG) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
-    for (int a = 1; a < m; ++a) {  // insertion sort of <= 128 positions
-      const int v = bnd[a];
-      int b = a - 1;
-      while (b >= 0 && bnd[b] > v) { bnd[b + 1] = bnd[b]; --b; }
-      bnd[b + 1] = v;
-    }
-    int ne = 0;
-    for (int q = 0; q < m; ++q) {
-      o.start[q] = bnd[q];
-      const bool edge = t[bnd[q]] < 0;
-      o.eord[q] = edge ? ne : -1;
-      if (edge) ++ne;
-    }
-    if (ne > MAXE) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
-    o.nseg = m;
-    o.start[m] = n;
+}
+__global__ void __launch_bounds__(32) k_block_segments(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                       const int32_t* __restrict__ ts, int cap_rows, int32_t* __restrict__ bnd_all,
+                                                       SlabSegs* __restrict__ segs, int32_t* __restrict__ status) {
+  const int s = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const int n = (active && !active[s]) ? 0 : n_rows[s];
+  const int32_t* t = ts + (size_t)s * cap_rows;
+  int32_t* bnd = bnd_all + (size_t)s * BND_STRIDE + 1;
+  SlabSegs& o = segs[s];
+  int m = bnd[-1];
+  bnd[-1] = 0;  // ready for the next build
+  if (m > MAXSEG) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
+  for (int a = 1; a < m; ++a) {  // insertion sort of <= 128 positions
+    const int v = bnd[a];
+    int b = a - 1;
+    while (b >= 0 && bnd[b] > v) { bnd[b + 1] = bnd[b]; --b; }
+    bnd[b + 1] = v;
   }
+  int ne = 0;
+  for (int q = 0; q < m; ++q) {
+    o.start[q] = bnd[q];
+    const bool edge = t[bnd[q]] < 0;
+    o.eord[q] = edge ? ne : -1;
+    if (edge) ++ne;
+  }
+  if (ne > MAXE) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
+  o.nseg = m;
+  o.start[m] = n;
 }
 
 // counts: cnt[2k] = past edges, futlen[k][eord] = run length of detection k in edge segment eord
@@ -380,7 +386,8 @@ extern "C" int tmpnn_index_build(const tmpnn_graph* g, const tmpnn_index* ix, co
 }
 
 extern "C" size_t tmpnn_index_structured_scratch_bytes(int num_seqs, int cap_dets) {
-  return (size_t)num_seqs * sizeof(SlabSegs) + (size_t)cap_dets * MAXE * sizeof(int32_t) + 64;
+  return (size_t)num_seqs * sizeof(SlabSegs) + (size_t)cap_dets * MAXE * sizeof(int32_t) +
+         (size_t)num_seqs * BND_STRIDE * sizeof(int32_t) + 64;
 }
 
 extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_index* ix, const int32_t* active,
@@ -395,6 +402,8 @@ extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_in
   int32_t* sums = cnt + (2 * (size_t)ix->cap_dets + 4);
   SlabSegs* segs = (SlabSegs*)scratch2;
   int32_t* futlen = (int32_t*)((unsigned char*)scratch2 + (size_t)S * sizeof(SlabSegs));
+  int32_t* bnd = futlen + (size_t)ix->cap_dets * MAXE;  // per-slab boundary lists; the counts start at zero and are
+                                                        // re-zeroed by k_block_segments (SlabIndex allocates zeros)
 
   dim3 grid_rows(nblk, S);
   k_count_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk);
@@ -405,7 +414,10 @@ extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_in
   k_write_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk, ix->n_dets, ix->det_rows,
                                           ix->det_of_row, cnt);
   TMPNN_LAUNCH_CHECK();
-  k_block_segments<<<S, 1024, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, segs, g->status);
+  dim3 grid_b(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 16), 256)), S);
+  k_segment_bounds<<<grid_b, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, bnd);
+  TMPNN_LAUNCH_CHECK();
+  k_block_segments<<<S, 32, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, bnd, segs, g->status);
   TMPNN_LAUNCH_CHECK();
   TMPNN_CUDA_TRY(cudaMemsetAsync(futlen, 0, (size_t)ix->cap_dets * MAXE * sizeof(int32_t), st));
   dim3 grid_d(4, S);

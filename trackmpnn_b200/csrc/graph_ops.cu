@@ -145,10 +145,53 @@ __global__ void __launch_bounds__(256) k_associate(const int32_t* __restrict__ n
 // desc[s*DESC + ..]: 0 n_old, 1 A (or N0), 2 Nt (or N1), 3 offset of the new frame's ids in frame_dets,
 //   4 first slot in new_det_rows, 5 kind (0 none, 1 append, 2 init), 6 offset of t0's ids, 7 t (or t1), 8 t0
 constexpr int DESC = 12;
+// Inference-mode active set (detection, unassociated, p >= 0.5) over a grid: per-block counts, scanned by the plan
+// kernel, then written in row order.  (A 20-frame x 200-detection window has millions of rows per slab; the plan
+// kernel's own one-CTA scan took 14 % of a frame there.  Training graphs are small and keep the in-CTA scan.)
+__device__ __forceinline__ int active_flag(const tmpnn_graph& g, size_t row) {
+  return g.ts[row] >= 0 && g.ass[row] == -1 && g.score[row] >= 0.5f;
+}
+__global__ void __launch_bounds__(256) k_active_count(tmpnn_graph g, int nblk, int32_t* __restrict__ blk_cnt) {
+  __shared__ int sm[33];
+  const int s = blockIdx.y, b = blockIdx.x, n = g.n_rows[s];
+  if (b * ROWS_PER_BLOCK >= n) { if (threadIdx.x == 0) blk_cnt[s * nblk + b] = 0; return; }
+  const size_t base = (size_t)s * g.cap_rows;
+  const int r0 = b * ROWS_PER_BLOCK + threadIdx.x * 4;
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (r0 + q < n) c += active_flag(g, base + r0 + q);
+  int total;
+  block_exclusive_scan(c, sm, &total);
+  if (threadIdx.x == 0) blk_cnt[s * nblk + b] = total;
+}
+__global__ void __launch_bounds__(256) k_active_write(tmpnn_graph g, int nblk, const int32_t* __restrict__ blk_off,
+                                                      const int32_t* __restrict__ desc, int desc_stride,
+                                                      int32_t* __restrict__ act) {
+  __shared__ int sm[33];
+  const int s = blockIdx.y, b = blockIdx.x;
+  if (desc[desc_stride * s + 5] != 1) return;   // this sequence appends nothing from an active list
+  const int n = desc[desc_stride * s + 0];       // rows before the append
+  if (b * ROWS_PER_BLOCK >= n) return;
+  const size_t base = (size_t)s * g.cap_rows;
+  const int r0 = b * ROWS_PER_BLOCK + threadIdx.x * 4;
+  int f[4], c = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f[q] = (r0 + q < n) ? active_flag(g, base + r0 + q) : 0;
+    c += f[q];
+  }
+  int total;
+  int pos = blk_off[s * nblk + b] + block_exclusive_scan(c, sm, &total);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (f[q]) act[base + pos++] = r0 + q;
+}
 __global__ void __launch_bounds__(1024)
 k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state, const int32_t* __restrict__ t_dev,
               int start, int cur_win, int mode, int32_t* __restrict__ act, int32_t* __restrict__ desc,
-              int32_t* __restrict__ n_new, int cap_new, int32_t* __restrict__ n_appended) {
+              int32_t* __restrict__ n_new, int cap_new, int32_t* __restrict__ n_appended, int32_t* __restrict__ blk_cnt,
+              int nblk) {
   __shared__ int sm[33];
   __shared__ int s_kind, s_t, s_t1, s_tprev;
   const int s = blockIdx.x;
@@ -242,6 +285,17 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
   }
   const int tprev = s_tprev;
   int carry = 0;
+  if (mode != 1 && blk_cnt) {
+    // inference: the per-block counts of k_active_count become offsets for k_active_write
+    for (int b0 = 0; b0 < nblk; b0 += blockDim.x) {
+      const int b = b0 + threadIdx.x;
+      const int v = b < nblk ? blk_cnt[s * nblk + b] : 0;
+      int total;
+      const int ex = block_exclusive_scan(v, sm, &total);
+      if (b < nblk) blk_cnt[s * nblk + b] = carry + ex;
+      carry += total;
+    }
+  } else
   for (int r0 = 0; r0 < n; r0 += 4 * 1024) {
     const int r = r0 + threadIdx.x * 4;
     int f[4], c = 0;
@@ -704,7 +758,7 @@ extern "C" int tmpnn_graph_associate(const tmpnn_graph* g, const tmpnn_index* ix
 }
 
 extern "C" size_t tmpnn_graph_append_scratch_ints(int num_seqs, int cap_rows) {
-  return (size_t)num_seqs * cap_rows + DESC * (size_t)num_seqs;
+  return (size_t)num_seqs * cap_rows + DESC * (size_t)num_seqs + (size_t)num_seqs * tmpnn_div_up(cap_rows, ROWS_PER_BLOCK);
 }
 
 extern "C" int tmpnn_graph_append(const tmpnn_graph* g, const tmpnn_frames* fr, const tmpnn_seq_state* st_,
@@ -719,9 +773,21 @@ extern "C" int tmpnn_graph_append(const tmpnn_graph* g, const tmpnn_frames* fr, 
   int32_t* desc = scratch + (size_t)g->num_seqs * g->cap_rows;
   tmpnn_seq_state zero = {};
   TMPNN_CUDA_TRY(cudaMemsetAsync(n_new, 0, 2 * sizeof(int32_t), st));
+  const int nblk = tmpnn_div_up(g->cap_rows, ROWS_PER_BLOCK);
+  int32_t* blk_cnt = desc + DESC * (size_t)g->num_seqs;
+  const bool grid_scan = mode != 1 && !start;
+  dim3 grid_rows(nblk, g->num_seqs);
+  if (grid_scan) {
+    k_active_count<<<grid_rows, 256, 0, st>>>(*g, nblk, blk_cnt);
+    TMPNN_LAUNCH_CHECK();
+  }
   k_append_plan<<<g->num_seqs, 1024, 0, st>>>(*g, *fr, st_ ? *st_ : zero, st_ ? 1 : 0, t_dev, start, cur_win_size, mode,
-                                              act, desc, n_new, cap_new, n_appended);
+                                              act, desc, n_new, cap_new, n_appended, grid_scan ? blk_cnt : nullptr, nblk);
   TMPNN_LAUNCH_CHECK();
+  if (grid_scan) {
+    k_active_write<<<grid_rows, 256, 0, st>>>(*g, nblk, blk_cnt, desc, DESC, act);
+    TMPNN_LAUNCH_CHECK();
+  }
   dim3 grid(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 4), 128)), g->num_seqs);
   k_append_fill<<<grid, 256, 0, st>>>(*g, *fr, act, desc, h, ldh, new_det_rows, new_det_x);
   TMPNN_LAUNCH_CHECK();

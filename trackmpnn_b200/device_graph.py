@@ -84,7 +84,7 @@ class SlabIndex:
         if structured:
             if getattr(self, '_scratch2', None) is None:
                 nbytes = int(L.lib().tmpnn_index_structured_scratch_bytes(graph.num_seqs, self.cap_dets))
-                self._scratch2 = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=graph.device)
+                self._scratch2 = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=graph.device)  # boundary counts start at 0
             L.call('tmpnn_index_build_structured', graph.c, self.c, L.ptr(active), L.ptr(self._scratch2), L.stream())
         else:
             L.call('tmpnn_index_build', graph.c, self.c, L.ptr(active), L.stream())
