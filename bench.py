@@ -387,11 +387,10 @@ def main():
     k_edges = sum(int(p[2].item()) for p in prof)
     hbm_peak, peak_src = measured_peaks()
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    tk = {'auto': 'pre3'}.get(eng.tensor_kernel, eng.tensor_kernel)
-    kname = ({'pre3': 'k_det_prepare + k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied '
+    tk = {'auto': 'pre'}.get(eng.tensor_kernel, eng.tensor_kernel)
+    kname = ({'pre': 'k_det_prepare + k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied '
                       'by cp.async, tcgen05.mma kind::f16 with a 3-term fp16 split, TMEM accumulators, dedicated MMA issuer warp, '
                       'two epilogue teams)',
-              'pre': 'k_det_prepare + k_mp_edge_tc<pre> (fused edge step, endpoints prepared once per detection)',
               'gather': 'k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'}[tk]
              if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
     # detection aggregation (K1): every association row's state is read for its two endpoints; compulsory bytes

@@ -220,9 +220,9 @@ int tmpnn_mp_edge_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const floa
  * biases folded in into det_p [index cap_dets][192] (fp32 FMA); the step kernel then copies the far endpoint's
  * image (cp.async), multiplies it on the tensor cores (negated for 'diff') and adds det_p[src] in the epilogue.
  * The source-side half of weight_ih (transposed, fp32) and the folded biases travel in the tail of edge_image.
- * tile_table: NULL = the kernel of csrc/mp_step_tc.cu (8 producer + 8 epilogue warps); a 16-byte aligned scratch of
- * tmpnn_tc_tile_table_bytes() = the re-staged kernel of csrc/mp_step_tc3.cu (dedicated MMA issuer warp, two epilogue
- * teams on alternating tiles, tiles located through the table, which the call rebuilds when group == 0). */
+ * The step kernel (csrc/mp_step_tc3.cu) has a dedicated MMA issuer warp and two epilogue teams on alternating tiles;
+ * it locates tiles through a table the call rebuilds (when group == 0) in tile_table, a 16-byte aligned scratch of
+ * tmpnn_tc_tile_table_bytes(). */
 size_t tmpnn_tc_tile_table_bytes(int num_seqs, int cap_rows);
 int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                              int group, int num_groups, int concat, const void *edge_image, float *det_img,

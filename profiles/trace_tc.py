@@ -37,9 +37,9 @@ def run():
     eng.run(max_ticks=8); torch.cuda.synchronize()
     cap = 2048
     buf = torch.zeros((cap, 16), dtype=torch.int64, device=dev)
-    kern = os.environ.get('TC_KERNEL', 'pre3')
+    kern = os.environ.get('TC_KERNEL', 'pre')
     eng.tensor_kernel = kern
-    f = getattr(L.lib(), 'tmpnn_debug_set_tc3_trace' if kern == 'pre3' else 'tmpnn_debug_set_tc_trace')
+    f = getattr(L.lib(), 'tmpnn_debug_set_tc3_trace' if kern == 'pre' else 'tmpnn_debug_set_tc_trace')
     f.argtypes = [C.c_void_p, C.c_int]; f(buf.data_ptr(), cap)
     eng._tick(flip=False); torch.cuda.synchronize()   # one more frame, traced (later launches overwrite earlier ones)
     f(None, 0)

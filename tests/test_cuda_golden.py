@@ -50,7 +50,7 @@ def _fix(scores, y_pred, tp):
 INFER = golden_names('infer')
 
 
-@pytest.mark.parametrize('tensor', [False, 'gather', 'pre', 'pre3'], ids=['fma', 'tcgen05', 'tcgen05-pre', 'tcgen05-pre3'])
+@pytest.mark.parametrize('tensor', [False, 'gather', 'pre'], ids=['fma', 'tcgen05', 'tcgen05-pre'])
 @pytest.mark.parametrize('name', INFER)
 def test_infer_free_running(name, tensor):
     """tensor=False: fp32 FMA kernel; 'gather' / 'pre': the tcgen05 kernels (3-term fp16 split; endpoints gathered

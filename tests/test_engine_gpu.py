@@ -54,7 +54,6 @@ GAT_SEEDS = [108, 41, 52, 68, 49, 44, 105]
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True),
     dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True, kernel='gather'),
     dict(seeds=[35, 36, 40], msg_type='concat', ret=2, graph=True, gap=(), tensor=True),
-    dict(seeds=[30, 49, 34, 52, 54, 72, 77], msg_type='diff', ret=0, graph=True, gap=(49, 52, 54), tensor=True, kernel='pre'),
     dict(seeds=[108, 84, 77, 100, 72, 32, 56], msg_type='diff', ret=0, graph=True, gap=(), hungarian=True),
     dict(seeds=GAT_SEEDS, msg_type='diff', ret=0, graph=True, gap=(), heads=2),
     dict(seeds=[84, 100, 48, 125, 56], msg_type='diff', ret=2, graph=False, gap=(), hungarian=True),
@@ -148,7 +147,7 @@ def test_structured_index_equals_general_index(ret):
         assert sa[-1] == 2 * int(a.n_edges.item())
 
 
-@pytest.mark.parametrize('kernel', ['fma', 'gather', 'pre', 'pre3'])
+@pytest.mark.parametrize('kernel', ['fma', 'gather', 'pre'])
 def test_engine_state_at_workload_size(kernel):
     """BDD-shaped sequences at the bench workload's size (~80 detections / frame, ~60 k association rows per
     window, hundreds of 128-row tiles per launch, so every pipeline stage / barrier phase of the tensor-core

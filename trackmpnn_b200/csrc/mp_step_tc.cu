@@ -93,23 +93,15 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-// PRE = false: the producers gather h[src], h[dst], subtract and split (msg_type 'diff' only).
-// PRE = true : gi = h[src] W_x^T -+ h[dst] W_d^T is linear in its two endpoints, and endpoints are detection
-//   rows, ~150x fewer than association rows.  k_det_prepare computes once per detection (a) its fp16 hi/lo
-//   image and (b) P' = its source-side contribution to the three input gates with the biases folded in.  The
-//   producers then only COPY the far endpoint's image into the x stage (cp.async, no registers, no ALU), the
-//   tensor cores multiply it with the far-endpoint weights (A negated through the instruction descriptor for
-//   'diff'), and the epilogue reads P'[src] where it used to read the biases (rows of a tile share a handful of
-//   sources, so those loads are warp-uniform L1 hits).
-template <bool PRE>
+// The producers gather h[src], h[dst], subtract and split per association row (msg_type 'diff' only); the form with
+// the endpoints prepared once per detection row lives in mp_step_tc3.cu.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
              const int32_t* __restrict__ n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
              int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const unsigned char* __restrict__ image,
              float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
              int32_t* __restrict__ status, const int32_t* __restrict__ phys, const int32_t* __restrict__ psrc,
-             const int32_t* __restrict__ pdst, const float* __restrict__ det_img, const float* __restrict__ det_p,
-             const int32_t* __restrict__ det_of_row, uint32_t xflags) {
+             const int32_t* __restrict__ pdst) {
   extern __shared__ unsigned char smem_dyn[];
   const int total = tile_ptr[num_seqs];
   if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
@@ -147,111 +139,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
   const uint32_t tmem_base = *tmem_slot;
   const int stride = gridDim.x;
 
-  if (PRE && warp >= EPI_WARPS) {
-    // ================= producers (pre-split endpoints) =================
-    const int pt = threadIdx.x - 32 * EPI_WARPS;
-    const int g = pt >> 4, l = pt & 15, gl0 = lane & 16;  // row group (rows g + 16 p), 16-byte chunk within the row
-    const uint32_t FULL = 0xffffffffu;
-    const float4* __restrict__ h4p = reinterpret_cast<const float4*>(h_in);
-    const uint32_t ldh4 = (uint32_t)ldh >> 2, cl4 = ((uint32_t)col >> 2) + (uint32_t)l;
-    const bool dfr = phys != nullptr;  // deferred compaction: own rows at GLOBAL physical rows
-    const int idx_row = g + 16 * (l & 7);  // lane l (and l + 8) of a group keeps the far endpoint of row g + 16 (l & 7)
-    // detection images have the geometry of h: chunk l of the 256 B image of row R sits at
-    // (R * ldh + col) * 4 + 16 l; chunks 0-7 are the hi halves (K order), 8-15 the lo halves
-    const unsigned char* __restrict__ imgb = reinterpret_cast<const unsigned char*>(det_img) + (size_t)col * 4 + 16 * l;
-    const size_t row_bytes = (size_t)ldh * 4;
-    const uint32_t x_dst0 = sm_u + OFF_A + (uint32_t)(l >> 3) * A_PART + sw128(g, l & 7);  // + 2048 p: row g + 16 p
-    const uint32_t h_off0 = sw128(g, l >> 1) + ((l & 1) << 3);
-    int seq = 0;
-    auto coords = [&](int tile, uint32_t& b, int& r, int& nl) {
-      seek_seq(tile_ptr, num_seqs, tile, seq);
-      b = (uint32_t)seq * (uint32_t)cap_rows;
-      r = (tile - __ldg(tile_ptr + seq)) * TCM;
-      nl = __ldg(n_rows + seq) - r;
-    };
-    // rows past the end of the slab repeat its last row; everything they produce is masked by the epilogue
-    auto ld_idx = [&](uint32_t b, int r, int nl) { return __ldg(dst + b + r + min(idx_row, nl - 1)); };
-    auto ld_phys = [&](uint32_t b, int r, int nl) { return dfr ? __ldg(phys + b + r + min(idx_row, nl - 1)) : 0; };
-    // far-endpoint images of one tile -> x images of a stage: 8 x 16 B per thread, no registers, no ALU
-    auto issue_x = [&](int st, uint32_t b, int iv) {
-      const uint32_t s0 = x_dst0 + (uint32_t)st * A_STAGE;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int d = __shfl_sync(FULL, iv, gl0 + p);  // -1 for detection rows inside the tile: any valid row will do
-        const unsigned char* sp = imgb + (size_t)(b + (uint32_t)max(d, 0)) * row_bytes;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2048u * p), "l"(sp) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // coordinates: this tile, the next one, and (inside the loop) the one after; indices are fetched two
-    // tiles ahead so that the copies of the next tile can be issued while this one is in the tensor core
-    uint32_t base, b1;
-    int r0, r1, nl0, nl1;
-    coords(blockIdx.x, base, r0, nl0);
-    b1 = base; r1 = r0; nl1 = nl0;
-    if ((int)blockIdx.x + stride < total) coords(blockIdx.x + stride, b1, r1, nl1);
-    const int i0 = ld_idx(base, r0, nl0), pw0 = ld_phys(base, r0, nl0);
-    int i1 = ld_idx(b1, r1, nl1), pw1 = ld_phys(b1, r1, nl1);
-    float4 own[8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int sp = __shfl_sync(FULL, pw0, gl0 + p);
-      const uint32_t orow = dfr ? (uint32_t)sp : base + r0 + min(g + 16 * p, nl0 - 1);
-      own[p] = __ldg(h4p + orow * ldh4 + cl4);
-    }
-    issue_x(0, base, i0);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
-      const int stage = it & 1;
-      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-      unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
-      uint32_t b2 = b1;
-      int r2 = r1, nl2 = nl1, i2 = 0, pw2 = pw1;
-      if (tile + 2 * stride < total) {
-        coords(tile + 2 * stride, b2, r2, nl2);
-        i2 = ld_idx(b2, r2, nl2);   // in flight for a whole tile
-        pw2 = ld_phys(b2, r2, nl2);
-      }
-      float amax = 0.f;
-      // h images: released by the epilogue of the previous tile of this stage
-      mbar_wait(bar_hfree + 8 * stage, phase ^ 1u, status);
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const float4 h4 = own[p];
-        // this row's slot of the next tile: HBM latency, one tile ahead (unconditional, clamped address)
-        const int sp = __shfl_sync(FULL, pw1, gl0 + p);
-        const uint32_t orow = dfr ? (uint32_t)sp : b1 + r1 + min(g + 16 * p, nl1 - 1);
-        own[p] = __ldg(h4p + orow * ldh4 + cl4);
-        uint2 hh, hl;
-        split4(h4, hh, hl, amax);
-        const uint32_t off = h_off0 + 2048u * p;
-        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh;
-        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl;
-      }
-      if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
-      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's x images (issued one tile ago) have landed
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_full + 8 * stage);
-        if (warp - EPI_WARPS == (it & (PROD_WARPS - 1))) {  // this tile's MMA issuer
-          mbar_wait(bar_tfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained
-          mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows
-          tc_fence_after();
-          issue_tile_mma(sm_u, tmem_base, stage, xflags, bar_xfree + 8 * stage);
-          umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
-        }
-      }
-      __syncwarp();
-      if (tile + stride < total) {
-        // the other stage's x images are free once the previous tile's x MMAs retired (issued a tile ago)
-        mbar_wait(bar_xfree + 8 * (stage ^ 1), ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u, status);
-        issue_x(stage ^ 1, b1, i1);
-      }
-      base = b1; r0 = r1; nl0 = nl1;
-      b1 = b2; r1 = r2; nl1 = nl2; i1 = i2; pw1 = pw2;
-    }
-  } else if (warp >= EPI_WARPS) {
+  if (warp >= EPI_WARPS) {
     // ================= producers =================
     const int pt = threadIdx.x - 32 * EPI_WARPS;
     const int g = pt >> 4, l = pt & 15, gl0 = lane & 16;  // row group (rows g + 16 p), float4 within the row
@@ -386,7 +274,6 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
     // this row's coordinates and its source (< 0: not an edge row) are fetched two tiles ahead, the source's
-    // position in the detection list (PRE: row of P') one tile ahead
     int seq = 0, it = 0;
     auto coords = [&](int tile, size_t& rw, int& nr, int& lrr) {
       seek_seq(tile_ptr, num_seqs, tile, seq);
@@ -396,7 +283,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     };
     auto ld_src = [&](size_t rw, int nr, int lrr) { return __ldg(src + (nr > 0 ? rw : rw - lrr)); };  // clamped to the slab's first row
     size_t row, row1;
-    int nrem, nrem1, lr, lr1, srcv, srcv1, ks = 0, ks1 = 0;
+    int nrem, nrem1, lr, lr1, srcv, srcv1;
     coords(blockIdx.x, row, nrem, lr);
     srcv = ld_src(row, nrem, lr);
     row1 = row; nrem1 = nrem; lr1 = lr; srcv1 = srcv;
@@ -404,15 +291,12 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       coords(blockIdx.x + stride, row1, nrem1, lr1);
       srcv1 = ld_src(row1, nrem1, lr1);
     }
-    if (PRE) ks = __ldg(det_of_row + (row - lr) + max(srcv, 0));
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
       const int stage = it & 1;
       const uint32_t phase = (uint32_t)(it >> 1) & 1u;
       unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
       const size_t row_cur = row;
       const int nrem_cur = nrem, src_cur = srcv;
-      const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // PRE: this row's source contribution
-      if (PRE) ks1 = __ldg(det_of_row + (row1 - lr1) + max(srcv1, 0));  // srcv1 landed during the previous tile
       size_t row2 = row1;
       int nrem2 = nrem1, lr2 = lr1, srcv2 = srcv1;
       if (tile + 2 * stride < total) {
@@ -456,25 +340,12 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         tmem_ld8u(t0 + 128 + ch * 8, an);
         tmem_ld8u(t0 + 192 + ch * 8, ahn);
         const int j0 = c0 + ch * 8;
-        // additive terms of the three input gates: the fused biases, or (PRE) the source's P' row, which
-        // already holds -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
-        ulonglong2 brv[2], bzv[2], biv[2];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          if (PRE) {
-            brv[v] = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
-            bzv[v] = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
-            biv[v] = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
-          } else {
-            brv[v] = *reinterpret_cast<const ulonglong2*>(bias + j0 + 4 * v);
-            bzv[v] = *reinterpret_cast<const ulonglong2*>(bias + H + j0 + 4 * v);
-            biv[v] = *reinterpret_cast<const ulonglong2*>(bias + 2 * H + j0 + 4 * v);
-          }
-        }
         tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          const ulonglong2 br = brv[v], bz = bzv[v], bi = biv[v];
+          const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(bias + j0 + 4 * v);
+          const ulonglong2 bz = *reinterpret_cast<const ulonglong2*>(bias + H + j0 + 4 * v);
+          const ulonglong2 bi = *reinterpret_cast<const ulonglong2*>(bias + 2 * H + j0 + 4 * v);
           const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
           const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
           f32x2 o[2];
@@ -527,7 +398,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       }
       named_bar_sync(1 + quad, 64);
       TC_TRACE(it, 13, threadIdx.x == 0);
-      row = row1; nrem = nrem1; lr = lr1; srcv = srcv1; ks = ks1;
+      row = row1; nrem = nrem1; lr = lr1; srcv = srcv1;
       row1 = row2; nrem1 = nrem2; lr1 = lr2; srcv1 = srcv2;
     }
   }
@@ -599,8 +470,7 @@ k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* _
 }  // namespace
 
 int tmpnn_init_tc() {
-  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_det_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
   return TMPNN_OK;
 }
@@ -624,10 +494,10 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   int rc = tmpnn_init();
   if (rc) return rc;
-  k_mp_edge_tc<false><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+  k_mp_edge_tc<<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
       (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
-      g->psrc, g->pdst, nullptr, nullptr, nullptr, 0u);
+      g->psrc, g->pdst);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -636,7 +506,7 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
                                         int group, int num_groups, int concat, const void* edge_image, float* det_img,
                                         float* det_p, void* tile_table, void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_image && ix->tile128_ptr && ix->det_of_row && ix->det_rows, "null argument");
-  TMPNN_REQUIRE(det_img && det_p, "null argument");
+  TMPNN_REQUIRE(det_img && det_p && tile_table, "null argument");
   TMPNN_REQUIRE(h_in != h_out && det_img != h_in && det_img != h_out, "h_in, h_out and det_img must be distinct buffers");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   int rc = tmpnn_init();
@@ -645,15 +515,6 @@ extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index*
   k_det_prepare<<<TMPNN_SM_COUNT * 4, 256, PREP_SMEM, st>>>(h_in, ldh, group * H, ix->n_dets, ix->det_rows, g->phys,
                                                        (const unsigned char*)edge_image, det_img, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
-  if (tile_table) {  // re-staged kernel (mp_step_tc3.cu)
-    TMPNN_REQUIRE(((uintptr_t)tile_table & 15) == 0, "tile_table must be 16-byte aligned");
-    return tmpnn_edge_tc3_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_image, det_img, det_p, tile_table, st);
-  }
-  // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
-  k_mp_edge_tc<true><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, st>>>(
-      h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
-      (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
-      g->psrc, g->pdst, det_img, det_p, ix->det_of_row, concat ? 0u : (1u << 13));
-  TMPNN_LAUNCH_CHECK();
-  return TMPNN_OK;
+  TMPNN_REQUIRE(((uintptr_t)tile_table & 15) == 0, "tile_table must be 16-byte aligned");
+  return tmpnn_edge_tc3_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_image, det_img, det_p, tile_table, st);
 }

@@ -113,8 +113,8 @@ class TrackEngine:
             self.hung_scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
         diff = all(g.msg_type == 'diff' for g in model.factor_grus)
         # tcgen05 path when the batch can fill 128-row tiles on every SM; fp32 FMA path otherwise.
-        # tensor_kernel 'gather': endpoints gathered and split per association row ('diff' only); 'pre': prepared
-        # once per detection row (both msg_types); 'auto': gather for diff, pre for concat
+        # tensor_kernel 'pre' (= 'auto'): endpoints prepared once per detection row (both msg_types); 'gather':
+        # gathered and split per association row ('diff' only)
         self.tensor_kernel = tensor_kernel
         self.tensor = (diff or tensor_kernel != 'gather') and (
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))

@@ -134,16 +134,15 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
 
 
 def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, kernel='auto'):
-    """Edge rows of feature group g on the tensor cores.  kernel 'gather': endpoints gathered, subtracted and split
-    per association row (tmpnn_mp_edge_fwd_tc, msg_type 'diff' only); 'pre' / 'pre3': endpoints prepared once per
-    detection row (tmpnn_mp_edge_fwd_tc_pre without / with the tile table = first / re-staged kernel; both msg_types);
-    'auto': pre3."""
+    """Edge rows of feature group g on the tensor cores.  kernel 'pre' (= 'auto'): endpoints prepared once per
+    detection row, re-staged kernel (tmpnn_mp_edge_fwd_tc_pre; both msg_types); 'gather': endpoints gathered,
+    subtracted and split per association row (tmpnn_mp_edge_fwd_tc, the first tensor-core kernel, 'diff' only)."""
     gru = model.factor_grus[g]
     concat = int(gru.msg_type == 'concat')
     st = L.stream()
     if kernel == 'auto':
-        kernel = 'pre3'
-    if kernel not in ('pre3', 'pre', 'gather'):
+        kernel = 'pre'
+    if kernel not in ('pre', 'gather'):
         raise ValueError(f'unknown tensor-core kernel {kernel!r}')
     if kernel == 'gather':
         if concat:
@@ -157,12 +156,10 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
     dp = scratch.get('det_p')
     if dp is None or dp.shape[0] < index.cap_dets:
         dp = scratch['det_p'] = torch.empty((index.cap_dets, 3 * H), dtype=torch.float32, device=h_in.device)
-    tab = None
-    if kernel == 'pre3':
-        nb = int(L.lib().tmpnn_tc_tile_table_bytes(graph.num_seqs, graph.cap_rows))
-        tab = scratch.get('tile_tab')
-        if tab is None or tab.numel() * 4 < nb:
-            tab = scratch['tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
+    nb = int(L.lib().tmpnn_tc_tile_table_bytes(graph.num_seqs, graph.cap_rows))
+    tab = scratch.get('tile_tab')
+    if tab is None or tab.numel() * 4 < nb:
+        tab = scratch['tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
     L.call('tmpnn_mp_edge_fwd_tc_pre', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(image),
            L.ptr(img), L.ptr(dp), L.ptr(tab), st)
 
