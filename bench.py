@@ -250,6 +250,77 @@ def run_train_leg(a, dev):
     return out
 
 
+def run_c1_leg(a, dev):
+    """BASELINE.json configs[0]: one KITTI-shaped sequence (--category=Car shape: ~10 detections / frame, 100 frames,
+    window 5, F = 8), the reference's own CPU-runnable case.  Timed three ways: the reference's driver loop
+    (infer.py:48-87) over the drop-in modules (one sequence, tensors in / tensors out, host-visible counts every
+    call), the batched TrackEngine with S = 1 (CUDA-graph replay), and the oracle port on the host cores."""
+    import torch
+    from trackmpnn_b200 import synth
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.utils.graph import initialize_graph, update_graph, decode_tracks
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories('kitti'), 64, 0, 'diff').to(dev).eval()
+    Xn, yn = synth.make_sequence(5, 100, 10, 'kitti')
+    X, y = torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)
+
+    def two(sc):
+        return torch.cat((1 - sc, sc), dim=1)
+
+    def dropin():
+        y_out = yn[0].astype(np.int64); y_out[:, 1] = -1
+        frames = edges = 0
+        with torch.no_grad():
+            y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, 0, 'test', True)
+            scores, logits, states, _ = model(feats, None, node_adj, edge_adj)
+            scores = two(scores)
+            for t in range(t_st, t_end):
+                y_pred, feats, node_adj, edge_adj, labels = update_graph(node_adj, labels, scores, y_pred, X, y, t,
+                                                                         use_hungraian=False, mode='test', cuda=True)
+                scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+                scores = two(scores)
+                edges += int((y_pred[:, 0] == -1).sum())
+                t_upto = t_end if t == t_end - 1 else t - 5 + 2
+                y_pred, y_out, states, node_adj, labels, scores = decode_tracks(
+                    states, node_adj, labels, scores, y_pred, y_out, t_upto, 0, use_hungraian=False, cuda=True)
+                frames += 1
+        return frames, edges
+
+    dropin()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    frames, edges = dropin()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {'workload': 'C1 kitti-shaped, 1 sequence, 100 frames, ~Poisson(10) dets/frame, win 5, greedy decode, stock init',
+           'dropin': {'frames_per_s': frames / dt, 'edge_updates_per_s': edges / dt, 'api': 'initialize_graph / update_graph / '
+                      'TrackMPNN.forward / decode_tracks, one call each per frame (infer.py:48-87)'}}
+    eng = TrackEngine(model, [(Xn[0], yn[0])], cur_win_size=5, ret_win_size=0)
+    for _ in range(3):
+        eng.run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        eng.run()
+    _, st = eng.results()
+    dt = (time.perf_counter() - t0) / reps
+    out['engine_s1'] = {'frames_per_s': st['frames'] / dt, 'edge_updates_per_s': st['edge_updates'] / dt,
+                        'api': 'TrackEngine(S = 1).run(), CUDA-graph replay (launch-latency bound: ~1 k rows per window)'}
+    if not a.skip_cpu:
+        from oracle import trackmpnn_oracle as O
+        from oracle.infer_loop import run_infer
+        params = O.init_params('2d', synth.num_categories('kitti'), 64, 'diff', seed=5)
+        t0 = time.perf_counter()
+        _, stc = run_infer(params, Xn, yn, ncategories=synth.num_categories('kitti'), cur_win_size=5)
+        dtc = time.perf_counter() - t0
+        out['cpu_baseline'] = {'frames_per_s': stc['frames'] / dtc, 'edge_updates_per_s': stc['edge_updates'] / dtc,
+                               'cores': os.cpu_count(), 'kind': 'port',
+                               'note': 'the reference itself measured 14.1 frames/s on this shape (SURVEY.md section 6)'}
+    return out
+
+
 def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     """BASELINE.json configs[4]: data-parallel training.  Every rank runs forward + losses + backward of its own
     chunk (drop-in modules), the ranks all-reduce ONE flat buffer of all parameter gradients over NCCL
@@ -457,6 +528,10 @@ def main():
     if rank == 0 and world == 1 and not a.skip_train:
         train = run_train_leg(a, dev)
 
+    c1 = None
+    if rank == 0 and world == 1 and not a.skip_train:
+        c1 = run_c1_leg(a, dev)
+
     train_ddp = None
     if world > 1 and not a.skip_train:
         train_ddp = run_train_ddp_leg(a, dev, rank, world, barrier, reduce_)
@@ -471,7 +546,7 @@ def main():
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
                           'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
-               'roofline': roof, 'roofline_aggregation': agg, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'train': train, 'train_ddp': train_ddp}
+               'roofline': roof, 'roofline_aggregation': agg, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'c1': c1, 'train': train, 'train_ddp': train_ddp}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
