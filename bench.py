@@ -433,6 +433,7 @@ def main():
     # current stream), so the timed passes do not use CUDA-graph replay
     eng.use_cuda_graph = False
     eng.profile = []
+    eng.profile_compact = []
     clocks = ClockSampler(local)
     barrier(); torch.cuda.synchronize()
     clocks.start()
@@ -453,6 +454,8 @@ def main():
     tot_frames = reduce_(frames, dist.ReduceOp.SUM if world > 1 else None)
     prof = eng.profile
     eng.profile = None
+    cprof = eng.profile_compact
+    eng.profile_compact = None
     eng.ga.check_status()
     k_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
     k_edges = sum(int(p[2].item()) for p in prof)
@@ -473,6 +476,20 @@ def main():
            'frac': agg_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak if a_ms > 0 else 0.0, 'avg_launch_ms': a_ms / max(1, len(prof)),
            'share_of_step': a_ms / ms if ms > 0 else None, 'algorithmic_bytes': '256 B per association row + 256 B per detection',
            'traffic': None}
+    # window slide (K4): keep-mask scan + order-preserving compaction with index remap.  With deferred compaction
+    # the states stay where they are: per surviving row 36 B of metadata are read and written, 12 B of position maps
+    # written, 4 B of new_of_old written and read back for the two endpoints; per row 1 B keep flag + 4 B new_of_old.
+    c_ms = sum(p[0].elapsed_time(p[1]) for p in cprof)
+    rows_in = sum(int(p[2].item()) for p in cprof)
+    rows_out = sum(int(p[3].item()) for p in cprof)
+    per_kept = (36 + 36 + 12 + 8) if eng.deferred else (36 + 36 + 8 + 512 * eng.G)
+    c_bytes = float(per_kept) * rows_out + 9.0 * rows_in
+    comp = {'kernel': 'tmpnn_graph_compact (k_compact_count / scan / map / move: prefix-sum stream compaction + src/dst remap'
+                      + (', position maps instead of moving the states)' if eng.deferred else ', states moved)'),
+            'bound': 'hbm', 'achieved': c_bytes / (c_ms * 1e-3) / 1e9 if c_ms > 0 else 0.0, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': c_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak if c_ms > 0 else 0.0, 'avg_launch_ms': c_ms / max(1, len(cprof)),
+            'share_of_step': c_ms / ms if ms > 0 else None, 'rows_in': rows_in, 'rows_kept': rows_out,
+            'algorithmic_bytes': f'{per_kept} B per surviving row + 9 B per row', 'traffic': None}
     n_l = max(1, len(prof))
     tr_e, tr_a = (measured_traffic('k_mp_edge_tc3') if eng.tensor else None), measured_traffic('k_aggregate_dets')
     agg['traffic'] = tr_a * k_edges / n_l if tr_a else None
@@ -546,7 +563,7 @@ def main():
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
                           'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
-               'roofline': roof, 'roofline_aggregation': agg, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'c1': c1, 'train': train, 'train_ddp': train_ddp}
+               'roofline': roof, 'roofline_aggregation': agg, 'roofline_compaction': comp, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'c1': c1, 'train': train, 'train_ddp': train_ddp}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

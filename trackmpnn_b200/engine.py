@@ -121,6 +121,7 @@ class TrackEngine:
         self._tc_scratch = {}
         self._gat_scratch = {}
         self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end) per step
+        self.profile_compact = None  # when a list: (start, end, rows before, rows after) per window slide
         self._graph = None
         self.ticks = 0
 
@@ -212,9 +213,15 @@ class TrackEngine:
                L.ptr(self.keep), L.ptr(self.decode_scratch), st)
         # plain: move the survivors h_alt -> h_cur; deferred: emit the maps only (sequences that sat the step out
         # are copied h_in -> h_out)
+        if self.profile_compact is not None:
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
         L.call('tmpnn_graph_compact', g.c, go.c, L.ptr(self.keep), L.ptr(h_out), L.ptr(h_in),
                L.ptr(self.st['active']), L.ptr(h_out if self.deferred else h_in), self.ldh, L.ptr(self.new_of_old),
                L.ptr(self.compact_scratch), st)
+        if self.profile_compact is not None:
+            c1.record()
+            self.profile_compact.append((c0, c1, g.n_rows.sum(), go.n_rows.sum()))
         self.frames_done += self.st['active'].sum()
         self.t_dev += 1
 
