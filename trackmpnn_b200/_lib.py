@@ -169,7 +169,7 @@ _LAUNCHES = [0]
 # kernels launched per C-ABI call (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
-    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 12, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 2, 'tmpnn_pack_gru_tc': 1,
+    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 12, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
