@@ -108,7 +108,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi was started a little earlier so that its start-up latency does not
+        eat a short region; only samples taken from here on count (all of them if the region was shorter than one
+        sampling period)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -120,7 +126,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t_mark = getattr(self, 't_mark', 0.0)
+        rows = [r for t, r in self.rows if t >= t_mark] or [r for _, r in self.rows[-2:]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -435,8 +443,10 @@ def main():
     eng.profile = []
     eng.profile_compact = []
     clocks = ClockSampler(local)
-    barrier(); torch.cuda.synchronize()
     clocks.start()
+    eng.run(); torch.cuda.synchronize()   # one more untimed pass while nvidia-smi starts up
+    barrier(); torch.cuda.synchronize()
+    clocks.mark()
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
