@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--skip-train', action='store_true')
     ap.add_argument('--train-chunks', type=int, default=6, help='BPTT chunks timed by the training leg')
     ap.add_argument('--train-dets', type=int, default=40)
+    ap.add_argument('--train-batch', type=int, default=32, help='chunks per batch of the batched trainer')
     return ap.parse_args()
 
 
@@ -215,6 +216,46 @@ def train_chunk_cuda(model, opt, X, y):
     return edges, float(loss.item())
 
 
+def run_train_batched(a, dev, model, opt, chunk, steps=4):
+    """The same training step for B chunks at once (trackmpnn_b200/train_engine.py): per message-passing step ONE
+    block-diagonal graph, so every kernel runs once for the whole batch; BatchNorm statistics and the BCE means stay
+    per chunk, the batch loss is the sum of the chunk losses (verified against the chunk-by-chunk path in
+    tests/test_train_engine_gpu.py).  The graphs depend on the labels only and are built once, outside the timed
+    steps (reported separately)."""
+    import torch
+    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    B = a.train_batch
+    chunks = []
+    for i in range(B):
+        Xn, yn = chunk(3000 + i)
+        chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    batch = TrainBatch(chunks, dev)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+
+    def step():
+        opt.zero_grad()
+        loss = batch_loss(model, batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    step(); step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    lv = float(loss.item())
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {'chunks_per_batch': B, 'message_passing_steps': len(batch.steps), 'edge_rows_per_batch': int(batch.edge_rows),
+            'value': batch.edge_rows / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': B / dt,
+            'ms_per_batch': 1e3 * dt, 'graph_build_ms_per_chunk': 1e3 * t_build / B, 'loss': lv,
+            'value_incl_graph_build': batch.edge_rows / (dt + t_build)}
+
+
 def run_train_leg(a, dev):
     import torch
     from trackmpnn_b200 import synth
@@ -244,6 +285,7 @@ def run_train_leg(a, dev):
                        f'tp_classifier, teacher forcing, BPTT over all steps, CE+BCE, Adam), drop-in modules, 1 chunk at a time',
            'value': edges / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': a.train_chunks / dt,
            'ms_per_chunk': 1e3 * dt / a.train_chunks, 'edge_rows_per_chunk': edges // max(1, a.train_chunks)}
+    out['batched'] = run_train_batched(a, dev, model, opt, chunk)
     if not a.skip_cpu:
         from oracle import train_ref as T, trackmpnn_oracle as O
         params = O.init_params('2d', 3, 64, 'diff', seed=5)

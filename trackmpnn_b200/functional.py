@@ -304,6 +304,26 @@ def _param_list(model):
     return ps
 
 
+class NewRowGroups:
+    """New detection rows of a block-diagonal batch of window graphs (trackmpnn_b200/train_engine.py): ``xd`` holds
+    the feature rows, every group ``(x_idx, out_rows, n_dets, n_edge_rows)`` is one chunk's share -- one BatchNorm
+    batch, as in the reference, which feeds one chunk per forward."""
+
+    def __init__(self, xd, groups):
+        self.xd, self.groups = xd, groups
+
+
+def _input_rows_forward(model, xd, x_idx, out_rows, nd, n_edge_rows, h_cur, ldh):
+    """K0 of every feature group on one BatchNorm batch of new rows (nd detections + n_edge_rows all-zero edge
+    rows); returns what tmpnn_input_bwd needs."""
+    per_group = []
+    for g in range(len(model.feature_idx)):
+        training = model.input_transforms[g][1].training
+        a, mean, var = input_transform_rows(model, g, xd, x_idx, nd, n_edge_rows, h_cur, ldh, out_rows)
+        per_group.append((a, mean.clone(), var.clone(), training))
+    return (xd, x_idx, out_rows, nd, n_edge_rows, per_group)
+
+
 class _MPStepFn(torch.autograd.Function):
     """One ``TrackMPNN.forward`` with everything its backward needs kept on the device: the state the
     step consumed, the GRU gates of every row, the detection aggregates, Linear1 outputs and the
@@ -319,26 +339,32 @@ class _MPStepFn(torch.autograd.Function):
         n_tot = wg.n
         G = len(model.feature_idx)
         ldh = G * H
-        n_new = int(x.size()[0])
-        n_old = n_tot - n_new
-        if (0 if h_in is None else int(h_in.shape[0])) != n_old:
-            raise ValueError(f'h_in has {0 if h_in is None else int(h_in.shape[0])} rows, graph has {n_tot} rows of '
-                             f'which {n_new} are new')
-        h_cur = torch.zeros((n_tot, ldh), dtype=torch.float32, device=dev)
-        if n_old:
-            h_cur[:n_old].copy_(h_in.detach())
-        saved_in = None
+        saved_in = []
+        if isinstance(x, NewRowGroups):
+            # batched trainer: h_in already has one row per graph row (zeros where rows are new); the new detection rows
+            # come in groups, one per chunk = one BatchNorm batch each (the reference normalises chunk by chunk)
+            if h_in is None or int(h_in.shape[0]) != n_tot:
+                raise ValueError('with NewRowGroups h_in must have one row per graph row')
+            n_old, n_new = n_tot, 0
+            h_cur = h_in.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+            for x_idx, out_rows, nd, n_edge in x.groups:
+                if nd > 0:
+                    saved_in.append(_input_rows_forward(model, x.xd, x_idx, out_rows, nd, n_edge, h_cur, ldh))
+        else:
+            n_new = int(x.size()[0])
+            n_old = n_tot - n_new
+            if (0 if h_in is None else int(h_in.shape[0])) != n_old:
+                raise ValueError(f'h_in has {0 if h_in is None else int(h_in.shape[0])} rows, graph has {n_tot} rows of '
+                                 f'which {n_new} are new')
+            h_cur = torch.zeros((n_tot, ldh), dtype=torch.float32, device=dev)
+            if n_old:
+                h_cur[:n_old].copy_(h_in.detach())
         if n_new > 0:
             new_det = torch.nonzero(wg.g.ts[n_old:n_tot] >= 0)[:, 0].to(torch.int32)
             nd = int(new_det.numel())
             out_rows = (new_det + n_old).contiguous()
             xd = x.detach().to(device=dev, dtype=torch.float32).contiguous()
-            per_group = []
-            for g in range(G):
-                training = model.input_transforms[g][1].training
-                a, mean, var = input_transform_rows(model, g, xd, new_det, nd, n_new - nd, h_cur, ldh, out_rows)
-                per_group.append((a, mean.clone(), var.clone(), training))
-            saved_in = (xd, new_det, out_rows, nd, n_new - nd, per_group)
+            saved_in.append(_input_rows_forward(model, xd, new_det, out_rows, nd, n_new - nd, h_cur, ldh))
         ix = wg.index()
         h_out = torch.empty_like(h_cur)
         packs = packed_cells(model)
@@ -414,9 +440,10 @@ class _MPStepFn(torch.autograd.Function):
                    L.ptr(grads[b + 11]), st)
             # through the gather / segmented sum, into the state this step consumed
             L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx, L.ptr(dagg), L.ptr(dh_cur), ldh, col, st)
-            # new detection rows: through the input transform
-            if ctx.saved_in is not None and ctx.saved_in[3] > 0:
-                xd, new_det, out_rows, nd, n_edge_new, per_group = ctx.saved_in
+            # new detection rows: through the input transform (one group of rows per BatchNorm batch)
+            for xd, new_det, out_rows, nd, n_edge_new, per_group in ctx.saved_in:
+                if nd <= 0:
+                    continue
                 a, mean, var, training = per_group[g]
                 cols = model.feature_idx[g]
                 scratch = torch.empty((2 * nd, H), **f32)
