@@ -373,42 +373,32 @@ def run_c1_leg(a, dev):
 
 def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     """BASELINE.json configs[4]: data-parallel training.  Every rank runs forward + losses + backward of its own
-    chunk (drop-in modules), the ranks all-reduce ONE flat buffer of all parameter gradients over NCCL
+    batch of chunks (batched trainer), the ranks all-reduce ONE flat buffer of all parameter gradients over NCCL
     (trackmpnn_b200.parallel.allreduce_gradients), then every rank takes the same Adam step.  BatchNorm statistics
     stay per chunk (no SyncBN), as in the reference."""
     import torch
     import torch.distributed as dist
     from trackmpnn_b200 import parallel, synth
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories('kitti'), 64, 0, 'diff').to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
     params = list(model.parameters())
-    n_steps = a.train_chunks
-
-    def chunk(seed):
-        ts = synth.train_chunk_timestamps(seed, 5, 2)
-        Xn, yn = synth.make_sequence(seed, None, a.train_dets, 'kitti', timestamps=ts)
-        return torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)
-
-    data = [chunk(2000 + rank * 100 + i) for i in range(n_steps + 2)]
-
-    class _NoStep:   # train_chunk_cuda steps the optimizer itself; here the step comes after the all-reduce
-        def zero_grad(self):
-            opt.zero_grad()
-
-        def step(self):
-            pass
-
-    ar_ms, edges = 0.0, 0
-    for i, (X, y) in enumerate(data):
+    B, n_steps = a.train_batch, a.train_chunks
+    chunks = []
+    for i in range(B):
+        ts = synth.train_chunk_timestamps(2000 + rank * 1000 + i, 5, 2)
+        Xn, yn = synth.make_sequence(2000 + rank * 1000 + i, None, a.train_dets, 'kitti', timestamps=ts)
+        chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
+    batch = TrainBatch(chunks, dev)
+    ar_ms = 0.0
+    for i in range(n_steps + 2):
         if i == 2:
             barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-        tc0 = time.perf_counter()
-        e, _ = train_chunk_cuda(model, _NoStep(), X, y)
-        torch.cuda.synchronize()
-        tc1 = time.perf_counter()
+        opt.zero_grad()
+        batch_loss(model, batch).backward()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         nfl = parallel.allreduce_gradients(params, average=True)
@@ -417,20 +407,18 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
         if i >= 2:
             torch.cuda.synchronize()
             ar_ms += a0.elapsed_time(a1)
-            edges += e
-        if os.environ.get('TMPNN_BENCH_DEBUG'):
-            print(f'[rank {rank}] chunk {i}: fwd+bwd {1e3 * (tc1 - tc0):.1f} ms, allreduce+step {1e3 * (time.perf_counter() - tc1):.1f} ms, '
-                  f'{e} edge rows', file=sys.stderr, flush=True)
     torch.cuda.synchronize(); barrier()
     dt = reduce_(time.perf_counter() - t0, dist.ReduceOp.MAX)
-    tot_edges = reduce_(edges, dist.ReduceOp.SUM)
+    tot_edges = reduce_(batch.edge_rows * n_steps, dist.ReduceOp.SUM)
     # every rank must hold the same parameters after the same averaged step
     chk = torch.stack([p.detach().double().sum() for p in params]).sum()
     lo, hi = reduce_(float(chk), dist.ReduceOp.MIN), reduce_(float(chk), dist.ReduceOp.MAX)
-    return {'workload': f'C5 data-parallel training: {world} ranks x {n_steps} kitti-shaped chunks (~Poisson({a.train_dets}) dets/frame), '
-                        'forward + CE/BCE + backward per rank, one NCCL all-reduce of the flat gradient buffer, Adam',
+    return {'workload': f'C5 data-parallel training: {world} ranks x {n_steps} optimizer steps x {B} kitti-shaped chunks per rank '
+                        f'(~Poisson({a.train_dets}) dets/frame), batched forward + CE/BCE + backward per rank, one NCCL all-reduce of '
+                        'the flat gradient buffer, Adam',
             'value': tot_edges / dt, 'unit': 'edge-updates/s (forward+backward+allreduce+optimizer, all ranks)',
-            'chunks_per_s': world * n_steps / dt, 'allreduce_floats': int(nfl), 'allreduce_ms_avg_incl_peer_wait': ar_ms / max(1, n_steps),
+            'chunks_per_s': world * n_steps * B / dt, 'allreduce_floats': int(nfl),
+            'allreduce_ms_avg_incl_peer_wait': ar_ms / max(1, n_steps),
             'replicas_in_sync': bool(abs(hi - lo) <= 1e-9 * max(1.0, abs(hi)))}
 
 
