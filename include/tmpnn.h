@@ -275,6 +275,20 @@ int tmpnn_input_bwd(const float *x, int ldx, int col0, int f_in, const int32_t *
                     int n_edge_rows, int training, float *scratch, float *gw1, float *gb1, float *ggamma,
                     float *gbeta, float *gw2, float *gb2, void *stream);
 
+/* The same for several groups of rows in one launch, one CTA per group -- the chunks of the batched trainer, each its own
+ * BatchNorm batch (trackmpnn_b200/train_engine.py).  groups: HOST array of n_groups descriptors (device pointers inside;
+ * they travel in the kernel parameters, 32 per launch); the gradient buffers are shared and added to atomically. */
+typedef struct tmpnn_input_group {
+  const float *a, *mean, *var;      /* Linear1 outputs [n][64] and the batch statistics [64] of this group */
+  const int32_t *x_idx, *out_rows;  /* feature rows / state rows of its n detections */
+  float *scratch;                   /* 2 n 64 floats */
+  int32_t n, n_edge_rows;
+} tmpnn_input_group;
+int tmpnn_input_bwd_groups(const float *x, int ldx, int col0, int f_in, const tmpnn_input_group *groups, int n_groups,
+                           const float *gamma, const float *beta, const float *b1, const float *w2, const float *dh,
+                           int ldh, int col, int training, float *gw1, float *gb1, float *ggamma, float *gbeta,
+                           float *gw2, float *gb2, void *stream);
+
 /* create_targets (models/loss.py:8-44) on a single-slab graph with labels: targets[N] int32. */
 int tmpnn_loss_targets(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, int32_t *targets, void *stream);
 

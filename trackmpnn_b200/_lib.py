@@ -38,6 +38,11 @@ class Graph(C.Structure):
                 ('phys', C.c_void_p), ('psrc', C.c_void_p), ('pdst', C.c_void_p), ('phys_end', C.c_void_p)]
 
 
+class InputGroup(C.Structure):   # tmpnn_input_group
+    _fields_ = [('a', C.c_void_p), ('mean', C.c_void_p), ('var', C.c_void_p), ('x_idx', C.c_void_p), ('out_rows', C.c_void_p),
+                ('scratch', C.c_void_p), ('n', C.c_int32), ('n_edge_rows', C.c_int32)]
+
+
 class Index(C.Structure):
     _fields_ = [('cap_dets', C.c_int32), ('cap_inc', C.c_int32), ('n_dets', C.c_void_p), ('n_edges', C.c_void_p),
                 ('det_rows', C.c_void_p), ('det_of_row', C.c_void_p), ('seq_det_ptr', C.c_void_p),
@@ -92,6 +97,7 @@ _PROTOS = {
     'tmpnn_rows_outer': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP], _I),
     'tmpnn_scatter_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP], _I),
     'tmpnn_input_bwd': ([_VP, _I, _I, _I] + [_VP] * 9 + [_I, _I, _VP, _I, _I, _I] + [_VP] * 8, _I),
+    'tmpnn_input_bwd_groups': ([_VP, _I, _I, _I, C.POINTER(InputGroup), _I] + [_VP] * 5 + [_I, _I, _I] + [_VP] * 7, _I),
     'tmpnn_loss_targets': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP], _I),
     'tmpnn_loss_ce_fwd': ([C.POINTER(Index), _I] + [_VP] * 7, _I),
     'tmpnn_loss_ce_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I] + [_VP] * 6, _I),
@@ -174,7 +180,7 @@ KERNELS_PER_CALL = {
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
     'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
-    'tmpnn_input_bwd': 1, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
+    'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }
 

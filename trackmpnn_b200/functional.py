@@ -441,9 +441,26 @@ class _MPStepFn(torch.autograd.Function):
             # through the gather / segmented sum, into the state this step consumed
             L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx, L.ptr(dagg), L.ptr(dh_cur), ldh, col, st)
             # new detection rows: through the input transform (one group of rows per BatchNorm batch)
-            for xd, new_det, out_rows, nd, n_edge_new, per_group in ctx.saved_in:
-                if nd <= 0:
-                    continue
+            groups_in = [t for t in ctx.saved_in if t[3] > 0]
+            if len(groups_in) > 1:
+                # batched trainer: all chunks in one launch, one CTA per chunk (tmpnn_input_group descriptors)
+                xd = groups_in[0][0]
+                cols = model.feature_idx[g]
+                tot = sum(t[3] for t in groups_in)
+                scratch = torch.empty((2 * tot, H), **f32)
+                desc = (L.InputGroup * len(groups_in))()
+                off = 0
+                for k, (_, x_idx, out_rows, nd, n_edge_new, per_group) in enumerate(groups_in):
+                    a, mean, var, training = per_group[g]
+                    desc[k] = L.InputGroup(a.data_ptr(), mean.data_ptr(), var.data_ptr(), x_idx.data_ptr(), out_rows.data_ptr(),
+                                           scratch.data_ptr() + 4 * H * 2 * off, nd, n_edge_new)
+                    off += nd
+                L.call('tmpnn_input_bwd_groups', L.ptr(xd), int(xd.shape[1]), int(cols[0]), len(cols), desc,
+                       len(groups_in), L.ptr(P[b + 2]), L.ptr(P[b + 3]), L.ptr(P[b + 1]), L.ptr(P[b + 4]), L.ptr(dh_cur), ldh,
+                       col, int(groups_in[0][5][g][3]), L.ptr(grads[b + 0]), L.ptr(grads[b + 1]), L.ptr(grads[b + 2]),
+                       L.ptr(grads[b + 3]), L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), st)
+                groups_in = []
+            for xd, new_det, out_rows, nd, n_edge_new, per_group in groups_in:
                 a, mean, var, training = per_group[g]
                 cols = model.feature_idx[g]
                 scratch = torch.empty((2 * nd, H), **f32)
