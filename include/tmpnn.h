@@ -284,6 +284,12 @@ typedef struct tmpnn_input_group {
   float *scratch;                   /* 2 n 64 floats */
   int32_t n, n_edge_rows;
 } tmpnn_input_group;
+/* Forward counterpart for train-mode BatchNorm: per group the batch statistics of its Linear1 outputs g.a (written to
+ * g.mean / g.var), the running statistics updated group by group in order, then BatchNorm -> ReLU -> Linear2 into
+ * h[g.out_rows][col:col+64].  (Linear1 itself is row-wise: one tmpnn_input_linear1 call over all groups' rows.) */
+int tmpnn_input_bn_groups_fwd(const tmpnn_input_group *groups, int n_groups, const float *b1, const float *gamma,
+                              const float *beta, const float *w2, const float *b2, float *running_mean,
+                              float *running_var, float *h, int ldh, int col, void *stream);
 int tmpnn_input_bwd_groups(const float *x, int ldx, int col0, int f_in, const tmpnn_input_group *groups, int n_groups,
                            const float *gamma, const float *beta, const float *b1, const float *w2, const float *dh,
                            int ldh, int col, int training, float *gw1, float *gb1, float *ggamma, float *gbeta,

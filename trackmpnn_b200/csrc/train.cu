@@ -256,6 +256,8 @@ k_scatter_bwd_dets(const int32_t* __restrict__ n_dets, const int32_t* __restrict
 // ------------------------------------------------------------------------------------------
 // input transform backward (Linear -> BatchNorm -> ReLU -> Linear), one CTA
 // ------------------------------------------------------------------------------------------
+constexpr int GROUPS_PER_LAUNCH = 32;  // descriptors travel by value in the kernel parameters (32 x 56 B)
+struct InputGroupBatch { tmpnn_input_group g[GROUPS_PER_LAUNCH]; };
 // ATOMIC: several CTAs (one per group of rows = one BatchNorm batch) add into the same gradient buffers
 template <bool ATOMIC>
 __device__ __forceinline__ void grad_add(float* p, float v) {
@@ -354,8 +356,6 @@ k_input_bwd(const float* __restrict__ x, int ldx, int col0, int f_in, const int3
                         training, scratch, gw1, gb1, ggamma, gbeta, gw2, gb2);
 }
 // one CTA per group (tmpnn_input_group): the batched trainer's chunks, each its own BatchNorm batch
-constexpr int GROUPS_PER_LAUNCH = 32;  // descriptors travel by value in the kernel parameters (32 x 56 B)
-struct InputGroupBatch { tmpnn_input_group g[GROUPS_PER_LAUNCH]; };
 __global__ void __launch_bounds__(256)
 k_input_bwd_groups(const float* __restrict__ x, int ldx, int col0, int f_in, const InputGroupBatch groups,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ b1,
@@ -561,6 +561,116 @@ extern "C" int tmpnn_input_bwd(const float* x, int ldx, int col0, int f_in, cons
                                                   out_rows, n, n_edge_rows, training, scratch, gw1, gb1, ggamma, gbeta, gw2,
                                                   gb2);
   TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+// ---- forward of the input transform for several groups (BatchNorm batches) in one launch each ----------------
+// batch statistics of every group (same two-pass arithmetic as k_input_bn_stats in mp_step.cu), one CTA per group
+__global__ void __launch_bounds__(256) k_input_bn_stats_groups(const InputGroupBatch groups, const float* __restrict__ b1) {
+  __shared__ double red[4][H];
+  const tmpnn_input_group& g = groups.g[blockIdx.x];
+  const int n = g.n, n_edge = g.n_edge_rows;
+  if (n <= 0) return;
+  const float* a = g.a;
+  const int j = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const double ntot = (double)n + (double)n_edge;
+  double s = 0;
+  for (int r = part; r < n; r += 4) s += a[(size_t)r * H + j];
+  red[part][j] = s;
+  __syncthreads();
+  const double mu = (red[0][j] + red[1][j] + red[2][j] + red[3][j] + (double)n_edge * b1[j]) / ntot;
+  __syncthreads();
+  double q = 0;
+  for (int r = part; r < n; r += 4) {
+    double d = a[(size_t)r * H + j] - mu;
+    q += d * d;
+  }
+  red[part][j] = q;
+  __syncthreads();
+  if (part == 0) {
+    double db = (double)b1[j] - mu;
+    double var = (red[0][j] + red[1][j] + red[2][j] + red[3][j] + (double)n_edge * db * db) / ntot;
+    const_cast<float*>(g.mean)[j] = (float)mu;
+    const_cast<float*>(g.var)[j] = (float)var;
+  }
+}
+// running statistics: the exponential averages depend on the order, so one thread per channel walks the groups in order
+__global__ void k_bn_running_groups(const InputGroupBatch groups, int n_groups, float* __restrict__ rmean,
+                                    float* __restrict__ rvar) {
+  const int j = threadIdx.x;
+  float m = rmean[j], v = rvar[j];
+  for (int k = 0; k < n_groups; ++k) {
+    const tmpnn_input_group& g = groups.g[k];
+    if (g.n <= 0) continue;
+    const double ntot = (double)g.n + (double)g.n_edge_rows;
+    m = 0.9f * m + 0.1f * g.mean[j];
+    v = 0.9f * v + 0.1f * (float)((double)g.var[j] * ntot / (ntot - 1.0));
+  }
+  rmean[j] = m;
+  rvar[j] = v;
+}
+// BatchNorm -> ReLU -> Linear2 of every group with its own statistics, one CTA per group
+__global__ void __launch_bounds__(128)
+k_input_bn_relu_linear2_groups(const InputGroupBatch groups, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h, int ldh,
+                               int col) {
+  __shared__ float w2t[H * H];  // [k][j]
+  __shared__ float act[4][H];
+  const tmpnn_input_group& g = groups.g[blockIdx.x];
+  const int n = g.n;
+  if (n <= 0) return;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    int k = i / H, j = i % H;
+    w2t[i] = w2[j * H + k];
+  }
+  __syncthreads();
+  const float* a = g.a;
+  const float* mean = g.mean;
+  const float* var = g.var;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int r = w; r < n; r += 4) {
+    // (a - mean) / sqrt(var + eps) * gamma + beta, written like torch's batch_norm
+    float v0 = (a[(size_t)r * H + lane] - mean[lane]) * (1.0f / sqrtf(var[lane] + 1e-5f)) * gamma[lane] + beta[lane];
+    float v1 = (a[(size_t)r * H + lane + 32] - mean[lane + 32]) * (1.0f / sqrtf(var[lane + 32] + 1e-5f)) * gamma[lane + 32] + beta[lane + 32];
+    act[w][lane] = fmaxf(v0, 0.f);
+    act[w][lane + 32] = fmaxf(v1, 0.f);
+    __syncwarp();
+    float o0 = b2[lane], o1 = b2[lane + 32];
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+      float av = act[w][k];
+      o0 = fmaf(av, w2t[k * H + lane], o0);
+      o1 = fmaf(av, w2t[k * H + lane + 32], o1);
+    }
+    __syncwarp();
+    float* hr = h + (size_t)g.out_rows[r] * ldh + col;
+    hr[lane] = o0;
+    hr[lane + 32] = o1;
+  }
+}
+
+extern "C" int tmpnn_input_bn_groups_fwd(const tmpnn_input_group* groups, int n_groups, const float* b1, const float* gamma,
+                                         const float* beta, const float* w2, const float* b2, float* running_mean,
+                                         float* running_var, float* h, int ldh, int col, void* stream) {
+  TMPNN_REQUIRE(groups && b1 && gamma && beta && w2 && b2 && h, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g0 = 0; g0 < n_groups; g0 += GROUPS_PER_LAUNCH) {
+    InputGroupBatch batch;
+    const int nb = min(GROUPS_PER_LAUNCH, n_groups - g0);
+    for (int k = 0; k < nb; ++k) {
+      batch.g[k] = groups[g0 + k];
+      TMPNN_REQUIRE(batch.g[k].n <= 0 || batch.g[k].n + batch.g[k].n_edge_rows > 1,
+                    "Expected more than 1 value per channel when training");
+    }
+    k_input_bn_stats_groups<<<nb, 256, 0, st>>>(batch, b1);
+    TMPNN_LAUNCH_CHECK();
+    if (running_mean && running_var) {
+      k_bn_running_groups<<<1, H, 0, st>>>(batch, nb, running_mean, running_var);
+      TMPNN_LAUNCH_CHECK();
+    }
+    k_input_bn_relu_linear2_groups<<<nb, 128, 0, st>>>(batch, gamma, beta, w2, b2, h, ldh, col);
+    TMPNN_LAUNCH_CHECK();
+  }
   return TMPNN_OK;
 }
 

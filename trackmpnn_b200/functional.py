@@ -309,8 +309,8 @@ class NewRowGroups:
     the feature rows, every group ``(x_idx, out_rows, n_dets, n_edge_rows)`` is one chunk's share -- one BatchNorm
     batch, as in the reference, which feeds one chunk per forward."""
 
-    def __init__(self, xd, groups):
-        self.xd, self.groups = xd, groups
+    def __init__(self, xd, groups, x_idx_all=None):
+        self.xd, self.groups, self.x_idx_all = xd, groups, x_idx_all   # x_idx_all: the groups' x_idx concatenated
 
 
 def _input_rows_forward(model, xd, x_idx, out_rows, nd, n_edge_rows, h_cur, ldh):
@@ -322,6 +322,47 @@ def _input_rows_forward(model, xd, x_idx, out_rows, nd, n_edge_rows, h_cur, ldh)
         a, mean, var = input_transform_rows(model, g, xd, x_idx, nd, n_edge_rows, h_cur, ldh, out_rows)
         per_group.append((a, mean.clone(), var.clone(), training))
     return (xd, x_idx, out_rows, nd, n_edge_rows, per_group)
+
+
+def _input_groups_forward(model, x, h_cur, ldh):
+    """K0 for the row groups of a NewRowGroups (one BatchNorm batch each).  Train-mode BatchNorm: Linear1 over all
+    rows at once, then statistics / running averages / BatchNorm-ReLU-Linear2 of all groups in three launches
+    (tmpnn_input_bn_groups_fwd); otherwise group by group.  Returns the per-group tuples tmpnn_input_bwd needs."""
+    groups = [t for t in x.groups if t[2] > 0]
+    G = len(model.feature_idx)
+    if not groups:
+        return []
+    if not all(model.input_transforms[g][1].training for g in range(G)) or len(groups) == 1:
+        return [_input_rows_forward(model, x.xd, xi, orow, nd, ne, h_cur, ldh) for xi, orow, nd, ne in groups]
+    dev = h_cur.device
+    tot = sum(t[2] for t in groups)
+    x_all = torch.cat([t[0] for t in groups]) if x.x_idx_all is None else x.x_idx_all
+    st = L.stream()
+    per = [[] for _ in groups]
+    for g in range(G):
+        seq = model.input_transforms[g]
+        lin1, bn, lin2 = seq[0], seq[1], seq[3]
+        cols = model.feature_idx[g]
+        assert bn.momentum == 0.1 and bn.eps == 1e-5, 'kernels assume BatchNorm1d defaults'
+        a = torch.empty((tot, H), dtype=torch.float32, device=dev)
+        L.call('tmpnn_input_linear1', L.ptr(x.xd), int(x.xd.shape[1]), int(cols[0]), len(cols), L.ptr(x_all),
+               L.ptr(lin1.weight.detach()), L.ptr(lin1.bias.detach()), L.ptr(a), None, int(tot), st)
+        stats = torch.empty((len(groups), 2, H), dtype=torch.float32, device=dev)
+        desc = (L.InputGroup * len(groups))()
+        off = 0
+        for k, (xi, orow, nd, ne) in enumerate(groups):
+            if nd + ne <= 1:
+                raise ValueError('Expected more than 1 value per channel when training, got input size '
+                                 f'torch.Size([{nd + ne}, {H}])')
+            desc[k] = L.InputGroup(a.data_ptr() + 4 * H * off, stats[k, 0].data_ptr(), stats[k, 1].data_ptr(), xi.data_ptr(),
+                                   orow.data_ptr(), None, nd, ne)
+            per[k].append((a[off:off + nd], stats[k, 0], stats[k, 1], True))
+            off += nd
+        L.call('tmpnn_input_bn_groups_fwd', desc, len(groups), L.ptr(lin1.bias.detach()), L.ptr(bn.weight.detach()),
+               L.ptr(bn.bias.detach()), L.ptr(lin2.weight.detach()), L.ptr(lin2.bias.detach()), L.ptr(bn.running_mean),
+               L.ptr(bn.running_var), L.ptr(h_cur), int(ldh), g * H, st)
+        bn.num_batches_tracked += len(groups)
+    return [(x.xd, xi, orow, nd, ne, per[k]) for k, (xi, orow, nd, ne) in enumerate(groups)]
 
 
 class _MPStepFn(torch.autograd.Function):
@@ -347,9 +388,7 @@ class _MPStepFn(torch.autograd.Function):
                 raise ValueError('with NewRowGroups h_in must have one row per graph row')
             n_old, n_new = n_tot, 0
             h_cur = h_in.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
-            for x_idx, out_rows, nd, n_edge in x.groups:
-                if nd > 0:
-                    saved_in.append(_input_rows_forward(model, x.xd, x_idx, out_rows, nd, n_edge, h_cur, ldh))
+            saved_in = _input_groups_forward(model, x, h_cur, ldh)
         else:
             n_new = int(x.size()[0])
             n_old = n_tot - n_new
@@ -383,7 +422,9 @@ class _MPStepFn(torch.autograd.Function):
         ctx.model, ctx.wg, ctx.ix = model, wg, ix
         ctx.n_old, ctx.has_h_in = n_old, h_in is not None
         ctx.saved_in, ctx.gates, ctx.aggs = saved_in, gates, aggs
-        ctx.h_cur, ctx.h_out, ctx.p = h_cur, h_out, scores
+        # outputs are kept as detached aliases: an attribute holding an output tensor itself would close a reference
+        # cycle (ctx -> output -> grad_fn -> ctx) that only the cycle collector frees -- GBs per batched step
+        ctx.h_cur, ctx.h_out, ctx.p = h_cur, h_out.detach(), scores.detach()
         ctx.param_vals = [p.detach() for p in params]
         return scores, logits, h_out
 

@@ -108,7 +108,7 @@ class TrainBatch:
             xs.append(d['x_new'])
             xo += nd
         xd = torch.cat(xs).contiguous() if xo else torch.zeros((1, per_chunk[act[0]][i]['x_new'].shape[1]), device=dev)
-        st.new_rows = NewRowGroups(xd, groups)
+        st.new_rows = NewRowGroups(xd, groups, torch.arange(max(1, xo), dtype=_I32, device=dev))
         # rows carried over from the previous step's layout
         if prev is not None:
             src_idx, dst_idx = [], []
