@@ -75,3 +75,36 @@ def test_batch_equals_sum_of_chunks(msg_type):
     # BatchNorm saw one batch per chunk and step in both runs
     for bm, br in zip(model.input_transforms, ref.input_transforms):
         assert int(bm[1].num_batches_tracked) == int(br[1].num_batches_tracked)
+
+
+def test_training_steps_do_not_accumulate_device_memory():
+    """The autograd step must not keep its graph alive after backward (a ctx attribute holding an output tensor closes
+    a reference cycle that only the cycle collector frees: GBs per batched step)."""
+    import gc
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    chunks = []
+    for i in range(4):
+        ts = synth.train_chunk_timestamps(60 + i, 5, 2)
+        Xn, yn = synth.make_sequence(60 + i, None, 12, 'kitti', timestamps=ts)
+        chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
+    batch = TrainBatch(chunks, dev)
+    gc.collect()
+    gc.disable()
+    try:
+        used = []
+        for _ in range(4):
+            opt.zero_grad()
+            loss = batch_loss(model, batch)
+            loss.backward()
+            opt.step()
+            del loss
+            torch.cuda.synchronize()
+            used.append(torch.cuda.memory_allocated())
+        assert used[-1] <= used[1] + (1 << 20), used   # steady after the optimizer state exists
+    finally:
+        gc.enable()
