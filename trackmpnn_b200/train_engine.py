@@ -24,7 +24,6 @@ from . import _lib as L
 from .device_graph import WindowGraph
 from .functional import H, NewRowGroups, _MPStepFn, _param_list
 from .models.loss import CELoss, create_targets
-from .utils.graph import initialize_graph, update_graph
 
 _I32 = torch.int32
 
@@ -39,48 +38,61 @@ class TrainBatch:
         dev = device if device is not None else chunks[0][0].device
         if dev.type != 'cuda':
             raise L.TmpnnError('TrainBatch needs a CUDA device; there is no CPU path')
-        per_chunk = [self._chunk_graphs(X.to(dev), y.to(dev)) for X, y in chunks]
-        per_chunk = [c for c in per_chunk if c]
+        built = [self._chunk_graphs(X.to(dev), y.to(dev)) for X, y in chunks]
+        built = [c for c in built if c is not None]
+        graphs = [c[0] for c in built]
+        per_chunk = [c[1] for c in built]
         self.device, self.num_chunks = dev, len(per_chunk)
         self.steps = []
         n_steps = max(len(c) for c in per_chunk) if per_chunk else 0
         prev = None
         for i in range(n_steps):
-            st = self._concat(i, per_chunk, prev, dev)
+            st = self._concat(i, per_chunk, graphs, prev, dev)
             self.steps.append(st)
             prev = st
         self.edge_rows = sum(int(s.n_edge_rows) for s in self.steps)
 
-    # ---- one chunk: its window graph at every step (drop-in graph functions, labels only) ----------------
+    # ---- one chunk: its window graph at every step (labels only) --------------------------------------------------
     @staticmethod
     def _chunk_graphs(X, y):
-        y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, 0, 'train', True)
-        if y_pred is None:
-            return []
-        out = []
+        """The training loop's graph bookkeeping for one chunk (``train.py:65,92-104``: ``initialize_graph`` then
+        ``update_graph(mode='train')`` for every integer timestep), on ONE growing single-slab graph: training never
+        deletes rows, so the graph of step i is the first ``n_i`` rows of the final one.  Returns ``(graph, steps)``
+        or None when the reference would skip the chunk (``utils/graph.py:132-133``)."""
+        from .utils.graph import _append, _associate, _frames_of, _seq_state
+        dev = X.device
+        if bool((y[0, :, 1] == -1).all()):
+            return None
+        ft = _frames_of(y, dev)
+        fp = ft.host_frame_ptr[0]
+        counts = np.diff(fp[:ft.t_max + 2]).astype(np.int64)
+        nz = [t for t in range(len(counts)) if counts[t] > 0]
+        if len(nz) < 2:
+            return None
+        # every detection can at most be connected to every later one
+        cap = int(counts.sum() + sum(int(counts[:t].sum()) * int(counts[t]) for t in range(len(counts))))
+        wg = WindowGraph(0, cap, dev, with_labels=True)
+        st_t, st_c = _seq_state(dev)
+        Xd = X[0].to(torch.float32)
+        steps = []
 
-        def snap(node_adj, feats, n_old):
-            wg = node_adj._tmpnn
-            n = wg.n
-            g = wg.g
-            ts = g.ts[:n].clone()
-            new_det = torch.nonzero(ts[n_old:] >= 0)[:, 0]
-            out.append(dict(n=n, n_old=n_old, ts=ts, det=g.det[:n].clone(), src=g.src[:n].clone(), dst=g.dst[:n].clone(),
-                            label=g.label[:n].clone(), new_det=(new_det + n_old).to(_I32),
-                            x_new=feats[new_det].to(torch.float32), n_new_edges=(n - n_old) - int(new_det.numel())))
+        def snap(n_old, new_rows, new_x):
+            steps.append(dict(n=wg.n, n_old=n_old, new_det=new_rows.clone(), x_new=Xd[new_x.long()],
+                              n_new_edges=(wg.n - n_old) - int(new_rows.numel())))
 
-        snap(node_adj, feats, 0)
+        new_rows, new_x = _append(wg, ft, st_c, 0, 1, 0, int(counts[nz[0]] + counts[nz[1]]))
+        t_st, t_end = int(st_t['skip_until'].item()), int(st_t['t_end'].item())
+        snap(0, new_rows, new_x)
         for t in range(t_st, t_end):
-            n_old = int(y_pred.shape[0])
-            dummy = torch.zeros((n_old, 2), dtype=torch.float32, device=X.device)   # train mode never reads the scores
-            y_pred, feats, node_adj, edge_adj, labels = update_graph(node_adj, labels, dummy, y_pred, X, y, t,
-                                                                     use_hungraian=False, mode='train', cuda=True)
-            snap(node_adj, feats, n_old)
-        return out
+            n_old = wg.n
+            _associate(wg, None, False, 'train')          # teacher forcing from the labels (utils/graph.py:229-245)
+            new_rows, new_x = _append(wg, ft, None, t, 0, 1, ft.count(0, t))
+            snap(n_old, new_rows, new_x)
+        return wg, steps
 
     # ---- one step: block-diagonal concatenation of the active chunks' graphs ----------------------------------
     @staticmethod
-    def _concat(i, per_chunk, prev, dev):
+    def _concat(i, per_chunk, graphs, prev, dev):
         act = [c for c in range(len(per_chunk)) if len(per_chunk[c]) > i]
         st = _Step()
         st.chunks = act
@@ -90,9 +102,9 @@ class TrainBatch:
             off += per_chunk[c][i]['n']
         n = off
         st.n, st.base = n, base
-        cat = lambda key: torch.cat([per_chunk[c][i][key] for c in act])
-        shift = lambda key: torch.cat([torch.where(per_chunk[c][i][key] >= 0, per_chunk[c][i][key] + base[c],
-                                                   per_chunk[c][i][key]) for c in act])
+        col = lambda c, key: getattr(graphs[c].g, key)[:per_chunk[c][i]['n']]   # step i = a prefix of the final graph
+        cat = lambda key: torch.cat([col(c, key) for c in act])
+        shift = lambda key: torch.cat([torch.where(col(c, key) >= 0, col(c, key) + base[c], col(c, key)) for c in act])
         wg = WindowGraph(n, n, dev, with_labels=True)
         g = wg.g
         g.ts[:n] = cat('ts'); g.det[:n] = cat('det'); g.ass[:n] = -1
