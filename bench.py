@@ -220,8 +220,9 @@ def run_train_batched(a, dev, model, opt, chunk, steps=9):
     """The same training step for B chunks at once (trackmpnn_b200/train_engine.py): per message-passing step ONE
     block-diagonal graph, so every kernel runs once for the whole batch; BatchNorm statistics and the BCE means stay
     per chunk, the batch loss is the sum of the chunk losses (verified against the chunk-by-chunk path in
-    tests/test_train_engine_gpu.py).  The graphs depend on the labels only and are built once, outside the timed
-    steps (reported separately)."""
+    tests/test_train_engine_gpu.py).  The graphs depend on the labels only (teacher forcing), so a batch is built once
+    and replayed; `value` times the optimizer steps, `value_incl_graph_build` charges a full rebuild of the batch's
+    graphs to every step, which is what the reference's loop does (train.py:92-104)."""
     import torch
     from trackmpnn_b200.train_engine import TrainBatch, batch_loss
     B = a.train_batch
@@ -229,6 +230,7 @@ def run_train_batched(a, dev, model, opt, chunk, steps=9):
     for i in range(B):
         Xn, yn = chunk(3000 + i)
         chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
+    TrainBatch(chunks, dev)   # untimed: first use of the graph kernels (module load, allocator warm-up)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     batch = TrainBatch(chunks, dev)
@@ -257,7 +259,8 @@ def run_train_batched(a, dev, model, opt, chunk, steps=9):
     return {'chunks_per_batch': B, 'message_passing_steps': len(batch.steps), 'edge_rows_per_batch': int(batch.edge_rows),
             'value': batch.edge_rows / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': B / dt,
             'ms_per_batch': 1e3 * dt, 'ms_per_batch_mean': 1e3 * float(np.mean(times)), 'graph_build_ms_per_chunk': 1e3 * t_build / B, 'loss': lv,
-            'value_incl_graph_build': batch.edge_rows / (dt + t_build)}
+            'value_incl_graph_build': batch.edge_rows / (dt + t_build), 'chunks_per_s_incl_graph_build': B / (dt + t_build),
+            'graph_builder': batch.builder}
 
 
 def run_train_leg(a, dev):

@@ -39,8 +39,9 @@ def _chunk_loss_dropin(model, X, y, tp=True):
     return loss
 
 
+@pytest.mark.parametrize('builder', ['slab', 'chunk'])
 @pytest.mark.parametrize('msg_type', ['diff', 'concat'])
-def test_batch_equals_sum_of_chunks(msg_type):
+def test_batch_equals_sum_of_chunks(msg_type, builder):
     features = '2d'
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     from trackmpnn_b200.train_engine import TrainBatch, batch_loss
@@ -63,7 +64,8 @@ def test_batch_equals_sum_of_chunks(msg_type):
         l = _chunk_loss_dropin(ref, X, y)
         l.backward()                      # gradients accumulate over the chunks
         tot += float(l)
-    batch = TrainBatch(chunks, dev)
+    batch = TrainBatch(chunks, dev, builder=builder)
+    assert batch.builder == builder
     assert batch.num_chunks == len(chunks) and len(batch.steps) >= 7
     loss = batch_loss(model, batch)
     loss.backward()

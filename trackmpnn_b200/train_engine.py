@@ -33,15 +33,22 @@ class _Step:
 
 
 class TrainBatch:
-    def __init__(self, chunks, device=None):
-        """chunks: list of ``(X [1, ND, F], y [1, ND, 2])`` tensors (``y`` = [timestamp, track id])."""
+    def __init__(self, chunks, device=None, builder='slab'):
+        """chunks: list of ``(X [1, ND, F], y [1, ND, 2])`` tensors (``y`` = [timestamp, track id]).  builder 'slab':
+        all chunks' graphs grow in lock step in one multi-slab graph (one host read-back of the row counts per step);
+        'chunk': one chunk at a time (also the fallback when the chunks do not start tracking at the same timestep)."""
         dev = device if device is not None else chunks[0][0].device
         if dev.type != 'cuda':
             raise L.TmpnnError('TrainBatch needs a CUDA device; there is no CPU path')
-        built = [self._chunk_graphs(X.to(dev), y.to(dev)) for X, y in chunks]
-        built = [c for c in built if c is not None]
-        graphs = [c[0] for c in built]
-        per_chunk = [c[1] for c in built]
+        fast = self._build_slabs(chunks, dev) if builder == 'slab' else None
+        if fast is not None:
+            graphs, per_chunk = fast
+        else:
+            built = [self._chunk_graphs(X.to(dev), y.to(dev)) for X, y in chunks]
+            built = [c for c in built if c is not None]
+            graphs = [c[0] for c in built]
+            per_chunk = [c[1] for c in built]
+        self.builder = 'slab' if fast is not None else 'chunk'
         self.device, self.num_chunks = dev, len(per_chunk)
         self.steps = []
         n_steps = max(len(c) for c in per_chunk) if per_chunk else 0
@@ -51,6 +58,84 @@ class TrainBatch:
             self.steps.append(st)
             prev = st
         self.edge_rows = sum(int(s.n_edge_rows) for s in self.steps)
+
+    # ---- all chunks in lock step: slabs of one device graph ---------------------------------------------------------
+    @staticmethod
+    def _build_slabs(chunks, dev):
+        """The bookkeeping of ``_chunk_graphs`` for all chunks at once with the batched engine's kernels (train mode:
+        teacher-forced association, active set of ``utils/graph.py:271-275``): chunk c owns slab c, every step is one
+        index build + associate + append for all slabs and ONE read-back of the row counts.  Returns
+        ``(per-chunk graph views, per-chunk step records)`` or None when a chunk cannot be tracked / the chunks do not
+        share the first tracked timestep."""
+        import ctypes as C
+        from .device_graph import FrameTable, SlabGraph, SlabIndex
+        B = len(chunks)
+        ys = [y[0].detach().cpu().numpy() for _, y in chunks]
+        xs = [X[0].detach().cpu().numpy().astype(np.float32) for X, _ in chunks]
+        if any((y[:, 1] == -1).all() for y in ys):
+            return None
+        ft = FrameTable(ys, dev, xs)
+        fp = ft.host_frame_ptr
+        counts = (fp[:, 1:] - fp[:, :-1]).astype(np.int64)               # [B, t_max + 1]
+        if any((counts[c] > 0).sum() < 2 for c in range(B)):
+            return None
+        cap = max(int(counts[c].sum() + sum(int(counts[c, :t].sum()) * int(counts[c, t]) for t in range(counts.shape[1])))
+                  for c in range(B))
+        cap = (cap + 63) // 64 * 64
+        g = SlabGraph(B, cap, dev, with_labels=True)
+        max_dets = int(counts.sum(1).max())
+        index = SlabIndex(g, cap_dets=B * max_dets, cap_inc=2 * B * cap)
+        z = lambda n: torch.zeros(n, dtype=_I32, device=dev)
+        st = {k: z(B) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')}
+        st_c = L.SeqState(*[L.ptr(st[k]) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')])
+        cap_new = 2 * B * int(counts.max())
+        new_rows, new_x, n_new, n_app = z(cap_new), z(cap_new), z(2), z(B)
+        scratch = z(int(L.lib().tmpnn_graph_append_scratch_ints(B, cap)))
+        t_dev = z(1)
+        per_chunk = [[] for _ in range(B)]
+        n_prev = np.zeros(B, dtype=np.int64)
+
+        def append(start, mode):
+            L.call('tmpnn_graph_append', g.c, ft.c, C.byref(st_c), L.ptr(t_dev), int(start), 0, int(mode), None, 0,
+                   L.ptr(new_rows), L.ptr(new_x), L.ptr(n_new), cap_new, L.ptr(n_app), L.ptr(scratch), L.stream())
+            # the one host read-back of the step: row counts, who stepped, how many detections are new
+            host = torch.cat((g.n_rows, st['active'], n_new, g.status)).cpu().numpy()
+            if host[-1]:
+                g.check_status()
+            n_rows, active, nn = host[:B].astype(np.int64), host[B:2 * B], int(host[2 * B])
+            rows = new_rows[:nn].long()
+            order = torch.argsort(rows)                                   # slab-major, ascending rows inside a slab
+            rows, xrow = rows[order], new_x[:nn].long()[order]
+            per = torch.bincount(rows // cap, minlength=B).cpu().numpy()
+            off = 0
+            for c in range(B):
+                k = int(per[c])
+                if active[c]:
+                    per_chunk[c].append(dict(n=int(n_rows[c]), n_old=int(n_prev[c]), new_det=(rows[off:off + k] - c * cap).to(_I32),
+                                             x_new=ft.x[xrow[off:off + k]],
+                                             n_new_edges=int(n_rows[c] - n_prev[c]) - k))
+                    n_prev[c] = n_rows[c]
+                off += k
+
+        append(1, 0)
+        t_first = st['skip_until'].cpu().numpy()
+        t_last = st['t_end'].cpu().numpy()
+        if len(set(int(t) for t in t_first)) != 1:
+            return None
+        for t in range(int(t_first[0]), int(t_last.max())):
+            t_dev.fill_(t)
+            # who is active at t is decided inside the append; the association needs the mask of the sequences still
+            # running: t < t_end (a finished chunk keeps its graph)
+            running = (st['t_end'] > t).to(_I32)
+            index.build(g, running, structured=False)
+            L.call('tmpnn_graph_associate', g.c, index.c, 1, L.ptr(running), L.stream())
+            append(0, 1)
+
+        class _View:   # chunk c's columns of the slab arrays: what _concat reads
+            def __init__(self, c):
+                self.g = types.SimpleNamespace(**{k: getattr(g, k)[c * cap:(c + 1) * cap] for k in ('ts', 'det', 'src', 'dst', 'label')})
+
+        return [_View(c) for c in range(B)], per_chunk
 
     # ---- one chunk: its window graph at every step (labels only) --------------------------------------------------
     @staticmethod
@@ -104,7 +189,10 @@ class TrainBatch:
         st.n, st.base = n, base
         col = lambda c, key: getattr(graphs[c].g, key)[:per_chunk[c][i]['n']]   # step i = a prefix of the final graph
         cat = lambda key: torch.cat([col(c, key) for c in act])
-        shift = lambda key: torch.cat([torch.where(col(c, key) >= 0, col(c, key) + base[c], col(c, key)) for c in act])
+        ns = torch.tensor([per_chunk[c][i]['n'] for c in act], dtype=torch.int64, device=dev)
+        chunk_of_row = torch.repeat_interleave(torch.arange(len(act), device=dev), ns)
+        base_of_row = torch.tensor([base[c] for c in act], dtype=_I32, device=dev)[chunk_of_row]
+        shift = lambda key: (lambda v: torch.where(v >= 0, v + base_of_row, v))(cat(key))
         wg = WindowGraph(n, n, dev, with_labels=True)
         g = wg.g
         g.ts[:n] = cat('ts'); g.det[:n] = cat('det'); g.ass[:n] = -1
@@ -136,16 +224,14 @@ class TrainBatch:
         st.idx_node = torch.nonzero(is_det)[:, 0]
         st.idx_edge = torch.nonzero(~is_det)[:, 0]
         st.targets = create_targets(labels, st.holder, st.idx_node)
-        w = torch.zeros(n, dtype=torch.float32, device=dev)
-        for c in act:
-            d = per_chunk[c][i]
-            rows = slice(base[c], base[c] + d['n'])
-            det_c = is_det[rows]
-            nd_c, ne_c = int(det_c.sum()), d['n'] - int(det_c.sum())
-            wc = torch.where(det_c, torch.full((), 1.0 / max(1, nd_c), device=dev), torch.full((), 1.0 / max(1, ne_c), device=dev))
-            w[rows] = wc
+        # detections per chunk are known on the host (the new-detection counts add up): no read-back
+        nd_c = np.array([sum(int(per_chunk[c][k]['new_det'].numel()) for k in range(i + 1)) for c in act], dtype=np.float64)
+        ne_c = np.array([per_chunk[c][i]['n'] for c in act], dtype=np.float64) - nd_c
+        wd = torch.from_numpy(1.0 / np.maximum(nd_c, 1)).to(device=dev, dtype=torch.float32)[chunk_of_row]
+        we = torch.from_numpy(1.0 / np.maximum(ne_c, 1)).to(device=dev, dtype=torch.float32)[chunk_of_row]
+        w = torch.where(is_det, wd, we)
         st.bce_w = w
-        st.n_edge_rows = int(st.idx_edge.numel())
+        st.n_edge_rows = int(ne_c.sum())
         return st
 
 
