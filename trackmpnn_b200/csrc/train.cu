@@ -95,27 +95,31 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
 // C[rc(i)][0:N] (+)= A[ra(i)][0:K] . W[K][N]      rows i < R with mask[ra(i)] >= 0
 // ------------------------------------------------------------------------------------------
 constexpr int GK = 192;
+// Register tiled: 32 rows per pass, thread (tr, tn) owns rows 2 tr, 2 tr + 1 and N / 16 consecutive columns; per k it
+// reads 2 staged A values (warp-uniform per row pair) and one 128-bit slice of W (L1 resident) for 2 N / 16 FMAs
+// (the first version: one column per thread, 4 shared loads + 1 global load per 4 FMAs).
 template <int N>
 __global__ void __launch_bounds__(256)
 k_rows_times_w(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __restrict__ a_rows,
                const int32_t* __restrict__ c_rows, const int32_t* __restrict__ mask, const float* __restrict__ A,
                const float* __restrict__ W, float* __restrict__ C, int ldc, int accumulate) {
-  constexpr int RPB = 16;           // rows per block pass
-  constexpr int RPT = RPB * N / 256;  // rows per thread (N = 64 -> 4, N = 128 -> 8)
-  __shared__ float As[RPB][GK];
+  constexpr int RPB = 32;     // rows per block pass
+  constexpr int RT = 2;       // rows per thread
+  constexpr int TN = N / 16;  // 4 or 8 consecutive columns per thread
+  __shared__ __align__(16) float As[RPB][GK + 4];
   __shared__ int32_t rc_s[RPB];
   const int R = r_dev ? *r_dev : r_host;
-  const int nn = threadIdx.x % N, rg = threadIdx.x / N;  // rg < 256 / N
+  const int tn = threadIdx.x & 15, tr = threadIdx.x >> 4;
   for (int i0 = blockIdx.x * RPB; i0 < R; i0 += gridDim.x * RPB) {
     __syncthreads();
-    for (int q = threadIdx.x; q < RPB * GK; q += 256) {
-      const int ri = q / GK, k = q % GK, i = i0 + ri;
-      float v = 0.f;
+    for (int q = threadIdx.x; q < RPB * GK / 4; q += 256) {
+      const int ri = q / (GK / 4), k4 = q % (GK / 4), i = i0 + ri;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < R) {
         const int ra = a_rows ? a_rows[i] : i;
-        if (!mask || mask[ra] >= 0) v = A[(size_t)ra * GK + k];
+        if (!mask || mask[ra] >= 0) v = ldg4(A + (size_t)ra * GK + 4 * k4);
       }
-      As[ri][k] = v;
+      *reinterpret_cast<float4*>(&As[ri][4 * k4]) = v;
     }
     if (threadIdx.x < RPB) {
       const int i = i0 + threadIdx.x;
@@ -127,20 +131,37 @@ k_rows_times_w(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
       rc_s[threadIdx.x] = rc;
     }
     __syncthreads();
-    float acc[RPT];
+    float acc[RT][TN];
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) acc[q] = 0.f;
+    for (int u = 0; u < RT; ++u)
+#pragma unroll
+      for (int v = 0; v < TN; ++v) acc[u][v] = 0.f;
+#pragma unroll 8
     for (int k = 0; k < GK; ++k) {
-      const float w = __ldg(W + (size_t)k * N + nn);
+      float wv[TN];
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) acc[q] = fmaf(As[rg * RPT + q][k], w, acc[q]);
+      for (int v = 0; v < TN / 4; ++v) *reinterpret_cast<float4*>(&wv[4 * v]) = ldg4(W + (size_t)k * N + TN * tn + 4 * v);
+#pragma unroll
+      for (int u = 0; u < RT; ++u) {
+        const float a = As[RT * tr + u][k];
+#pragma unroll
+        for (int v = 0; v < TN; ++v) acc[u][v] = fmaf(a, wv[v], acc[u][v]);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      const int rc = rc_s[rg * RPT + q];
+    for (int u = 0; u < RT; ++u) {
+      const int rc = rc_s[RT * tr + u];
       if (rc >= 0) {
-        float* c = C + (size_t)rc * ldc + nn;
-        *c = accumulate ? *c + acc[q] : acc[q];
+        float4* c = reinterpret_cast<float4*>(C + (size_t)rc * ldc + TN * tn);
+#pragma unroll
+        for (int v = 0; v < TN / 4; ++v) {
+          float4 o = make_float4(acc[u][4 * v], acc[u][4 * v + 1], acc[u][4 * v + 2], acc[u][4 * v + 3]);
+          if (accumulate) {
+            const float4 p = c[v];
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          c[v] = o;
+        }
       }
     }
   }
@@ -508,9 +529,10 @@ extern "C" int tmpnn_rows_times_w(const int32_t* r_dev, int r_host, const int32_
                                   const int32_t* mask, const float* A, const float* W, int n, float* C, int ldc,
                                   int accumulate, void* stream) {
   TMPNN_REQUIRE(A && W && C && (n == 64 || n == 128), "bad argument");
-  const int r_max = r_dev ? TMPNN_SM_COUNT * 16 * 4 : r_host;
+  TMPNN_REQUIRE(ldc % 4 == 0 && ((uintptr_t)C & 15) == 0, "C rows must be 16-byte aligned");
+  const int r_max = r_dev ? TMPNN_SM_COUNT * 32 * 4 : r_host;
   if (r_max <= 0) return TMPNN_OK;
-  const int blocks = min(tmpnn_div_up(r_max, 16), TMPNN_SM_COUNT * 4);
+  const int blocks = min(tmpnn_div_up(r_max, 32), TMPNN_SM_COUNT * 4);
   if (n == 64)
     k_rows_times_w<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(r_dev, r_host, a_rows, c_rows, mask, A, W, C, ldc, accumulate);
   else
