@@ -310,6 +310,15 @@ int tmpnn_loss_ce_bwd(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, c
 int tmpnn_loss_focal_fwd(int n, const float *p, const int64_t *targets, float *per_elem, float *loss, void *stream);
 int tmpnn_loss_focal_bwd(int n, const float *p, const int64_t *targets, const float *grad_out, float *dp, void *stream);
 
+/* ---- feature construction: the step in front of the path (dataset/kitti_mot.py:545-566) ---- */
+
+/* x[i] = ([one-hot(cat_id - 1, ncat) | score, xc, yc, w, h (use_2d) | sin, cos(pi (frame mod fr_range) / fr_range)
+ * (use_temp)] - mean) / std for the n_dets detection records bbox_pred[i][16] =
+ * (frame, track, cat_id, alpha, x1, y1, x2, y2, h, w, l, x, y, z, rotation_y, score); the visual block of the
+ * reference ('vis' features, the embedding CNN) is out of scope. */
+int tmpnn_build_features(const float *bbox_pred, int n_dets, int ncat, int use_2d, int use_temp, int fr_range,
+                         const float *mean, const float *std, float *x, int ldx, void *stream);
+
 /* ---- graph bookkeeping (utils/graph.py) ------------------------------------------------ */
 
 /* y_pred[N,3] int64 <-> ts/det/ass, scores[N,2] -> p, labels int64 -> int32 for ONE slab. */

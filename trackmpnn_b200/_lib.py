@@ -99,6 +99,7 @@ _PROTOS = {
     'tmpnn_input_bwd': ([_VP, _I, _I, _I] + [_VP] * 9 + [_I, _I, _VP, _I, _I, _I] + [_VP] * 8, _I),
     'tmpnn_input_bn_groups_fwd': ([C.POINTER(InputGroup), _I] + [_VP] * 8 + [_I, _I, _VP], _I),
     'tmpnn_input_bwd_groups': ([_VP, _I, _I, _I, C.POINTER(InputGroup), _I] + [_VP] * 5 + [_I, _I, _I] + [_VP] * 7, _I),
+    'tmpnn_build_features': ([_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _VP], _I),
     'tmpnn_loss_targets': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP], _I),
     'tmpnn_loss_ce_fwd': ([C.POINTER(Index), _I] + [_VP] * 7, _I),
     'tmpnn_loss_ce_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I] + [_VP] * 6, _I),
@@ -181,7 +182,7 @@ KERNELS_PER_CALL = {
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
     'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
-    'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
+    'tmpnn_build_features': 1, 'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }
 
