@@ -14,7 +14,12 @@ update_graph -> TrackMPNN.forward -> decode_tracks (reference infer.py:48-87).
 metric: edge_updates_per_s = sum over forward calls of the edge rows in the graph / time
 (SURVEY.md section 8d); frames_per_s is reported beside it.  `value` is measured with the
 inputs resident in HBM; `e2e` re-uploads the detections from pinned host memory and reads
-the decoded tracks back every step.  See DESIGN.md "Measurement".
+the decoded tracks back every step.  `roofline` / `roofline_aggregation` / `roofline_compaction` time the fused edge
+step, the detection aggregation and the window slide launch by launch with CUDA events.  Side legs (N = 1): `c1`
+(configs[0]: one KITTI-shaped sequence through the drop-in loop and the S = 1 engine), `train` (configs[1]: training
+chunks through the drop-in modules, and 32 at a time through the batched trainer), `cpu_baseline` (oracle port);
+N > 1 adds `train_ddp` (configs[4]: data-parallel batched training, one NCCL gradient all-reduce per step).
+configs[3] (stress graph) is the same program with --win 20 --dets 180 --seqs-per-gpu 4.  See DESIGN.md "Measurement".
 """
 import argparse
 import json
