@@ -32,6 +32,25 @@ def parse_kitti_detections(lines_by_frame, cat):
     return np.asarray(rows, dtype=np.float32).reshape(-1, 16)
 
 
+def parse_bdd100k_detections(lines_by_frame, cat):
+    """``load_detections`` of the BDD100K loader (``dataset/bdd100k_mot.py:295-350``): same row layout, category ids of
+    its ``class_dict``; types outside ``self.cats`` (``:83-86``), distractor types and scores <= 0.8 dropped."""
+    class_dict = {'pedestrian': 1, 'rider': 2, 'car': 3, 'bus': 4, 'truck': 5, 'train': 6, 'motorcycle': 7, 'bicycle': 8}
+    distractors = {'other person': 9, 'trailer': 9, 'other vehicle': 9, 'crowd': -1}
+    cat_ids = {**class_dict, **distractors}
+    cats = (list(class_dict) if cat == 'All' else [cat]) + list(distractors)
+    rows = []
+    for fr in sorted(lines_by_frame):
+        for line in lines_by_frame[fr]:
+            tmp = line.split(',')
+            cid, score = cat_ids[tmp[0]], float(tmp[5])
+            if tmp[0] not in cats or tmp[0] in distractors or score <= 0.8:
+                continue
+            rows.append([fr, -1, cid, -10, float(tmp[1]), float(tmp[2]), float(tmp[3]), float(tmp[4]), -1, -1, -1,
+                         -1000, -1000, -1000, -10, score])
+    return np.asarray(rows, dtype=np.float32).reshape(-1, 16)
+
+
 def norm_constants(dataset, detections, feats, ncat):
     """Hard-coded mean / std rows (``dataset/kitti_mot.py:155-177``, ``dataset/bdd100k_mot.py:154-176``)."""
     two_d = {('kitti', 'centertrack'): ([0.78, 544.57, 171.58, 71.54, 61.50], [0.14, 285.65, 13.94, 69.92, 47.39]),

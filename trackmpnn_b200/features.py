@@ -1,7 +1,7 @@
 """Detection ingest and feature construction: the step in front of the hot path.
 
-``load_kitti_detections`` reads the per-frame detection text files the reference's loader reads
-(``dataset/kitti_mot.py:311-365``; host I/O), ``build_features`` turns the detection records into the normalised
+``load_kitti_detections`` / ``load_bdd100k_detections`` read the per-frame detection text files the reference's loaders
+read (``dataset/kitti_mot.py:311-365``, ``dataset/bdd100k_mot.py:295-350``; host I/O), ``build_features`` turns the detection records into the normalised
 feature matrix ``X`` the tracker consumes (``dataset/kitti_mot.py:545-566``, ``dataset/bdd100k_mot.py:530-551``) with one
 CUDA kernel (``tmpnn_build_features``).  The 'vis' block (the embedding CNN) is out of scope.
 """
@@ -50,6 +50,43 @@ def load_kitti_detections(detections_path, seq, frames, cat='All'):
         with open(os.path.join(detections_path, seq, '%.4d.txt' % (fr,))) as f:
             lines[fr] = f.readlines()
     b = torch.from_numpy(parse_kitti_detection_lines(lines, cat))
+    return b.pin_memory() if torch.cuda.is_available() and b.numel() else b
+
+
+_BDD_CLASSES = {'pedestrian': 1, 'rider': 2, 'car': 3, 'bus': 4, 'truck': 5, 'train': 6, 'motorcycle': 7, 'bicycle': 8}
+_BDD_DISTRACTORS = ('other person', 'trailer', 'other vehicle', 'crowd')
+BDD_SCORE_FLOOR = 0.8  # detections with score <= 0.8 never reach the tracker (dataset/bdd100k_mot.py:340-341)
+
+
+def parse_bdd100k_detection_lines(lines_by_frame, cat='All'):
+    """{frame: iterable of ``type,x1,y1,x2,y2,score`` lines} -> ``bbox_pred [ND, 16] float32`` in frame order, with the
+    BDD100K rules (``dataset/bdd100k_mot.py:319-350``): the eight tracked classes (or the one ``--category``), distractor
+    classes and every detection scoring <= 0.8 dropped; an unknown type is a ``KeyError`` like in the reference."""
+    keep = set(_BDD_CLASSES) if cat == 'All' else {cat}
+    rows = []
+    for fr in sorted(lines_by_frame):
+        for line in lines_by_frame[fr]:
+            tmp = line.rstrip('\n').split(',')
+            if tmp[0] not in _BDD_CLASSES and tmp[0] not in _BDD_DISTRACTORS:
+                raise KeyError(tmp[0])
+            score = float(tmp[5])
+            if tmp[0] in keep and tmp[0] in _BDD_CLASSES and score > BDD_SCORE_FLOOR:
+                rows.append((fr, -1, _BDD_CLASSES[tmp[0]], -10, float(tmp[1]), float(tmp[2]), float(tmp[3]), float(tmp[4]), -1, -1,
+                             -1, -1000, -1000, -1000, -10, score))
+    return np.asarray(rows, dtype=np.float32).reshape(-1, 16)
+
+
+def load_bdd100k_detections(detections_path, seq, frames, cat='All'):
+    """Reads ``<detections_path>/<seq>/%04d.txt`` for every frame; a frame without a file has no detections
+    (``dataset/bdd100k_mot.py:321-324``)."""
+    lines = {}
+    for fr in frames:
+        try:
+            with open(os.path.join(detections_path, seq, '%.4d.txt' % (fr,))) as f:
+                lines[fr] = f.readlines()
+        except OSError:
+            lines[fr] = []
+    b = torch.from_numpy(parse_bdd100k_detection_lines(lines, cat))
     return b.pin_memory() if torch.cuda.is_available() and b.numel() else b
 
 
