@@ -185,6 +185,26 @@ int tmpnn_gat_aggregate_dets(const tmpnn_graph *g, const tmpnn_index *ix, const 
                              const float *w_att, const float *a, int head, int num_heads, float *hatt,
                              float *escore, float *agg, float *alpha, void *stream);
 
+/* Train-mode form (single-slab training graph): nn.Dropout(0.5) on the attention (layers.py:24,37) through the
+ * caller's keep mask -- keep[i] != 0 keeps incidence entry i with weight alpha_i * keep_scale (= 1 / (1 - p)),
+ * keep == NULL is eval mode.  Stores what tmpnn_gat_bwd needs: hatt (cap_dets*64, per head), escore (cap_rows, per
+ * head), alpha (cap_inc, before dropout) and att_edge[2 e + side] (2*cap_rows): the weight after dropout that edge
+ * row e has in the list of its src (side 0) / dst (side 1) detection. */
+int tmpnn_gat_aggregate_dets_train(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
+                                   const float *w_att, const float *a, int head, int num_heads, const uint8_t *keep,
+                                   float keep_scale, float *hatt, float *escore, float *agg, float *alpha,
+                                   float *att_edge, void *stream);
+
+/* Backward of one head (autograd of models/layers.py:26-43 on the edge list): given dagg [cap_dets][64] (gradient of
+ * the node GRU's input) ADDS this head's share to dh_in (columns [col, col+64): edge rows through the weighted sum,
+ * detection rows through W_att), dw_att [64][64] and da [64].  Scratch: dal cap_inc, de_side 2*n_rows, dpre n_rows,
+ * dhatt cap_dets*64 floats.  h is the state the step consumed. */
+int tmpnn_gat_bwd(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, const float *h, int ldh, int col,
+                  const float *w_att, const float *a, int num_heads, const uint8_t *keep, float keep_scale,
+                  const float *hatt, const float *escore, const float *alpha, const float *att_edge,
+                  const float *dagg, float *dal, float *de_side, float *dpre, float *dhatt, float *dh_in,
+                  float *dw_att, float *da, void *stream);
+
 /* ---- K2+K3: one message-passing step (models/layers.py:84-116 + track_mpnn.py:73-75) ---- */
 
 /* For feature group `group` (columns [64 group, 64 group + 64) of h): every edge row runs the
@@ -235,6 +255,11 @@ int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph *g, const tmpnn_index *ix, const 
 int tmpnn_mp_step_fwd_train(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                             int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
                             float *agg, float *gates, void *stream);
+
+/* The same with the detection aggregates supplied by the caller (attention heads: tmpnn_gat_aggregate_dets_train). */
+int tmpnn_mp_step_fwd_train_agg(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                                int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
+                                const float *agg, float *gates, void *stream);
 
 /* Gate gradients of one feature group for every row of a single-slab graph (row type from src):
  * dh' = dh_out (nullable) + (dlogits + dscores p (1-p)) w_type;  dgi = [dpr,dpz,dpn], dgh = [dpr,dpz,dpn r]

@@ -223,8 +223,10 @@ def gat_heads(params, gi):
     return k
 
 
-def gat_support(h, g, w_att, a, alpha=0.2):
-    """One ``GraphAttentionLayer.forward`` in eval mode (``models/layers.py:26-43``) on the edge list:
+def gat_support(h, g, w_att, a, alpha=0.2, keep=None):
+    """One ``GraphAttentionLayer.forward`` (``models/layers.py:26-43``) on the edge list; eval mode, or -- with
+    ``keep`` (bool [N, N], the dropout decision of every attention entry) -- train mode, where the softmax output is
+    multiplied by ``keep / (1 - 0.5)`` before the weighted sum (``:37``; the returned attention is after dropout):
     e_j = LeakyReLU(a . |W h[src_j] - W h[dst_j]|) per edge row, softmax over the edges incident to each
     detection, h'_d = sum_j alpha_dj (+1 if d is the source of j else -1) h_j.
     Returns (support for every row [N, H] -- zero off the detection rows --, e [N], per-detection
@@ -247,6 +249,8 @@ def gat_support(h, g, w_att, a, alpha=0.2):
         x = ev[inc]
         w = np.exp(x - x.max(), dtype=np.float32)
         w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+        if keep is not None:
+            w = (w * keep[r, inc].astype(np.float32) * np.float32(2.0)).astype(np.float32)
         sign = np.where(g.src[inc] == r, 1.0, -1.0).astype(np.float32)
         out[r] = ((w * sign)[:, None] * h[inc]).sum(0, dtype=np.float32)
         att[int(r)] = (inc, w)
@@ -264,8 +268,10 @@ def dense_attention(att, n):
 
 
 def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, msg_type='diff',
-            training=False, update_running_stats=True, return_attention=False):
-    """``TrackMPNN.forward`` (``models/track_mpnn.py:54-75``) for ``nattheads == 0``.
+            training=False, update_running_stats=True, return_attention=False, attention_keep=None):
+    """``TrackMPNN.forward`` (``models/track_mpnn.py:54-75``).  With attention heads in training mode
+    ``attention_keep(group, head, n) -> bool [n, n]`` supplies the dropout decisions (the reference draws them from
+    torch's generator; fixtures pin them instead).
 
     x_new [N'-N, F] float32 (edge rows all-zero), h_in [N, G*H] or None, g has N' rows.
     Returns scores [N',1], logits [N',1], h_out [N', G*H] (attention is a tuple of None)."""
@@ -298,11 +304,12 @@ def forward(params, x_new, h_in, g, features='2d', ncategories=3, nhidden=64, ms
         xs, agg, e, d = aggregate(h, g, msg_type)
         nheads = gat_heads(params, gi)
         if nheads:  # attention-weighted edge_support instead of the plain signed sum (models/layers.py:105-112)
-            assert not training, 'the oracle restates the attention heads in eval mode only (dropout p=0.5 in training)'
+            assert not training or attention_keep is not None, 'train-mode attention needs the dropout decisions'
             acc = np.zeros_like(h)
             heads = []
             for k in range(nheads):
-                sup, _, att = gat_support(h, g, params[f'factor_grus.{gi}.gat.{k}.W_att'], params[f'factor_grus.{gi}.gat.{k}.a'])
+                sup, _, att = gat_support(h, g, params[f'factor_grus.{gi}.gat.{k}.W_att'], params[f'factor_grus.{gi}.gat.{k}.a'],
+                                          keep=attention_keep(gi, k, n_tot) if training else None)
                 acc = acc + sup
                 heads.append(att)
             agg = (acc / np.float32(nheads)).astype(np.float32)[d]

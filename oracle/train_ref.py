@@ -45,9 +45,33 @@ def input_transform_train(p, gi, x_det, n_edge_rows, eps=1e-5):
     return torch.relu(bn) @ w2.t() + b2, mu, var
 
 
-def forward_train(p, x_new, h_in, g, groups, msg_type):
+def gat_support_train(p, gi, k, h, g, keep):
+    """One attention head in train mode (``models/layers.py:26-43``) in differentiable torch ops on the edge list:
+    per-edge score, softmax over each detection's incident edges, dropout through the pinned ``keep`` [N, N]
+    decisions (x 2), signed weighted sum.  Returns the support of every row ([N, H], zero off the detection rows)."""
+    w_att, a = p[f'factor_grus.{gi}.gat.{k}.W_att'], p[f'factor_grus.{gi}.gat.{k}.a']
+    e_rows = np.nonzero(g.ts < 0)[0]
+    hatt = h @ w_att
+    pre = (torch.abs(hatt[torch.from_numpy(g.src[e_rows])] - hatt[torch.from_numpy(g.dst[e_rows])]) @ a).reshape(-1)
+    ev = torch.zeros(g.n, dtype=torch.float32).index_put((torch.from_numpy(e_rows),), torch.nn.functional.leaky_relu(pre, 0.2))
+    past, fut = O._segments(g)
+    rows, sup = [], []
+    for r in np.nonzero(g.ts >= 0)[0]:
+        inc = np.asarray(sorted(past.get(int(r), []) + fut.get(int(r), [])), np.int64)
+        if inc.size == 0:
+            continue
+        w = torch.softmax(ev[torch.from_numpy(inc)], 0) * torch.from_numpy(keep[r, inc].astype(np.float32) * 2.0)
+        sign = torch.from_numpy(np.where(g.src[inc] == r, 1.0, -1.0).astype(np.float32))
+        rows.append(int(r))
+        sup.append(((w * sign)[:, None] * h[torch.from_numpy(inc)]).sum(0))
+    out = torch.zeros_like(h)
+    return out.index_put((torch.tensor(rows, dtype=torch.int64),), torch.stack(sup)) if rows else out
+
+
+def forward_train(p, x_new, h_in, g, groups, msg_type, attention_keep=None):
     """One train-mode ``TrackMPNN.forward`` on graph ``g`` (oracle Graph).  p: dict of torch
-    parameters (requires_grad).  Returns scores[N,1], logits[N,1], h_out[N, G*H]."""
+    parameters (requires_grad).  ``attention_keep(group, head, n)``: pinned dropout decisions when the parameters hold
+    attention heads.  Returns scores[N,1], logits[N,1], h_out[N, G*H]."""
     n_tot = g.n
     n_new = x_new.shape[0]
     n_old = n_tot - n_new
@@ -70,7 +94,11 @@ def forward_train(p, x_new, h_in, g, groups, msg_type):
             xs = torch.cat((h[src], h[dst]), 1)
         else:
             xs = h[src] - h[dst]
-        agg = torch.zeros_like(h).index_add(0, src, h[e]).index_add(0, dst, -h[e])[d]
+        nheads = O.gat_heads(p, gi)
+        if nheads:   # models/layers.py:105-112: heads summed, divided by their number
+            agg = sum(gat_support_train(p, gi, k, h, g, attention_keep(gi, k, n_tot)) for k in range(nheads))[d] / float(nheads)
+        else:
+            agg = torch.zeros_like(h).index_add(0, src, h[e]).index_add(0, dst, -h[e])[d]
         pre = f'factor_grus.{gi}.'
         he = _gru(xs, h[e], p[pre + 'edge_gru.weight_ih'], p[pre + 'edge_gru.weight_hh'],
                   p[pre + 'edge_gru.bias_ih'], p[pre + 'edge_gru.bias_hh'])
@@ -121,8 +149,9 @@ def step_losses(scores, logits, g, tp_classifier):
     return lc, lf, tg
 
 
-def train_chunk(params, X, y, features='2d', ncategories=3, msg_type='diff', tp_classifier=True):
+def train_chunk(params, X, y, features='2d', ncategories=3, msg_type='diff', tp_classifier=True, attention_keep=None):
     """One chunk of ``train.py:65-134``.  params: dict name -> numpy array (state_dict layout).
+    ``attention_keep(step, group, head, n)``: pinned dropout decisions of the attention heads, if any.
     Returns dict(loss, loss_c, loss_f, grads {name: ndarray}, graphs [Graph per step], logits, h)."""
     groups = O.feature_groups(features, ncategories)
     p = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=True) for k, v in params.items()
@@ -131,12 +160,13 @@ def train_chunk(params, X, y, features='2d', ncategories=3, msg_type='diff', tp_
     h = None
     loss_c = loss_f = 0.0
     graphs, all_logits, all_h = [], [], []
-    for t_cur in [None] + list(range(t_st, t_end)):
+    for step, t_cur in enumerate([None] + list(range(t_st, t_end))):
         if t_cur is not None:
             # teacher forcing: the graph growth does not read the scores (utils/graph.py:229-245, 271-274)
             g, feats = O.update_graph(g, np.zeros((g.n, 2), np.float32), X, y, t_cur, mode='train')
+        keep = None if attention_keep is None else (lambda gi, k, n, step=step: attention_keep(step, gi, k, n))
         scores, logits, h = forward_train(p, torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float32)), h, g,
-                                          groups, msg_type)
+                                          groups, msg_type, keep)
         lc, lf, _ = step_losses(scores, logits, g, tp_classifier)
         loss_c = loss_c + lc; loss_f = loss_f + lf
         graphs.append(g.copy()); all_logits.append(logits.detach().numpy()); all_h.append(h.detach().numpy())

@@ -26,6 +26,8 @@ from models.track_mpnn import TrackMPNN  # noqa: E402  (reference)
 from models.loss import create_targets, CELoss, FocalLoss  # noqa: E402  (reference)
 from utils.graph import initialize_graph, update_graph, prune_graph, decode_tracks  # noqa: E402  (reference)
 from trackmpnn_b200 import synth  # noqa: E402
+sys.path.insert(0, os.path.dirname(HERE))
+from golden_util import attention_keep_matrix  # noqa: E402  (the pinned dropout decisions of the attention heads)
 
 
 def coo(adj):
@@ -150,17 +152,34 @@ def run_infer(name, seed, frames, dets, dataset, features, msg_type, scale, edge
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
 
 
-def run_train(name, seed, dets, dataset, features, msg_type, scale, edge_bias, tp_classifier, ret_win=0, cur_win=5):
+class _PinnedDropout(torch.nn.Module):
+    """Stands in for ``GraphAttentionLayer.dropout`` (reference models/layers.py:24) with the pinned mask."""
+
+    def __init__(self, seed, group, head, step_ref):
+        super().__init__()
+        self.seed, self.group, self.head, self.step_ref = seed, group, head, step_ref
+
+    def forward(self, attention):
+        keep = attention_keep_matrix(self.seed, self.step_ref[0], self.group, self.head, attention.shape[0])
+        return attention * torch.from_numpy(keep.astype(np.float32) * 2.0)
+
+
+def run_train(name, seed, dets, dataset, features, msg_type, scale, edge_bias, tp_classifier, ret_win=0, cur_win=5,
+              nattheads=0):
     ts = synth.train_chunk_timestamps(seed, cur_win, ret_win + 2)
     Xn, yn = synth.make_sequence(seed, None, dets, dataset, timestamps=ts)
     Xn = add_features(Xn, yn, features)
     ncat = synth.num_categories(dataset)
-    model = make_model(features, ncat, msg_type, scale, edge_bias)
+    model = make_model(features, ncat, msg_type, scale, edge_bias, nattheads=nattheads)
     model.train()
+    step_ref = [0]
+    for g, gru in enumerate(model.factor_grus):
+        for k, head in enumerate(gru.gat or ()):
+            head.dropout = _PinnedDropout(seed, g, k, step_ref)
     X = torch.from_numpy(Xn); y = torch.from_numpy(yn)
     out = {'X': Xn, 'y': yn}
     meta = dict(kind='train', features=features, ncategories=ncat, msg_type=msg_type, tp_classifier=tp_classifier,
-                ret_win_size=ret_win, cur_win_size=cur_win, dataset=dataset, timestamps=ts)
+                ret_win_size=ret_win, cur_win_size=cur_win, dataset=dataset, timestamps=ts, nattheads=nattheads, seed=seed)
     for k, v in model.state_dict().items():
         out['w/' + k] = v.detach().cpu().numpy().copy()
     focal_node, focal_edge, ce = FocalLoss(gamma=0), FocalLoss(gamma=0), CELoss()
@@ -197,6 +216,7 @@ def run_train(name, seed, dets, dataset, features, msg_type, scale, edge_bias, t
         if t_cur < t_skip:
             continue
         s += 1
+        step_ref[0] = s
         if feats.size()[0] == 0 and states.size()[0] == 0:
             raise RuntimeError('unexpected re-init in a training chunk')
         y_pred, feats, node_adj, edge_adj, labels = update_graph(
@@ -224,7 +244,12 @@ def run_train(name, seed, dets, dataset, features, msg_type, scale, edge_bias, t
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gat':
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gat_train':
+    # attention heads in train mode: dropout mask pinned (attention_keep_matrix), gradients of W_att / a included
+    torch.set_num_threads(4)
+    run_train('train_gat2', 24, 6, 'kitti', '2d', 'diff', 20.0, 0.0, True, nattheads=2)
+    run_train('train_gat3_concat', 25, 5, 'kitti', '2d+temp', 'concat', 20.0, 0.0, True, nattheads=3)
+elif __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gat':
     # added after the first batch of fixtures: attention heads (--num-att-heads 2), eval mode
     torch.set_num_threads(4)
     run_infer('infer_gat2', 18, 10, 5, 'kitti', '2d', 'diff', 20.0, 0.0, False, 0, 5, True, nattheads=2)

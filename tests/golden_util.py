@@ -10,6 +10,14 @@ from oracle import trackmpnn_oracle as O
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
+def attention_keep_matrix(seed, step, group, head, n):
+    """The dropout decision for every entry of the dense [n, n] attention of (step, group, head): the reference's
+    nn.Dropout draws from torch's CPU generator, which no other implementation can replay, so the train fixtures with
+    attention heads pin the mask instead -- the generator script replaces ``GraphAttentionLayer.dropout`` by a
+    multiplication with ``keep / (1 - p)`` (p = 0.5), and every replay uses the same matrix."""
+    return np.random.RandomState(seed * 100000 + step * 100 + group * 10 + head).rand(n, n) >= 0.5
+
+
 def golden_names(kind=None):
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
     if kind is not None:
@@ -65,3 +73,27 @@ def assert_grads_close(got, gold, rel=2e-3):
         want = gold.z['g/' + k]
         atol = rel * float(np.abs(want).max()) + 1e-6 * gmax + 1e-9
         np.testing.assert_allclose(np.asarray(got[k]).reshape(want.shape), want, atol=atol, rtol=0, err_msg=k)
+
+
+def pin_attention_dropout(model, gold, state):
+    """Makes the CUDA model's attention heads use the fixture's dropout decisions: ``state['s']`` (MP step) and
+    ``state['n']`` (rows of the graph at that step) are set by the test before each forward; the dense decision matrix
+    is read at (detection row, incident edge row) for every entry of the incidence index."""
+    import torch
+    seed = gold.meta.get('seed')
+    for g, gru in enumerate(model.factor_grus):
+        if gru.gat is None:
+            continue
+
+        def fn(head, index, device, g=g):
+            M = attention_keep_matrix(seed, state['s'], g, head, state['n'])
+            nd = int(index.n_dets.item())
+            seg = index.seg_ptr[:2 * nd + 1].long().cpu()
+            lens = seg[2::2] - seg[0:-1:2]
+            tot = int(seg[-1])
+            owner = torch.repeat_interleave(index.det_rows[:nd].long().cpu(), lens).numpy()
+            cols = index.inc[:tot].long().cpu().numpy()
+            keep = torch.zeros(index.cap_inc, dtype=torch.uint8)
+            keep[:tot] = torch.from_numpy(M[owner, cols].astype(np.uint8))
+            return keep.to(device)
+        gru.attention_keep_fn = fn

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import Golden, golden_names
+from golden_util import Golden, golden_names, pin_attention_dropout
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -134,6 +134,8 @@ def test_train_forward(name):
     m = gold.meta
     dev = torch.device('cuda:0')
     model = _model(gold, dev, train=True)
+    state = {'s': 0, 'n': 0}
+    pin_attention_dropout(model, gold, state)
     X, y = torch.from_numpy(gold.X).to(dev), torch.from_numpy(gold.y).to(dev)
     with torch.no_grad():
         y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, 0, 'train', True)
@@ -148,6 +150,7 @@ def test_train_forward(name):
             np.testing.assert_array_equal(y_pred.cpu().numpy(), gold.get(s, 'y_pred'), err_msg=f'step {s}')
             np.testing.assert_array_equal(labels.cpu().numpy(), gold.get(s, 'labels'))
             np.testing.assert_array_equal(_dense(node_adj), _ref_dense(gold, s))
+            state.update(s=s, n=int(y_pred.shape[0]))
             scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
             np.testing.assert_allclose(logits.cpu().numpy(), gold.get(s, 'logits'), atol=TOL, rtol=0)
             np.testing.assert_allclose(states.cpu().numpy(), gold.get(s, 'h'), atol=TOL, rtol=0)
@@ -170,6 +173,8 @@ def test_train_backward(name):
     m = gold.meta
     dev = torch.device('cuda:0')
     model = _model(gold, dev, train=True)
+    state = {'s': 0, 'n': 0}
+    pin_attention_dropout(model, gold, state)
     X, y = torch.from_numpy(gold.X).to(dev), torch.from_numpy(gold.y).to(dev)
     ce, focal_node, focal_edge = CELoss(), FocalLoss(gamma=0), FocalLoss(gamma=0)
 
@@ -192,6 +197,7 @@ def test_train_backward(name):
         return scores, loss_c, loss_f
 
     y_pred, feats, node_adj, edge_adj, labels, t_st, t_end = initialize_graph(X, y, t_st=0, mode='train', cuda=True)
+    state.update(s=0, n=int(y_pred.shape[0]))
     scores, logits, states, _ = model(feats, None, node_adj, edge_adj)
     assert logits.requires_grad and states.requires_grad
     s = 0
@@ -200,6 +206,7 @@ def test_train_backward(name):
         s += 1
         y_pred, feats, node_adj, edge_adj, labels = update_graph(
             node_adj, labels, scores, y_pred, X, y, t_cur, use_hungraian=False, mode='train', cuda=True)
+        state.update(s=s, n=int(y_pred.shape[0]))
         scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
         np.testing.assert_allclose(logits.detach().cpu().numpy(), gold.get(s, 'logits'), atol=TOL, rtol=0)
         scores, lc, lf = losses(scores, logits, y_pred, labels, node_adj, s)

@@ -9,15 +9,16 @@ import numpy as np
 import pytest
 
 from oracle import trackmpnn_oracle as O
-from golden_util import Golden, golden_names, assert_graph_equal, assert_grads_close
+from golden_util import Golden, golden_names, assert_graph_equal, assert_grads_close, attention_keep_matrix
 
 TOL = 1e-4
 
 
-def _fwd(gold, params, x, h_in, g, training=False):
+def _fwd(gold, params, x, h_in, g, training=False, step=0):
     m = gold.meta
+    keep = (lambda gi, k, n: attention_keep_matrix(m['seed'], step, gi, k, n)) if m.get('nattheads', 0) and training else None
     return O.forward(params, x, h_in, g, features=m['features'], ncategories=m['ncategories'], nhidden=64,
-                     msg_type=m['msg_type'], training=training)
+                     msg_type=m['msg_type'], training=training, attention_keep=keep)
 
 
 @pytest.mark.parametrize('name', golden_names('infer'))
@@ -137,7 +138,7 @@ def test_train_chunk(name):
             g, feats = O.update_graph(g, gold.get(s - 1, 'scores'), gold.X, gold.y, t_cur, mode='train')
         assert_graph_equal(g, gold.graph(s), f'{name} step {s}')
         np.testing.assert_array_equal(feats, gold.get(s, 'feats'))
-        scores, logits, h = _fwd(gold, params, feats, h, g, training=True)
+        scores, logits, h = _fwd(gold, params, feats, h, g, training=True, step=s)
         np.testing.assert_allclose(logits, gold.get(s, 'logits'), atol=TOL, rtol=0)
         np.testing.assert_allclose(h, gold.get(s, 'h'), atol=TOL, rtol=0)
         tg = O.create_targets(g)
@@ -165,7 +166,9 @@ def test_train_gradients(name):
     gold = Golden(name)
     m = gold.meta
     out = T.train_chunk(gold.params(), gold.X, gold.y, features=m['features'], ncategories=m['ncategories'],
-                        msg_type=m['msg_type'], tp_classifier=m['tp_classifier'])
+                        msg_type=m['msg_type'], tp_classifier=m['tp_classifier'],
+                        attention_keep=(lambda s, gi, k, n: attention_keep_matrix(m['seed'], s, gi, k, n))
+                        if m.get('nattheads', 0) else None)
     np.testing.assert_allclose(out['loss'], float(gold.z['loss']), rtol=1e-4)
     assert len(out['graphs']) == gold.n_steps
     assert_grads_close(out['grads'], gold)

@@ -39,19 +39,22 @@ def _chunk_loss_dropin(model, X, y, tp=True):
     return loss
 
 
-@pytest.mark.parametrize('builder', ['slab', 'chunk'])
-@pytest.mark.parametrize('msg_type', ['diff', 'concat'])
-def test_batch_equals_sum_of_chunks(msg_type, builder):
+@pytest.mark.parametrize('builder,msg_type,heads', [('slab', 'diff', 0), ('chunk', 'diff', 0), ('slab', 'concat', 0),
+                                                     ('chunk', 'concat', 0), ('slab', 'diff', 2)])
+def test_batch_equals_sum_of_chunks(msg_type, builder, heads):
     features = '2d'
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
     from trackmpnn_b200.train_engine import TrainBatch, batch_loss
     dev = torch.device('cuda:0')
     torch.manual_seed(5)
-    model = TrackMPNN(features, 3, 64, 0, msg_type).to(dev)
+    model = TrackMPNN(features, 3, 64, heads, msg_type).to(dev)
     with torch.no_grad():
-        for p in model.parameters():
-            if p.dim() >= 2:
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and '.gat.' not in name:
                 p.mul_(5.0)
+    for gru in model.factor_grus:
+        # attention heads: dropout that keeps every entry (x 2), so that the batch and the chunk layouts agree
+        gru.attention_keep_fn = lambda head, index, device: torch.ones(index.cap_inc, dtype=torch.uint8, device=device)
     model.train()
     chunks = []
     for i, dets in enumerate((6, 9, 4, 7)):

@@ -82,6 +82,8 @@ _PROTOS = {
     'tmpnn_index_build_structured': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _VP], _I),
     'tmpnn_aggregate_dets': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP], _I),
     'tmpnn_gat_aggregate_dets': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_gat_aggregate_dets_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP, _I, _I, _VP, C.c_float] + [_VP] * 6, _I),
+    'tmpnn_gat_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _I, _I, _VP, _VP, _I, _VP, C.c_float] + [_VP] * 13, _I),
     'tmpnn_aggregate_edges': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_mp_step_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_edge_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP], _I),
@@ -92,6 +94,7 @@ _PROTOS = {
     'tmpnn_mp_edge_fwd_tc_pre': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_edge_fwd_tc': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_mp_step_fwd_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_mp_step_fwd_train_agg': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 16, _I),
     'tmpnn_rows_times_w': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _VP], _I),
     'tmpnn_rows_outer': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP], _I),
@@ -181,7 +184,7 @@ KERNELS_PER_CALL = {
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
-    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
+    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_build_features': 1, 'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }

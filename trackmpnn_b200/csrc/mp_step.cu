@@ -598,6 +598,15 @@ extern "C" int tmpnn_mp_step_fwd_train(const tmpnn_graph* g, const tmpnn_index* 
   return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, gates, stream);
 }
 
+extern "C" int tmpnn_mp_step_fwd_train_agg(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                           int group, int num_groups, int concat, const float* edge_pack,
+                                           const float* node_pack, const float* agg, float* gates, void* stream) {
+  TMPNN_REQUIRE(gates && agg, "null argument");
+  int rc = mp_edge_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, gates, stream);
+  if (rc) return rc;
+  return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, gates, stream);
+}
+
 extern "C" int tmpnn_mp_step_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
                                  int group, int num_groups, int concat, const float* edge_pack, const float* node_pack,
                                  float* agg, void* stream) {

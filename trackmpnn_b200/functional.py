@@ -110,9 +110,10 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
     if gru.gat is None:
         L.call('tmpnn_aggregate_dets', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(agg), st)
         return None
-    if gru.training and torch.is_grad_enabled():
-        raise NotImplementedError('attention heads are built for inference (eval mode); their training path '
-                                  '(dropout on the attention + backward) is not')
+    if gru.training:
+        # train mode: dropout on the attention (same kernels as the autograd path; the saved tensors are dropped)
+        saved = gat_forward_train(gru, graph, index, h_in, ldh, col, agg)
+        return [attention_after_dropout(sv) for sv in saved] if keep_attention else None
     dev = h_in.device
     if scratch is None:
         scratch = {}
@@ -131,6 +132,50 @@ def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, kee
                L.ptr(head.a.detach().contiguous()), k, nh, L.ptr(hatt), L.ptr(esc), L.ptr(agg), L.ptr(alpha), st)
         alphas.append(alpha)
     return alphas if keep_attention else None
+
+
+ATTENTION_DROPOUT_P = 0.5  # nn.Dropout(p=0.5) of the reference's GraphAttentionLayer (models/layers.py:24)
+
+
+def attention_keep_mask(gru, head, index, device):
+    """One keep byte per incidence entry (``index.inc`` order) for ``head`` of ``gru``.  Drawn from torch's CUDA
+    generator; a test (or a caller that wants reproducible masks) can set
+    ``gru.attention_keep_fn = fn(head, index, device) -> uint8 [index.cap_inc]``."""
+    n = index.cap_inc
+    fn = getattr(gru, 'attention_keep_fn', None)
+    if fn is not None:
+        keep = fn(head, index, device)
+        if keep.dtype != torch.uint8 or keep.numel() < n or keep.device != device:
+            raise ValueError('attention_keep_fn must return a uint8 tensor with one entry per incidence entry on the device')
+        return keep.contiguous()
+    return (torch.rand(n, device=device) >= ATTENTION_DROPOUT_P).to(torch.uint8)
+
+
+def gat_forward_train(gru, graph, index, h_in, ldh, col, agg):
+    """The attention-weighted aggregate of every head with dropout when ``gru.training`` (reference
+    ``models/layers.py:26-43, 105-112``); returns per head what ``tmpnn_gat_bwd`` needs."""
+    dev = h_in.device
+    st = L.stream()
+    nh = len(gru.gat)
+    training = bool(gru.training)
+    scale = 1.0 / (1.0 - ATTENTION_DROPOUT_P) if training else 1.0
+    saved = []
+    for k, head in enumerate(gru.gat):
+        f32 = dict(dtype=torch.float32, device=dev)
+        sv = dict(w=head.W_att.detach().contiguous(), a=head.a.detach().contiguous(),
+                  keep=attention_keep_mask(gru, k, index, dev) if training else None, scale=scale,
+                  hatt=torch.empty((index.cap_dets, H), **f32), esc=torch.empty(graph.cap_rows, **f32),
+                  alpha=torch.empty(index.cap_inc, **f32), att_edge=torch.empty(2 * graph.cap_rows, **f32))
+        L.call('tmpnn_gat_aggregate_dets_train', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(sv['w']), L.ptr(sv['a']), k, nh,
+               L.ptr(sv['keep']), scale, L.ptr(sv['hatt']), L.ptr(sv['esc']), L.ptr(agg), L.ptr(sv['alpha']),
+               L.ptr(sv['att_edge']), st)
+        saved.append(sv)
+    return saved
+
+
+def attention_after_dropout(sv):
+    """What the reference returns as ``attention`` in train mode: the softmax output after dropout, per incidence entry."""
+    return sv['alpha'] if sv['keep'] is None else sv['alpha'] * sv['keep'] * sv['scale']
 
 
 def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, kernel='auto'):
@@ -299,6 +344,9 @@ def _param_list(model):
         ps += [seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias]
         for cell in (gru.edge_gru, gru.node_gru):
             ps += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+    for gru in model.factor_grus:   # attention heads sit between the per-group blocks and the four head tensors
+        for head in (gru.gat or ()):
+            ps += [head.W_att, head.a]
     ps += [model.output_transform_node.weight, model.output_transform_node.bias,
            model.output_transform_edge.weight, model.output_transform_edge.bias]
     return ps
@@ -372,9 +420,6 @@ class _MPStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, node_adj, x, h_in, *params):
-        if any(g.gat is not None for g in model.factor_grus):
-            raise NotImplementedError('training with attention heads (--num-att-heads > 0) is not built: the heads '
-                                      'run in inference only (call model.eval() under torch.no_grad())')
         wg = window_graph_of(node_adj)
         dev = wg.device
         n_tot = wg.n
@@ -407,21 +452,28 @@ class _MPStepFn(torch.autograd.Function):
         ix = wg.index()
         h_out = torch.empty_like(h_cur)
         packs = packed_cells(model)
-        gates, aggs = [], []
+        gates, aggs, gats = [], [], []
         st = L.stream()
         for g in range(G):
-            concat = int(model.factor_grus[g].msg_type == 'concat')
+            gru = model.factor_grus[g]
+            concat = int(gru.msg_type == 'concat')
             gt = torch.empty((n_tot, 4 * H), dtype=torch.float32, device=dev)
             agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
-            L.call('tmpnn_mp_step_fwd_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat,
-                   L.ptr(packs[g][0]), L.ptr(packs[g][1]), L.ptr(agg), L.ptr(gt), st)
+            if gru.gat is None:
+                L.call('tmpnn_mp_step_fwd_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat,
+                       L.ptr(packs[g][0]), L.ptr(packs[g][1]), L.ptr(agg), L.ptr(gt), st)
+                gats.append(None)
+            else:
+                gats.append(gat_forward_train(gru, wg.g, ix, h_cur, ldh, g * H, agg))
+                L.call('tmpnn_mp_step_fwd_train_agg', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat,
+                       L.ptr(packs[g][0]), L.ptr(packs[g][1]), L.ptr(agg), L.ptr(gt), st)
             gates.append(gt)
             aggs.append(agg)
         logits = wg.g.logit[:n_tot].clone().unsqueeze(1)
         scores = wg.g.score[:n_tot].clone().unsqueeze(1)
         ctx.model, ctx.wg, ctx.ix = model, wg, ix
         ctx.n_old, ctx.has_h_in = n_old, h_in is not None
-        ctx.saved_in, ctx.gates, ctx.aggs = saved_in, gates, aggs
+        ctx.saved_in, ctx.gates, ctx.aggs, ctx.gats = saved_in, gates, aggs, gats
         # outputs are kept as detached aliases: an attribute holding an output tensor itself would close a reference
         # cycle (ctx -> output -> grad_fn -> ctx) that only the cycle collector frees -- GBs per batched step
         ctx.h_cur, ctx.h_out, ctx.p = h_cur, h_out.detach(), scores.detach()
@@ -444,6 +496,7 @@ class _MPStepFn(torch.autograd.Function):
         g_hw_node, g_hb_node, g_hw_edge, g_hb_edge = grads[-4], grads[-3], grads[-2], grads[-1]
         hw_node, hw_edge = P[-4], P[-2]
         h_cur, h_out = ctx.h_cur, ctx.h_out
+        gat_base = G * _PER_GROUP   # W_att, a of every head, group by group
         for g in range(G):
             col = g * H
             b = g * _PER_GROUP
@@ -480,7 +533,20 @@ class _MPStepFn(torch.autograd.Function):
             L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
                    L.ptr(grads[b + 11]), st)
             # through the gather / segmented sum, into the state this step consumed
-            L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx, L.ptr(dagg), L.ptr(dh_cur), ldh, col, st)
+            heads = ctx.gats[g]
+            L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx,
+                   L.ptr(dagg if heads is None else torch.zeros_like(dagg)), L.ptr(dh_cur), ldh, col, st)
+            if heads is not None:
+                # the aggregate came from the attention heads: through the weighted sum, the softmax and W_att, a
+                dal = torch.empty(ix.cap_inc, **f32)
+                de_side, dpre = torch.empty(2 * n, **f32), torch.empty(n, **f32)
+                dhatt = torch.empty((ix.cap_dets, H), **f32)
+                for k, sv in enumerate(heads):
+                    L.call('tmpnn_gat_bwd', wg.g.c, ix.c, n, L.ptr(h_cur), ldh, col, L.ptr(sv['w']), L.ptr(sv['a']), len(heads),
+                           L.ptr(sv['keep']), sv['scale'], L.ptr(sv['hatt']), L.ptr(sv['esc']), L.ptr(sv['alpha']),
+                           L.ptr(sv['att_edge']), L.ptr(dagg), L.ptr(dal), L.ptr(de_side), L.ptr(dpre), L.ptr(dhatt),
+                           L.ptr(dh_cur), L.ptr(grads[gat_base + 2 * k]), L.ptr(grads[gat_base + 2 * k + 1]), st)
+                gat_base += 2 * len(heads)
             # new detection rows: through the input transform (one group of rows per BatchNorm batch)
             groups_in = [t for t in ctx.saved_in if t[3] > 0]
             if len(groups_in) > 1:
