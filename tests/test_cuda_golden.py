@@ -207,7 +207,10 @@ def test_train_backward(name):
         y_pred, feats, node_adj, edge_adj, labels = update_graph(
             node_adj, labels, scores, y_pred, X, y, t_cur, use_hungraian=False, mode='train', cuda=True)
         state.update(s=s, n=int(y_pred.shape[0]))
-        scores, logits, states, _ = model(feats, states, node_adj, edge_adj)
+        scores, logits, states, att = model(feats, states, node_adj, edge_adj)
+        # attention slots: one SparseAttention per head (after dropout), None without heads
+        assert all((a is None) == (m.get('nattheads', 0) == 0) for a in att)
+        assert all(a is None or len(a) == m['nattheads'] for a in att)
         np.testing.assert_allclose(logits.detach().cpu().numpy(), gold.get(s, 'logits'), atol=TOL, rtol=0)
         scores, lc, lf = losses(scores, logits, y_pred, labels, node_adj, s)
         loss_c = loss_c + lc

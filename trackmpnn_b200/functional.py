@@ -265,9 +265,18 @@ def track_mpnn_forward(model, x, h_in, node_adj, edge_adj):
     """``TrackMPNN.forward`` (reference ``models/track_mpnn.py:54-75``) on the CUDA library."""
     if torch.is_grad_enabled() and (any(p.requires_grad for p in model.parameters())
                                     or (h_in is not None and h_in.requires_grad)):
-        G = len(model.feature_idx)
-        scores, logits, h_out = _MPStepFn.apply(model, node_adj, x, h_in, *_param_list(model))
-        return scores, logits, h_out, tuple(None for _ in range(G))
+        scores, logits, h_out, *alphas = _MPStepFn.apply(model, node_adj, x, h_in, *_param_list(model))
+        # attention slots: per group None or one SparseAttention per head (after dropout, as the reference returns it)
+        attention, wg = [], None
+        for gru in model.factor_grus:
+            if gru.gat is None:
+                attention.append(None)
+                continue
+            if wg is None:
+                wg = window_graph_of(node_adj)
+                ix = wg.index()
+            attention.append([SparseAttention(wg.n, ix.n_dets, ix.det_rows, ix.seg_ptr, ix.inc, alphas.pop(0)) for _ in gru.gat])
+        return scores, logits, h_out, tuple(attention)
     wg = window_graph_of(node_adj)
     dev = wg.device
     n_tot = wg.n
@@ -478,10 +487,13 @@ class _MPStepFn(torch.autograd.Function):
         # cycle (ctx -> output -> grad_fn -> ctx) that only the cycle collector frees -- GBs per batched step
         ctx.h_cur, ctx.h_out, ctx.p = h_cur, h_out.detach(), scores.detach()
         ctx.param_vals = [p.detach() for p in params]
-        return scores, logits, h_out
+        # the attention after dropout of every head, as extra non-differentiable outputs (copies: nothing ctx holds)
+        alphas = [attention_after_dropout(sv).clone() for heads in gats if heads is not None for sv in heads]
+        ctx.mark_non_differentiable(*alphas)
+        return (scores, logits, h_out, *alphas)
 
     @staticmethod
-    def backward(ctx, dscores, dlogits, dh_out):
+    def backward(ctx, dscores, dlogits, dh_out, *_dalphas):
         model, wg, ix = ctx.model, ctx.wg, ctx.ix
         dev = wg.device
         n, G = wg.n, len(model.feature_idx)

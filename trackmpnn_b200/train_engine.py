@@ -247,7 +247,7 @@ def batch_loss(model, batch, tp_classifier=True):
         h_in = torch.zeros((st.n, ldh), dtype=torch.float32, device=batch.device)
         if h_prev is not None:
             h_in = h_in.index_copy(0, st.carry_to, h_prev.index_select(0, st.carry_from))
-        scores, logits, h_prev = _MPStepFn.apply(model, st.holder, st.new_rows, h_in, *params)
+        scores, logits, h_prev = _MPStepFn.apply(model, st.holder, st.new_rows, h_in, *params)[:3]
         p = scores[:, 0]
         tgt = st.targets.to(p.dtype)
         p_t = p * tgt + (1 - p) * (1 - tgt)                      # FocalLoss(gamma=0): mean(-log(p_t + 1e-10)), per chunk
