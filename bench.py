@@ -622,4 +622,10 @@ def main():
 
 
 if __name__ == '__main__':
+    # stdout carries exactly one line, the JSON result: anything a library writes to file descriptor 1 while the bench
+    # runs (NCCL prints its version banner there when NCCL_DEBUG is set) is routed to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, 'w')
     main()
