@@ -484,6 +484,7 @@ def main():
     eng.use_cuda_graph = False
     eng.profile = []
     eng.profile_compact = []
+    eng.profile_phases = []
     clocks = ClockSampler(local)
     clocks.start()
     eng.run(); torch.cuda.synchronize()   # one more untimed pass while nvidia-smi starts up
@@ -508,6 +509,8 @@ def main():
     eng.profile = None
     cprof = eng.profile_compact
     eng.profile_compact = None
+    pprof = eng.profile_phases
+    eng.profile_phases = None
     eng.ga.check_status()
     k_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
     k_edges = sum(int(p[2].item()) for p in prof)
@@ -542,6 +545,15 @@ def main():
             'frac': c_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak if c_ms > 0 else 0.0, 'avg_launch_ms': c_ms / max(1, len(cprof)),
             'share_of_step': c_ms / ms if ms > 0 else None, 'rows_in': rows_in, 'rows_kept': rows_out,
             'algorithmic_bytes': f'{per_kept} B per surviving row + 9 B per row', 'traffic': None}
+    # the reference's three phases per frame (update_graph 20 % / forward 42 % / decode_tracks 33 % of its loop)
+    ph_ms = [sum(p[i].elapsed_time(p[i + 1]) for p in pprof) for i in range(3)]
+    ph_tot = sum(ph_ms) or 1.0
+    phases = {'ticks_timed': len(pprof), 'update_ms_per_tick': ph_ms[0] / max(1, len(pprof)),
+              'forward_ms_per_tick': ph_ms[1] / max(1, len(pprof)), 'decode_ms_per_tick': ph_ms[2] / max(1, len(pprof)),
+              'share': {'update': ph_ms[0] / ph_tot, 'forward': ph_ms[1] / ph_tot, 'decode': ph_ms[2] / ph_tot},
+              'reference_share': {'update': 0.20, 'forward': 0.42, 'decode': 0.33},
+              'what': 'update = tmpnn_graph_append (+ Hungarian re-association); forward = input transform + incidence index + '
+                      'aggregation + association-row and detection-row steps; decode = association + track walk + window slide'}
     n_l = max(1, len(prof))
     tr_e, tr_a = (measured_traffic('k_mp_edge_tc3') if eng.tensor else None), measured_traffic('k_aggregate_dets')
     agg['traffic'] = tr_a * k_edges / n_l if tr_a else None
@@ -615,6 +627,7 @@ def main():
                           'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
                           'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
                           'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
+               'det_updates_per_s': reduce_(dets, dist.ReduceOp.SUM if world > 1 else None) / (ms * 1e-3), 'phases': phases,
                'roofline': roof, 'roofline_aggregation': agg, 'roofline_compaction': comp, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'c1': c1, 'train': train, 'train_ddp': train_ddp}
         print(json.dumps(out), flush=True)
     if world > 1:

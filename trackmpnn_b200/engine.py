@@ -122,6 +122,9 @@ class TrackEngine:
         self._gat_scratch = {}
         self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end) per step
         self.profile_compact = None  # when a list: (start, end, rows before, rows after) per window slide
+        # when a list: four events per tick bracketing the reference's three phases -- update_graph (append) |
+        # forward (input transform, index, aggregation, both row types) | decode_tracks (associate, walk, window slide)
+        self.profile_phases = None
         self._graph = None
         self.ticks = 0
 
@@ -198,6 +201,10 @@ class TrackEngine:
         g, go = self.ga, self.gb
         h_in, h_out = (self.h_alt, self.h_cur) if (flip and self.deferred) else (self.h_cur, self.h_alt)
         st = L.stream()
+        ph = None
+        if self.profile_phases is not None:
+            ph = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ph[0].record()
         if self.use_hungarian:
             # update_graph re-solves the assignment on the graph decode_tracks left behind (utils/graph.py:247-249);
             # unlike the greedy choice it is not invariant under the deletion, so it is recomputed here
@@ -206,7 +213,11 @@ class TrackEngine:
         L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
                L.ptr(h_in), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
                L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
+        if ph:
+            ph[1].record()
         self._forward(g, h_in, h_out)
+        if ph:
+            ph[2].record()
         self._associate(g)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
@@ -222,6 +233,9 @@ class TrackEngine:
         if self.profile_compact is not None:
             c1.record()
             self.profile_compact.append((c0, c1, g.n_rows.sum(), go.n_rows.sum()))
+        if ph:
+            ph[3].record()
+            self.profile_phases.append(ph)
         self.frames_done += self.st['active'].sum()
         self.t_dev += 1
 
