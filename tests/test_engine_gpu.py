@@ -180,3 +180,49 @@ def test_engine_state_at_workload_size(kernel):
             np.testing.assert_array_equal(getattr(eng.ga, name)[rows].cpu().numpy(), getattr(g, name), err_msg=name)
         np.testing.assert_allclose(eng.ga.score[rows].cpu().numpy(), sc[:, 1], atol=1e-4, rtol=0)
         np.testing.assert_allclose(hb[eng.ga.phys[rows].long()].cpu().numpy(), h, atol=1e-4, rtol=0)
+
+
+def _edge_case_sequences():
+    """Degenerate streams next to a normal one: a single timestep (initialize_graph has nothing to pair: no tracks), two
+    timesteps (only the initial forward runs), holes shorter than the window, one detection per frame, no detection."""
+    out = []
+    for seed, frames, dets, kw in ((30, 10, 5, {}), (31, 1, 5, {}), (34, 2, 3, {}),
+                                   (32, None, 4, dict(timestamps=[0, 1, 3, 4, 7, 8, 9, 12])),
+                                   (33, 12, 1, dict(poisson=False, miss_rate=0.0, fp_rate=0.0))):
+        X, y = synth.make_sequence(seed, frames, dets, 'kitti', **kw)
+        out.append((X[0], y[0]))
+    return out
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_engine_edge_case_sequences(graph):
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    params = _params(model)
+    seqs = _edge_case_sequences()
+    empty = (np.zeros((0, 8), np.float32), np.zeros((0, 2), np.float32))   # the reference raises IndexError on this one
+    eng = TrackEngine(model, seqs[:2] + [empty] + seqs[2:], cur_win_size=5, ret_win_size=0, use_cuda_graph=graph)
+    outs, stats = eng.run().results()
+    assert outs[2].shape == (0,)
+    outs = outs[:2] + outs[3:]
+    tot_e = tot_f = 0
+    for (X, y), got in zip(seqs, outs):
+        want, st = run_infer(params, X, y, record_margin=True)
+        assert st['margin'] > 1e-4
+        np.testing.assert_array_equal(got, want[:, 1])
+        tot_e += st['edge_updates']; tot_f += st['frames']
+    assert (outs[1] == -1).all() and (outs[2] == -1).all()    # nothing to pair / never decoded
+    assert stats['edge_updates'] == tot_e and stats['frames'] == tot_f
+
+
+def test_engine_reports_capacity_overflow():
+    """A slab too small for the window graph sets the sticky device flag; results() raises instead of returning tracks."""
+    from trackmpnn_b200 import _lib as L
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    seqs = _sequences([30, 34])
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, cap_rows=48)
+    with pytest.raises(L.TmpnnError, match='capacity'):
+        eng.run().results()
