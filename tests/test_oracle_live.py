@@ -1,0 +1,28 @@
+"""CPU, build container only: the oracle's inference loop against the LIVE reference (``/root/reference``, unmodified,
+imported in a subprocess) on random streams that are not among the committed fixtures -- random message type,
+association mode, window and retention sizes, with and without a hole that forces re-initialisation.  Decoded tracks,
+edge-update and frame counters must be equal.  Skipped where the reference tree does not exist (the GPU box)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEEDS = [201, 202, 203, 204, 205, 206, 207, 208, 311, 312]
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference tree not present')
+def test_oracle_equals_live_reference_on_random_streams():
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'live_reference_check.py')] + [str(s) for s in SEEDS],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cases = [json.loads(line) for line in r.stdout.splitlines() if line.startswith('{')]
+    assert len(cases) == len(SEEDS)
+    assert {c['msg_type'] for c in cases} == {'diff', 'concat'} and {c['hungarian'] for c in cases} == {True, False}
+    for c in cases:
+        assert c['same_edges'] and c['same_frames'], c
+        # a score within float noise of the 0.5 threshold may legitimately flip a decision
+        assert c['same_tracks'] or c['margin'] < 1e-5, c
+        assert c['tracks'] > 0
