@@ -26,3 +26,19 @@ def test_oracle_equals_live_reference_on_random_streams():
         # a score within float noise of the 0.5 threshold may legitimately flip a decision
         assert c['same_tracks'] or c['margin'] < 1e-5, c
         assert c['tracks'] > 0
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference tree not present')
+def test_training_oracle_equals_live_reference_on_random_chunks():
+    """``oracle/train_ref.py`` against the live reference's ``loss.backward()`` on random training chunks (random message
+    type, TP classifier on / off, skip distance, density): total loss to 1e-5, every parameter gradient within the
+    bar the golden gradient tests use."""
+    seeds = [401, 402, 403, 404, 405, 406]
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'live_reference_check.py'), 'train'] + [str(s) for s in seeds],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cases = [json.loads(line) for line in r.stdout.splitlines() if line.startswith('{')]
+    assert len(cases) == len(seeds)
+    assert {c['msg_type'] for c in cases} == {'diff', 'concat'} and {c['tp_classifier'] for c in cases} == {True, False}
+    for c in cases:
+        assert c['loss_rel_err'] < 1e-5 and c['grad_err_over_bar'] < 1.0, c
