@@ -58,6 +58,13 @@ def parse():
     ap.add_argument('--train-chunks', type=int, default=6, help='BPTT chunks timed by the training leg')
     ap.add_argument('--train-dets', type=int, default=40)
     ap.add_argument('--train-batch', type=int, default=32, help='chunks per batch of the batched trainer')
+    ap.add_argument('--skip-strong', action='store_true', help='N > 1: skip the strong-scaling leg')
+    ap.add_argument('--skip-check', action='store_true', help='skip the same-tracks-on-every-rank check')
+    ap.add_argument('--skip-c4', action='store_true', help='N = 1: skip the configs[3] stress-graph leg')
+    ap.add_argument('--c4-win', type=int, default=20)
+    ap.add_argument('--c4-dets', type=int, default=200)
+    ap.add_argument('--c4-seqs', type=int, default=4)
+    ap.add_argument('--c4-frames', type=int, default=26)
     return ap.parse_args()
 
 
@@ -66,23 +73,28 @@ def workload_name(a):
             f'{a.frames} frames, win {a.win}, greedy decode, stock init, {a.seqs_per_gpu} sequences per GPU')
 
 
-def make_sequences(a, rank):
+def make_sequences(a, seed0, count):
     from trackmpnn_b200 import synth
     seqs = []
-    for i in range(a.seqs_per_gpu):
-        X, y = synth.make_sequence(5 + rank * a.seqs_per_gpu + i, a.frames, a.dets, a.dataset)
+    for i in range(count):
+        X, y = synth.make_sequence(seed0 + i, a.frames, a.dets, a.dataset)
         seqs.append((X[0], y[0]))
     return seqs
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per association row of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json)."""
-    p = os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')
+    """DRAM bytes per association row of `kernel` from this round's ncu capture of the shipped library
+    (profiles/r02_dram_traffic.json, written by profiles/make_dram_traffic.py from `ncu --metrics dram__bytes_*`;
+    the file names the kernel, the command and the git revision it was taken at).  Returns (bytes per row, source)."""
+    p = os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')
     try:
         with open(p) as f:
-            return float(json.load(f)[kernel]['dram_bytes_per_edge_row'])
+            d = json.load(f)
+        k = d[kernel]
+        return float(k['dram_bytes_per_edge_row']), (f"profiles/r02_dram_traffic.json: ncu dram__bytes_read+write of {k.get('kernel', kernel)} "
+                                                      f"per association row x rows per launch (captured at {d.get('git', '?')})")
     except Exception:
-        return None
+        return None, None
 
 
 def measured_peaks():
@@ -383,6 +395,38 @@ def run_c1_leg(a, dev):
     return out
 
 
+def run_c4_leg(a, dev):
+    """BASELINE.json configs[3]: stress graph, --cur-win-size 20, ~200 detections / frame (10^5 - 10^7 association rows per
+    window), single-GPU roofline study of the aggregation and the GRU step.  Same engine, same kernels; the reference cannot
+    run this size (dense N x N > host RAM)."""
+    import copy
+    import torch
+    from trackmpnn_b200 import synth
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    b = copy.copy(a)
+    b.win, b.dets, b.frames, b.seqs_per_gpu = a.c4_win, a.c4_dets, a.c4_frames, a.c4_seqs
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories(b.dataset), 64, 0, 'diff').to(dev).eval()
+    seqs = make_sequences(b, 7000, b.seqs_per_gpu)
+    eng = TrackEngine(model, seqs, cur_win_size=b.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph)
+    for _ in range(2):
+        eng.run()
+    eng.results()
+    prepare_passes(eng)
+    r = time_passes(eng, 2)
+    roof, agg, comp, phases = rooflines(b, eng, r, r['ms'])
+    sec = r['ms'] * 1e-3
+    out = {'workload': f'C4 stress graph: {b.seqs_per_gpu} sequences x {b.frames} frames, ~Poisson({b.dets}) dets/frame, win {b.win}, '
+                       'greedy decode, stock init', 'value': r['edges'] / sec, 'unit': 'edge-updates/s', 'frames_per_s': r['frames'] / sec,
+           'edge_rows_per_window_mean': int(roof['edge_rows_per_launch'] / b.seqs_per_gpu), 'cap_rows_per_sequence': eng.cap_rows,
+           'max_detection_rows_per_window': eng.max_dets, 'roofline': roof, 'roofline_aggregation': agg, 'roofline_compaction': comp,
+           'phases': phases['share']}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     """BASELINE.json configs[4]: data-parallel training.  Every rank runs forward + losses + backward of its own
     batch of chunks (batched trainer), the ranks all-reduce ONE flat buffer of all parameter gradients over NCCL
@@ -434,103 +478,80 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
             'replicas_in_sync': bool(abs(hi - lo) <= 1e-9 * max(1.0, abs(hi)))}
 
 
-def main():
-    a = parse()
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if a.impl == 'reference':
-        run_reference(a, rank)
-        return
-
+def prepare_passes(eng):
+    """One more untimed eager pass with the per-launch event lists attached (nvidia-smi starts up meanwhile)."""
     import torch
-    import torch.distributed as dist
-    from trackmpnn_b200 import _lib as L, synth
-    from trackmpnn_b200.engine import TrackEngine
-    from trackmpnn_b200.models.track_mpnn import TrackMPNN
-
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def reduce_(x, op):
-        if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=op)
-            return float(t.item())
-        return float(x)
-
-    torch.manual_seed(5)
-    model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff').to(dev).eval()
-    seqs = make_sequences(a, rank)
-    eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
-                      deferred_compaction=not a.no_deferred)
-
-    # ---- warm-up -------------------------------------------------------------------------
-    for _ in range(max(a.warmup, 1)):
-        eng.run()
-    _, st_w = eng.results()
-
-    # ---- timed region: K full passes, inputs resident in HBM ------------------------------
-    # the edge-row kernel is timed launch by launch with CUDA events (eager launches on the
-    # current stream), so the timed passes do not use CUDA-graph replay
     eng.use_cuda_graph = False
-    eng.profile = []
-    eng.profile_compact = []
-    eng.profile_phases = []
-    clocks = ClockSampler(local)
-    clocks.start()
-    eng.run(); torch.cuda.synchronize()   # one more untimed pass while nvidia-smi starts up
-    barrier(); torch.cuda.synchronize()
-    clocks.mark()
+    eng.profile, eng.profile_compact, eng.profile_phases = [], [], []
+    eng.run(); torch.cuda.synchronize()
+    eng.profile, eng.profile_compact, eng.profile_phases = [], [], []
+
+
+def time_passes(eng, steps, clocks=None):
+    """K eager passes of `eng` bracketed by CUDA events on the current stream (the edge kernel, the aggregation and the
+    window slide are additionally bracketed launch by launch: eng.profile*).  Returns this rank's numbers.  No collective
+    in here: the caller puts a barrier + synchronize on both sides and reduces the numbers over the ranks."""
+    import torch
+    from trackmpnn_b200 import _lib as L
+    if clocks is not None:
+        clocks.mark()
     l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     edges = frames = dets = 0
-    for _ in range(a.steps):
+    for _ in range(steps):
         eng.run()
         edges += eng.edge_updates.clone(); frames += eng.frames_done.clone(); dets += eng.det_updates.clone()
     e1.record()
-    torch.cuda.synchronize(); barrier()
-    clk = clocks.stop()
-    launches = L.launch_count() - l0
-    ms = reduce_(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
-    edges, frames, dets = int(edges.item()), int(frames.item()), int(dets.item())
-    tot_edges = reduce_(edges, dist.ReduceOp.SUM if world > 1 else None)
-    tot_frames = reduce_(frames, dist.ReduceOp.SUM if world > 1 else None)
-    prof = eng.profile
-    eng.profile = None
-    cprof = eng.profile_compact
-    eng.profile_compact = None
-    pprof = eng.profile_phases
-    eng.profile_phases = None
+    torch.cuda.synchronize()
+    out = dict(ms=e0.elapsed_time(e1), edges=int(edges.item()), frames=int(frames.item()), dets=int(dets.item()),
+               launches=L.launch_count() - l0, prof=eng.profile, cprof=eng.profile_compact, pprof=eng.profile_phases)
+    eng.profile = eng.profile_compact = eng.profile_phases = None
     eng.ga.check_status()
+    return out
+
+
+def rooflines(a, eng, r, ms):
+    """The three HBM rooflines of the pass `r` (time_passes): the fused edge step, the detection aggregation, the window slide.
+    `frac` is ALGORITHMIC bytes / time / peak; `frac_dram` is the DRAM traffic an ncu capture of the same
+    kernel measured (profiles/r02_dram_traffic.json, bytes per association row) / time / peak."""
+    prof, cprof, pprof = r['prof'], r['cprof'], r['pprof']
     k_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
     k_edges = sum(int(p[2].item()) for p in prof)
+    fresh = sum(int(p[5].item()) for p in prof)   # association rows appended this frame: state exactly 0, alias the slab's zero row
+    n_l = max(1, len(prof))
     hbm_peak, peak_src = measured_peaks()
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     tk = {'auto': 'pre'}.get(eng.tensor_kernel, eng.tensor_kernel)
-    kname = ({'pre': 'k_det_prepare + k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied '
-                      'by cp.async, tcgen05.mma kind::f16 with a 3-term fp16 split, TMEM accumulators, dedicated MMA issuer warp, '
-                      'two epilogue teams)',
+    kname = ({'pre': 'k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied by cp.async, '
+                     'tcgen05.mma kind::f16 with a 3-term fp16 split, TMEM accumulators, dedicated MMA issuer warp, two epilogue teams)',
               'gather': 'k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'}[tk]
              if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
-    # detection aggregation (K1): every association row's state is read for its two endpoints; compulsory bytes
-    # = one read of each row + one 256 B sum per detection (SURVEY.md 8d "K1")
+    tr_e, src_e = measured_traffic('k_mp_edge_tc3') if eng.tensor else (None, None)
+    tr_a, src_a = measured_traffic('k_aggregate_dets')
+    traffic = tr_e * k_edges / n_l if tr_e else None
+    roof = {'kernel': kname, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            'frac_algorithmic': achieved / hbm_peak,
+            'frac_dram': (traffic / (k_ms / n_l * 1e-3) / 1e9 / hbm_peak) if traffic and k_ms > 0 else None,
+            'traffic': traffic, 'traffic_source': src_e,
+            'algorithmic_bytes_per_launch': BYTES_PER_EDGE_UPDATE * k_edges / n_l,
+            'peak_source': peak_src, 'launches_timed': len(prof), 'avg_launch_ms': k_ms / n_l,
+            'share_of_step': k_ms / ms if ms > 0 else None,
+            'fp32_tflops': FLOP_PER_ROW_UPDATE * k_edges / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
+            'algorithmic_bytes_per_edge_update': BYTES_PER_EDGE_UPDATE, 'edge_rows_per_launch': k_edges / n_l,
+            'fresh_rows_share': fresh / max(1, k_edges)}
+    # detection aggregation (K1): algorithmic bytes = one read of every association row THAT HOLDS STATE (rows appended this
+    # frame are exactly zero and alias one zero row per slab: nothing to read) + one 256 B sum written per detection
     a_ms = sum(p[3].elapsed_time(p[4]) for p in prof)
-    agg_bytes = 256.0 * k_edges + 256.0 * dets
+    agg_bytes = 256.0 * (k_edges - fresh) + 256.0 * r['dets']
+    tr_agg = tr_a * k_edges / n_l if tr_a else None
     agg = {'kernel': 'k_aggregate_dets (CSR segmented signed sum of incident association rows, CTA per detection)',
            'bound': 'hbm', 'achieved': agg_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0, 'peak': hbm_peak, 'unit': 'GB/s',
-           'frac': agg_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak if a_ms > 0 else 0.0, 'avg_launch_ms': a_ms / max(1, len(prof)),
-           'share_of_step': a_ms / ms if ms > 0 else None, 'algorithmic_bytes': '256 B per association row + 256 B per detection',
-           'traffic': None}
+           'frac': agg_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak if a_ms > 0 else 0.0,
+           'frac_dram': (tr_agg / (a_ms / n_l * 1e-3) / 1e9 / hbm_peak) if tr_agg and a_ms > 0 else None,
+           'avg_launch_ms': a_ms / n_l, 'share_of_step': a_ms / ms if ms > 0 else None,
+           'algorithmic_bytes': '256 B per association row that holds state (rows appended this frame are zero and not read) + 256 B per detection',
+           'traffic': tr_agg, 'traffic_source': src_a}
     # window slide (K4): keep-mask scan + order-preserving compaction with index remap.  With deferred compaction
     # the states stay where they are: per surviving row 36 B of metadata are read and written, 12 B of position maps
     # written, 4 B of new_of_old written and read back for the two endpoints; per row 1 B keep flag + 4 B new_of_old.
@@ -554,22 +575,107 @@ def main():
               'reference_share': {'update': 0.20, 'forward': 0.42, 'decode': 0.33},
               'what': 'update = tmpnn_graph_append (+ Hungarian re-association); forward = input transform + incidence index + '
                       'aggregation + association-row and detection-row steps; decode = association + track walk + window slide'}
-    n_l = max(1, len(prof))
-    tr_e, tr_a = (measured_traffic('k_mp_edge_tc3') if eng.tensor else None), measured_traffic('k_aggregate_dets')
-    agg['traffic'] = tr_a * k_edges / n_l if tr_a else None
-    agg['traffic_source'] = 'profiles/r01_dram_traffic.json (ncu dram bytes per association row x rows per launch)'
-    roof = {'kernel': kname, 'bound': 'hbm',
-            'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-            'traffic': tr_e * k_edges / n_l if tr_e else None,
-            'traffic_source': 'profiles/r01_dram_traffic.json (ncu dram bytes per association row x rows per launch)',
-            'algorithmic_bytes_per_launch': BYTES_PER_EDGE_UPDATE * k_edges / n_l,
-            'peak_source': peak_src, 'launches_timed': len(prof), 'avg_launch_ms': k_ms / max(1, len(prof)),
-            'share_of_step': k_ms / ms if ms > 0 else None,
-            'fp32_tflops': FLOP_PER_ROW_UPDATE * k_edges / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
-            'algorithmic_bytes_per_edge_update': BYTES_PER_EDGE_UPDATE}
+    return roof, agg, comp, phases
 
-    # ---- end to end: host buffers in, decoded tracks out, copies inside the timed region ---
-    e2e = None
+
+def sharding_check(a, dev, rank, world):
+    """Identical per-sequence tracks whatever GPU and batch a sequence lands in: every rank tracks
+    the SAME two check sequences inside a batch of its own (rank-specific) other sequences, with decision-exercising weights
+    (x20, edge-head bias 0) so that associations, chain walks and deletions all carry load; rank 0 additionally tracks the two
+    alone.  Returns this rank's track arrays of the two sequences (int32 tensor on `dev`) and rank 0's stand-alone ones."""
+    import torch
+    from trackmpnn_b200 import synth
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff')
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(20.0)
+        model.output_transform_edge.bias.fill_(0.0)
+    model = model.to(dev).eval()
+    frames = min(a.frames, 30)
+
+    def seq(seed):
+        X, y = synth.make_sequence(seed, frames, a.dets, a.dataset)
+        return X[0], y[0]
+
+    check = [seq(90001), seq(90002)]
+    mine = [seq(91000 + 10 * rank + i) for i in range(1 + rank % 3)]
+    eng = TrackEngine(model, mine[:1] + check + mine[1:], cur_win_size=a.win, ret_win_size=0)
+    outs, _ = eng.run().results()
+    got = np.concatenate(outs[1:3]).astype(np.int32)
+    alone = None
+    if rank == 0:
+        outs0, _ = TrackEngine(model, check, cur_win_size=a.win, ret_win_size=0).run().results()
+        alone = np.concatenate(outs0).astype(np.int32)
+    del eng
+    return torch.from_numpy(got).to(dev), alone
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if a.impl == 'reference':
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from trackmpnn_b200 import parallel, synth
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    # Every collective of this program is issued from main()'s top level by ALL ranks (tests/test_bench_collectives.py
+    # checks that none sits under a rank test): a reduction only rank 0 joins hangs until the NCCL watchdog aborts.
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def reduce_(x, op):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=op)
+            return float(t.item())
+        return float(x)
+
+    MAX, SUM, MIN = dist.ReduceOp.MAX, dist.ReduceOp.SUM, dist.ReduceOp.MIN
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff').to(dev).eval()
+
+    # ---- weak-scaling leg (the headline line): --seqs-per-gpu sequences on EVERY rank ------------------------------------
+    seqs = make_sequences(a, 5 + rank * a.seqs_per_gpu, a.seqs_per_gpu)
+    eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
+                      deferred_compaction=not a.no_deferred)
+    for _ in range(max(a.warmup, 1)):
+        eng.run()
+    eng.results()
+    clocks = ClockSampler(local)
+    clocks.start()
+    prepare_passes(eng)
+    barrier(); torch.cuda.synchronize()
+    r = time_passes(eng, a.steps, clocks)
+    barrier()
+    clk = clocks.stop()
+    ms = reduce_(r['ms'], MAX)
+    tot_edges = reduce_(r['edges'], SUM)
+    tot_frames = reduce_(r['frames'], SUM)
+    tot_dets = reduce_(r['dets'], SUM)
+    roof, agg, comp, phases = rooflines(a, eng, r, r['ms'])
+    cap_rows, deferred = eng.cap_rows, eng.deferred
+
+    # ---- end to end: host buffers in, decoded tracks out, copies inside the timed region ---------------------------------
+    e2e_dt = e2e_edges = h2d = d2h = 0
     if not a.skip_e2e:
         eng.use_cuda_graph = not a.no_cuda_graph
         x_host = eng.frames.x.cpu().pin_memory()
@@ -579,7 +685,6 @@ def main():
         d2h = out_host.numel() * 4
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e_edges = 0
         for _ in range(a.steps):
             eng.frames.x.copy_(x_host, non_blocking=True)
             for dst, src in zip((eng.frames.frame_ptr, eng.frames.frame_dets, eng.frames.det_ptr), tab_host):
@@ -587,16 +692,74 @@ def main():
             eng.run()
             out_host.copy_(eng.y_out_track, non_blocking=True)
             torch.cuda.synchronize()
-            e_edges += int(eng.edge_updates.item())
-        dt = time.perf_counter() - t0
+            e2e_edges += int(eng.edge_updates.item())
+        e2e_dt = time.perf_counter() - t0
         barrier()
-        dt = reduce_(dt, dist.ReduceOp.MAX if world > 1 else None)
-        e_tot = reduce_(e_edges, dist.ReduceOp.SUM if world > 1 else None)
-        e2e = {'value': e_tot / dt, 'unit': 'edge-updates/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'ms_per_step': 1e3 * dt / a.steps, 'api': 'TrackEngine.run() + results copy, CUDA-graph replay'}
+    e2e_dt = reduce_(e2e_dt, MAX)
+    e2e_tot = reduce_(e2e_edges, SUM)
+    e2e = None
+    if not a.skip_e2e:
+        e2e = {'value': e2e_tot / e2e_dt, 'unit': 'edge-updates/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': 1e3 * e2e_dt / a.steps, 'api': 'TrackEngine.run() + results copy, CUDA-graph replay'}
+    del eng
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------
-    cpu = None
+    # ---- strong-scaling leg: BASELINE.json configs[2] literally -- --seqs-per-gpu sequences IN TOTAL, bin-packed onto the
+    # ranks by cost (parallel.partition_sequences over parallel.sequence_cost); at N = 1 it is the weak leg ----------------
+    strong = None
+    if world > 1 and not a.skip_strong:
+        all_seqs = seqs if rank == 0 else make_sequences(a, 5, a.seqs_per_gpu)
+        costs = [parallel.sequence_cost(np.bincount(np.asarray(y)[:, 0].astype(np.int64)), a.win) for _, y in all_seqs]
+        bins = parallel.partition_sequences(costs, world)
+        load = [sum(costs[i] for i in b) for b in bins]
+        eng = TrackEngine(model, [all_seqs[i] for i in bins[rank]], cur_win_size=a.win, ret_win_size=0,
+                          use_cuda_graph=not a.no_cuda_graph, deferred_compaction=not a.no_deferred)
+        for _ in range(max(a.warmup, 1)):
+            eng.run()
+        eng.results()
+        prepare_passes(eng)
+        barrier(); torch.cuda.synchronize()
+        rs = time_passes(eng, a.steps)
+        barrier()
+        s_roof = rooflines(a, eng, rs, rs['ms'])[0]
+        del eng, all_seqs
+        torch.cuda.empty_cache()
+    else:
+        rs, bins, load, s_roof = dict(ms=0.0, edges=0, frames=0), None, None, None
+    s_ms = reduce_(rs['ms'], MAX)
+    s_ms_min = reduce_(rs['ms'], MIN)
+    s_edges = reduce_(rs['edges'], SUM)
+    s_frames = reduce_(rs['frames'], SUM)
+    if bins is not None:
+        strong = {'workload': f'{a.seqs_per_gpu} sequences in total, bin-packed onto {world} ranks by sum_t D_t x (detections of the '
+                              f'previous {a.win - 1} frames) (longest-processing-time first)',
+                  'value': s_edges / (s_ms * 1e-3), 'unit': 'edge-updates/s', 'frames_per_s': s_frames / (s_ms * 1e-3),
+                  'ms_per_step': s_ms / a.steps, 'ms_per_step_fastest_rank': s_ms_min / a.steps,
+                  'sequences_per_rank': [len(b) for b in bins], 'cost_imbalance': max(load) / (sum(load) / world),
+                  'rank0_edge_kernel_frac': s_roof['frac'], 'rank0_edge_kernel_share_of_step': s_roof['share_of_step'],
+                  'scaling': 'strong'}
+    del seqs
+
+    # ---- the same sequence gives the same tracks on every GPU, in every batch --------------------------------------------
+    sharding_identical = None
+    chk_info = None
+    if not a.skip_check:
+        got, alone = sharding_check(a, dev, rank, world)
+        if world > 1:
+            gathered = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(gathered, got)
+        else:
+            gathered = [got]
+        if rank == 0:
+            per_rank = [t.cpu().numpy() for t in gathered]
+            sharding_identical = bool(all(np.array_equal(p, alone) for p in per_rank))
+            chk_info = {'identical': sharding_identical, 'ranks_compared': world, 'detections_compared': int(alone.size),
+                        'tracks': int(alone.max()) + 1, 'multi_detection_tracks': int((np.bincount(alone[alone >= 0]) > 1).sum()),
+                        'what': 'two check sequences tracked on every rank inside a rank-specific batch (x20 weights, edge-head bias 0) '
+                                'and alone on rank 0: track ids compared bit for bit'}
+
+    # ---- side legs ------------------------------------------------------------------------------------------------------
+    cpu = train = c1 = None
     if rank == 0 and world == 1 and not a.skip_cpu:
         frames_cap = a.cpu_frames or 60
         stc, dtc = cpu_oracle_sample(a, frames_cap)
@@ -604,15 +767,12 @@ def main():
                'frames_per_s': stc['frames'] / dtc, 'seconds': dtc,
                'sample': f'1 sequence of the workload, first {frames_cap} frames (oracle port: numpy BLAS threads for '
                          f'the GEMMs, one thread for graph bookkeeping)'}
-
-    train = None
     if rank == 0 and world == 1 and not a.skip_train:
         train = run_train_leg(a, dev)
-
-    c1 = None
-    if rank == 0 and world == 1 and not a.skip_train:
         c1 = run_c1_leg(a, dev)
-
+    c4 = None
+    if rank == 0 and world == 1 and not a.skip_c4:
+        c4 = run_c4_leg(a, dev)
     train_ddp = None
     if world > 1 and not a.skip_train:
         train_ddp = run_train_ddp_leg(a, dev, rank, world, barrier, reduce_)
@@ -624,13 +784,18 @@ def main():
                'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': workload_name(a), 'l2': 'inputs_larger_than_l2 (state >= 4 GB per GPU vs 126 MB L2)',
-                          'edge_rows_per_step_per_gpu': edges // max(1, a.steps), 'det_rows_per_step_per_gpu': dets // max(1, a.steps),
-                          'frames_per_step_per_gpu': frames // max(1, a.steps), 'cap_rows_per_sequence': eng.cap_rows, 'deferred_compaction': eng.deferred,
-                          'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)'},
-               'det_updates_per_s': reduce_(dets, dist.ReduceOp.SUM if world > 1 else None) / (ms * 1e-3), 'phases': phases,
-               'roofline': roof, 'roofline_aggregation': agg, 'roofline_compaction': comp, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'c1': c1, 'train': train, 'train_ddp': train_ddp}
+                          'edge_rows_per_step_per_gpu': r['edges'] // max(1, a.steps), 'det_rows_per_step_per_gpu': r['dets'] // max(1, a.steps),
+                          'frames_per_step_per_gpu': r['frames'] // max(1, a.steps), 'cap_rows_per_sequence': cap_rows,
+                          'deferred_compaction': deferred, 'timed_passes': 'eager launches (edge kernel bracketed by CUDA events)',
+                          'cpu_baseline_kind': 'port: the reference is Python and is not on the bench box; the CPU arm times the '
+                                               'numpy oracle port, which is ~100x faster than the reference own dense N x N code'},
+               'det_updates_per_s': tot_dets / sec, 'phases': phases,
+               'roofline': roof, 'roofline_aggregation': agg, 'roofline_compaction': comp, 'cpu_baseline': cpu, 'e2e': e2e,
+               'gpu_launches': int(r['launches']), 'clocks': clk, 'strong': strong, 'sharding_identical': sharding_identical,
+               'sharding_check': chk_info, 'c1': c1, 'train': train, 'c4': c4, 'train_ddp': train_ddp}
         print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

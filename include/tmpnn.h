@@ -59,6 +59,7 @@ typedef enum tmpnn_status {
 #define TMPNN_FLAG_TC_TIMEOUT 64    /* tensor-core kernel: an mbarrier wait timed out (results invalid) */
 #define TMPNN_FLAG_UNSTRUCTURED 256 /* tmpnn_index_build_structured: the window graph is not a chain of dense edge blocks */
 #define TMPNN_FLAG_TC_RANGE 128     /* tensor-core kernel: |value| > 6e4 would overflow the fp16 split; use the FMA path */
+#define TMPNN_NOTE_TC_RANGE_RERUN 512 /* not an error: a step hit TMPNN_FLAG_TC_RANGE and was re-run by the fp32 FMA kernel */
 
 typedef struct tmpnn_graph {
   int32_t num_seqs;   /* S */
@@ -222,6 +223,14 @@ int tmpnn_mp_edge_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *
                       int group, int num_groups, int concat, const float *edge_pack, void *stream);
 int tmpnn_mp_det_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                      int group, int num_groups, const float *node_pack, const float *agg, void *stream);
+
+/* tmpnn_mp_edge_fwd that only runs when the sticky status word holds one of flag_mask at launch time (the test is made on
+ * the device, so the call can sit in a CUDA graph): the engine enqueues it behind the tensor-core step with
+ * flag_mask = TMPNN_FLAG_TC_RANGE, which re-runs a step whose activations left the fp16 split's range on the fp32 FMA
+ * kernel (both are this library's kernels; for num_groups > 1 re-run every group, group 0 first: the logit accumulates
+ * over the groups), followed by tmpnn_status_ack(g, TMPNN_FLAG_TC_RANGE, TMPNN_NOTE_TC_RANGE_RERUN). */
+int tmpnn_mp_edge_fwd_on_flag(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                              int group, int num_groups, int concat, const float *edge_pack, int flag_mask, void *stream);
 
 /* Tensor-core form of tmpnn_mp_edge_fwd for msg_type 'diff' (tcgen05.mma kind::f16, 3-term fp16
  * split of activations and weights, accumulators in TMEM; csrc/mp_step_tc.cu).  edge_image is the
@@ -431,11 +440,24 @@ size_t tmpnn_graph_append_scratch_ints(int num_seqs, int cap_rows);
  * y_out_track[det_ptr[s] + d] is the reference's y_out[d,1]; next_track_id[s] its running
  * max+1.  t_upto = t_upto_seq[s] when given, else t_upto_host.  Sequences with active[s] == 0
  * (when active != NULL) keep every row.  Writes keep[row] in {0,1} for all rows in use.
- * Needs a fresh index and tmpnn_graph_associate first.  scratch: num_seqs ints. */
+ * Needs a fresh index and tmpnn_graph_associate first.  max_dets: the caller's bound of the detection rows one
+ * window can hold (<= 0: unknown, windows of up to 4096 detection rows); the walk's per-detection arrays live in shared
+ * memory up to 8192 detection rows and in `scratch` beyond (no limit; stress windows of BASELINE configs[3] and larger).
+ * scratch: tmpnn_graph_decode_scratch_ints(num_seqs, max_dets) ints.  A window that exceeds max_dets raises
+ * TMPNN_FLAG_WALK_CAPACITY. */
+size_t tmpnn_graph_decode_scratch_ints(int num_seqs, int max_dets);
 int tmpnn_graph_decode(const tmpnn_graph *g, const tmpnn_index *ix, const tmpnn_frames *fr,
                        int32_t *y_out_track, int32_t *next_track_id, const int32_t *t_upto_seq,
-                       int t_upto_host, const int32_t *active, int ret_win_size, uint8_t *keep,
+                       int t_upto_host, const int32_t *active, int ret_win_size, uint8_t *keep, int max_dets,
                        int32_t *scratch, void *stream);
+
+/* --no-tp-classifier (infer.py:54-57, 77-80): every detection row of the index gets score p = 1 (scores row (0, 1))
+ * before association and decoding; logits are left alone. */
+int tmpnn_graph_force_det_scores(const tmpnn_graph *g, const tmpnn_index *ix, void *stream);
+
+/* Sticky status word: if any of from_bits is set, clears them and sets to_bits (a condition that was handled on the
+ * device -- e.g. TMPNN_FLAG_TC_RANGE after the step was re-run by tmpnn_mp_edge_fwd_on_flag -- becomes a note). */
+int tmpnn_status_ack(const tmpnn_graph *g, int from_bits, int to_bits, void *stream);
 
 /* prune_graph mask (utils/graph.py:361-377): keep = p >= thr || detection || row < first || row > last
  * detection row with t_st <= ts <= t_ed. */

@@ -226,3 +226,169 @@ def test_engine_reports_capacity_overflow():
     eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, cap_rows=48)
     with pytest.raises(L.TmpnnError, match='capacity'):
         eng.run().results()
+
+
+# (seed, frames, detections / frame) chosen on the oracle: no score within 5e-4 of the 0.5 decision threshold
+WIDE = {
+    'w8': dict(win=8, ret=1, seqs=[(208, 20, 3), (210, 20, 3), (212, 20, 3), (214, 20, 3), (216, 20, 3), (218, 20, 3), (219, 20, 3)]),
+    'w8_hungarian': dict(win=8, ret=2, hungarian=True, seqs=[(300, 29, 3), (324, 26, 3), (342, 26, 3), (378, 26, 3), (387, 26, 3)]),
+    'w12': dict(win=12, ret=0, seqs=[(300, 29, 3), (486, 26, 3), (507, 29, 3), (534, 29, 3), (600, 32, 3)]),
+    'w20': dict(win=20, ret=3, seqs=[(218, 30, 3), (244, 30, 3), (486, 26, 3), (507, 29, 3)]),
+    # stock init: nothing is ever associated, the window holds every detection of 20 frames and all pairs between them
+    'w20_stock': dict(win=20, ret=0, stock=True, seqs=[(801, 30, 6), (802, 27, 5)]),
+    'w20_stock_tensor': dict(win=20, ret=2, stock=True, tensor=True, seqs=[(803, 30, 6), (804, 27, 5), (805, 24, 7)]),
+}
+
+
+@pytest.mark.parametrize('name', sorted(WIDE))
+@pytest.mark.parametrize('graph', [False, True])
+def test_engine_wide_windows(name, graph):
+    """--cur-win-size 8 / 12 / 20 (BASELINE configs[3] uses 20) with retention windows: decoded tracks bit-exact against the
+    oracle loop, work counters equal (reference infer.py:82-87: t_upto = t_cur - cur_win_size + 2)."""
+    from trackmpnn_b200.engine import TrackEngine
+    cfg = WIDE[name]
+    dev = torch.device('cuda:0')
+    stock = cfg.get('stock', False)
+    model = _model(dev, scale=1.0 if stock else 20.0, edge_bias=None if stock else 0.0)
+    params = _params(model)
+    seqs = []
+    for sd, T, D in cfg['seqs']:
+        X, y = synth.make_sequence(sd, T, D, 'kitti')
+        seqs.append((X[0], y[0]))
+    eng = TrackEngine(model, seqs, cur_win_size=cfg['win'], ret_win_size=cfg['ret'], use_cuda_graph=graph,
+                      tensor_cores=cfg.get('tensor', False), use_hungarian=cfg.get('hungarian', False))
+    outs, stats = eng.run().results()
+    tot_e = tot_f = 0
+    for (X, y), got in zip(seqs, outs):
+        want, st = run_infer(params, X, y, cur_win_size=cfg['win'], ret_win_size=cfg['ret'], record_margin=True,
+                             use_hungarian=cfg.get('hungarian', False))
+        assert stock or st['margin'] > 1e-4, 'decision margin too small for a meaningful bit-exact comparison; change the seed'
+        np.testing.assert_array_equal(got, want[:, 1])
+        tot_e += st['edge_updates']; tot_f += st['frames']
+    assert stats['edge_updates'] == tot_e and stats['frames'] == tot_f
+
+
+@pytest.mark.parametrize('n_frame', [1500, 3000])
+def test_decode_walk_beyond_shared_memory(n_frame):
+    """Windows with more detection rows than the walk's shared-memory arrays hold (4096 by default, 8192 at most): 3 frames of
+    1500 (4500 rows: the large shared-memory launch) / 3000 (9000 rows: global-memory scratch) detections joined by random
+    association rows; decode_tracks through the drop-in API against the oracle: track ids and the surviving graph bit-exact."""
+    from trackmpnn_b200.device_graph import WindowGraph
+    from trackmpnn_b200.utils.graph import decode_tracks
+    dev = torch.device('cuda:0')
+    rs = np.random.RandomState(n_frame)
+    n_e = 700
+    ts, det, src, dst = [], [], [], []
+    row0 = {}
+    n = 0
+    for t in range(3):
+        if t > 0:   # association rows into frame t, sorted by (source, target) like the reference's blocks
+            s_rows = np.concatenate([row0[u] + np.arange(n_frame) for u in range(t)])
+            pairs = sorted(set(zip(rs.choice(s_rows, n_e).tolist(), rs.randint(n_frame, size=n_e).tolist())))
+            tgt0 = n + len(pairs)
+            for a, j in pairs:
+                ts.append(-1); det.append(-1); src.append(a); dst.append(tgt0 + j)
+            n += len(pairs)
+        row0[t] = n
+        for j in range(n_frame):
+            ts.append(t); det.append(t * n_frame + j); src.append(-1); dst.append(-1)
+        n += n_frame
+    ts, det, src, dst = (np.asarray(v, np.int64) for v in (ts, det, src, dst))
+    p = rs.uniform(0.0, 1.0, n).astype(np.float32)
+    p[np.abs(p - 0.5) < 1e-3] = 0.9
+    scores = np.stack((1 - p, p), 1).astype(np.float32)
+    states = rs.normal(size=(n, 64)).astype(np.float32)
+    wg = WindowGraph(n, n, dev, with_labels=True)
+    for name, v in (('ts', ts), ('det', det), ('src', src), ('dst', dst)):
+        getattr(wg.g, name)[:n] = torch.from_numpy(v.astype(np.int32)).to(dev)
+    wg.g.ass[:n] = -1
+    y_out = np.stack((np.repeat(np.arange(3), n_frame), np.full(3 * n_frame, -1)), 1).astype(np.int64)
+    y_out_o = y_out.copy()
+    g = O.Graph(ts, det, np.full(n, -1, np.int64), src, dst, np.zeros(n, np.int64))
+    g_o, y_out_o, h_o, sc_o, _ = O.decode_tracks(g, states, scores, y_out_o, 2, 1, False)
+    y_pred, y_out, h, node_adj, labels, sc = decode_tracks(
+        torch.from_numpy(states).to(dev), wg.adjacency(False), wg.labels(), torch.from_numpy(scores).to(dev), wg.y_pred(),
+        y_out, 2, 1, use_hungraian=False, cuda=True)
+    np.testing.assert_array_equal(y_out, y_out_o)
+    assert (np.bincount(y_out[:, 1][y_out[:, 1] >= 0]) > 1).sum() > 50   # chains were walked
+    np.testing.assert_array_equal(y_pred.cpu().numpy(), g_o.y_pred())
+    np.testing.assert_array_equal(h.cpu().numpy(), h_o)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_engine_no_tp_classifier(graph):
+    """infer.py's --no-tp-classifier (infer.py:54-57, 77-80): detection scores forced to (0, 1) before association and
+    decoding.  Seeds 40 / 77 / 80 decode differently with and without the classifier (checked on the oracle)."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    params = _params(model)
+    seqs = _sequences([34, 36, 40, 61, 65, 68, 77, 80])
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=1, use_cuda_graph=graph, tp_classifier=False)
+    outs, stats = eng.run().results()
+    differs = 0
+    for (X, y), got in zip(seqs, outs):
+        want, st = run_infer(params, X, y, cur_win_size=5, ret_win_size=1, record_margin=True, tp_classifier=False)
+        assert st['margin'] > 1e-4
+        np.testing.assert_array_equal(got, want[:, 1])
+        with_tp, _ = run_infer(params, X, y, cur_win_size=5, ret_win_size=1)
+        differs += int((with_tp[:, 1] != want[:, 1]).any())
+    assert differs >= 2
+
+
+def test_engine_recaptures_after_weight_change():
+    """A captured CUDA graph bakes in the pointers of the packed weight images; after an in-place parameter update
+    (optimizer.step, load_state_dict) the engine must re-capture instead of replaying stale images: a re-used engine
+    equals a fresh one bit for bit, before and after the change."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev)
+    seqs = _sequences([30, 34, 48, 58, 65, 72, 77])
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=True)
+    outs0, stats0 = eng.run().results()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(0.8)
+        model.output_transform_edge.bias.add_(0.3)
+    outs1, stats1 = eng.run().results()
+    fresh = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False)
+    outs2, stats2 = fresh.run().results()
+    assert stats1 == stats2
+    for a, b in zip(outs1, outs2):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(eng.ga.score.cpu().numpy()[:64], fresh.ga.score.cpu().numpy()[:64])
+    assert any((a != b).any() for a, b in zip(outs0, outs1)) or stats0 != stats1, 'the weight change should change the tracking'
+    # load_state_dict copies in place as well
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        model.output_transform_edge.bias.add_(-0.3)
+    eng.run().results()
+    model.load_state_dict(sd)
+    outs3, stats3 = eng.run().results()
+    assert stats3 == stats1
+    for a, b in zip(outs1, outs3):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_tensor_core_range_overflow_reruns_on_fma():
+    """States beyond the fp16 split's range (|h| > 6e4): the tensor-core step raises TMPNN_FLAG_TC_RANGE on the device and
+    the conditional FMA launch behind it re-runs the association rows; the result equals the FMA engine's and results()
+    reports a note instead of raising."""
+    from trackmpnn_b200 import _lib as L
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev, scale=1.0, edge_bias=None)
+    with torch.no_grad():   # a huge second Linear of the input transform: detection states of ~1e5
+        model.input_transforms[0][3].weight.mul_(3e7)
+    seqs = _sequences([30, 34, 48, 58])
+    a = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=True)
+    b = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=False)
+    a.run(max_ticks=2); b.run(max_ticks=2)
+    outs_a, _ = a.results()
+    b.results()
+    assert a.ga.notes & L.NOTE_TC_RANGE_RERUN and not (b.ga.notes & L.NOTE_TC_RANGE_RERUN)
+    assert float(torch.maximum(a.h_cur.abs().max(), a.h_alt.abs().max())) > 6e4
+    n = int(a.ga.n_rows[0])
+    np.testing.assert_array_equal(a.ga.logit[:n].cpu().numpy(), b.ga.logit[:n].cpu().numpy())
+    np.testing.assert_array_equal(a.h_cur[a.ga.phys[:n].long()].cpu().numpy(), b.h_cur[b.ga.phys[:n].long()].cpu().numpy())

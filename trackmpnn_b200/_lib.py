@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, 'libtmpnn_sm100a.so')
 TILE_ROWS = 64
 HIDDEN = 64
 
+FLAG_TC_RANGE = 128
+NOTE_TC_RANGE_RERUN = 512   # not an error: a tensor-core step left the fp16 split's range and was re-run on the FMA kernel
 FLAG_NAMES = {
     1: 'row capacity of a slab exceeded (tmpnn_graph_append)',
     2: 'detection-row capacity of the index exceeded',
@@ -87,6 +89,9 @@ _PROTOS = {
     'tmpnn_aggregate_edges': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _I, _VP, _VP], _I),
     'tmpnn_mp_step_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_edge_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP], _I),
+    'tmpnn_mp_edge_fwd_on_flag': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP], _I),
+    'tmpnn_graph_force_det_scores': ([C.POINTER(Graph), C.POINTER(Index), _VP], _I),
+    'tmpnn_status_ack': ([C.POINTER(Graph), _I, _I, _VP], _I),
     'tmpnn_mp_det_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _VP], _I),
     'tmpnn_gru_tc_pack_bytes': ([], C.c_size_t),
     'tmpnn_pack_gru_tc': ([_VP] * 6 + [_I, _VP, _VP], _I),
@@ -120,8 +125,9 @@ _PROTOS = {
     'tmpnn_graph_append_scratch_ints': ([_I, _I], C.c_size_t),
     'tmpnn_graph_append': ([C.POINTER(Graph), C.POINTER(Frames), C.POINTER(SeqState), _VP, _I, _I, _I, _VP, _I,
                             _VP, _VP, _VP, _I, _VP, _VP, _VP], _I),
+    'tmpnn_graph_decode_scratch_ints': ([_I, _I], C.c_size_t),
     'tmpnn_graph_decode': ([C.POINTER(Graph), C.POINTER(Index), C.POINTER(Frames), _VP, _VP, _VP, _I, _VP, _I,
-                            _VP, _VP, _VP], _I),
+                            _VP, _I, _VP, _VP], _I),
     'tmpnn_graph_prune_mask': ([C.POINTER(Graph), C.POINTER(Index), _I, _I, C.c_float, _VP, _VP, _VP], _I),
     'tmpnn_graph_phys_identity': ([C.POINTER(Graph), _VP], _I),
     'tmpnn_graph_compact_scratch_ints': ([_I, _I], C.c_size_t),
@@ -183,7 +189,8 @@ KERNELS_PER_CALL = {
     'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 12, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
-    'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1,
+    'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1, 'tmpnn_mp_edge_fwd_on_flag': 1, 'tmpnn_graph_force_det_scores': 1,
+    'tmpnn_status_ack': 1,
     'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_build_features': 1, 'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,

@@ -18,7 +18,12 @@
 namespace {
 
 constexpr int ROWS_PER_BLOCK = 1024;
-constexpr int WALK_CAP = 4096;  // detection rows of one window the decode walk holds in shared memory
+// The decode walk keeps six ints per detection row of the window.  They live in shared memory up to
+// WALK_SMEM_MAX detection rows (196 KB of the 227 KB an sm_100a CTA can have; the launch sizes the buffer from the
+// caller's bound max_dets, so ordinary windows keep several CTAs per SM) and in a global-memory scratch beyond that --
+// same sort, same sequential walk (utils/graph.py:456-490), no capacity limit.
+constexpr int WALK_SMEM_DEFAULT = 4096;
+constexpr int WALK_SMEM_MAX = 8192;
 
 __device__ __forceinline__ bool seq_off(const int32_t* active, int s) { return active && !active[s]; }
 
@@ -75,6 +80,19 @@ __global__ void k_edges_from_coo(const int64_t* __restrict__ idx, const float* _
     if (v > 0.f) src[r] = (int32_t)c;
     else if (v < 0.f) dst[r] = (int32_t)c;
   }
+}
+
+// infer.py:54-57, 77-80 (--no-tp-classifier): detection rows count as true positives, scores (0, 1)
+__global__ void k_force_det_scores(const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows,
+                                   float* __restrict__ score) {
+  const int nd = *n_dets;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) score[det_rows[k]] = 1.0f;
+}
+
+// moves the bits `from` of the sticky status word to `to` (a handled condition becomes a note)
+__global__ void k_status_ack(int32_t* status, int from, int to) {
+  const int v = *status;
+  if (v & from) *status = (v & ~from) | to;
 }
 
 // ---- association -----------------------------------------------------------------------------
@@ -419,22 +437,29 @@ k_append_fill(tmpnn_graph g, tmpnn_frames fr, const int32_t* __restrict__ act, c
 }
 
 // ---- decode ------------------------------------------------------------------------------------
-struct WalkSmem {
-  int32_t key[WALK_CAP];   // detection id (sort key)
-  int32_t idx[WALK_CAP];   // position in det_rows
-  int32_t ts[WALK_CAP];
-  int32_t nxt[WALK_CAP];
-  int32_t yo[WALK_CAP];
-  int32_t flag[WALK_CAP];  // bit0: p >= 0.5, bit1: visited
+struct WalkArrays {
+  int32_t* key;   // detection id (sort key)
+  int32_t* idx;   // position in det_rows
+  int32_t* ts;
+  int32_t* nxt;
+  int32_t* yo;
+  int32_t* flag;  // bit0: p >= 0.5, bit1: visited
 };
+__device__ __forceinline__ WalkArrays walk_arrays(int32_t* base, int cap) {
+  return WalkArrays{base, base + cap, base + 2 * cap, base + 3 * cap, base + 4 * cap, base + 5 * cap};
+}
+__host__ __device__ inline int pow2_ceil(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
 
 __global__ void __launch_bounds__(256)
 k_decode(tmpnn_graph g, const int32_t* __restrict__ seq_det_ptr, const int32_t* __restrict__ det_rows,
          const int32_t* __restrict__ det_ptr, int32_t* __restrict__ y_out_track, int32_t* __restrict__ next_track_id,
          const int32_t* __restrict__ t_upto_seq, int t_upto_host, const int32_t* __restrict__ active, int ret_win,
-         uint8_t* __restrict__ keep, int32_t* __restrict__ max_id_out) {
+         uint8_t* __restrict__ keep, int32_t* __restrict__ max_id_out, int smem_cap, int32_t* __restrict__ gwalk, int gwalk_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WalkSmem& w = *reinterpret_cast<WalkSmem*>(smem_raw);
   __shared__ int s_unsorted, s_maxid;
   const int s = blockIdx.x;
   if (seq_off(active, s)) {
@@ -446,12 +471,16 @@ k_decode(tmpnn_graph g, const int32_t* __restrict__ seq_det_ptr, const int32_t* 
   const size_t base = (size_t)s * g.cap_rows;
   if (threadIdx.x == 0) { s_unsorted = 0; s_maxid = 0; }
   __syncthreads();
-  if (nd > WALK_CAP) {
+  const int p2 = pow2_ceil(nd);
+  WalkArrays w;
+  if (p2 <= smem_cap) {
+    w = walk_arrays(reinterpret_cast<int32_t*>(smem_raw), smem_cap);
+  } else if (gwalk && p2 <= gwalk_cap) {  // a window with more detection rows than shared memory holds: walk out of global memory
+    w = walk_arrays(gwalk + (size_t)s * 6 * gwalk_cap, gwalk_cap);
+  } else {
     if (threadIdx.x == 0) { atomicOr(g.status, TMPNN_FLAG_WALK_CAPACITY); max_id_out[s] = -1; }
     return;
   }
-  int p2 = 1;
-  while (p2 < nd) p2 <<= 1;
   for (int i = threadIdx.x; i < p2; i += blockDim.x) {
     if (i < nd) {
       const int v = g.det[det_rows[k0 + i]];
@@ -698,7 +727,7 @@ inline dim3 stride_grid(const tmpnn_graph* g) {
 
 static bool g_graph_init_done = false;
 int tmpnn_init_graph_ops() {
-  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 4 * WALK_SMEM_MAX));
   g_graph_init_done = true;
   return TMPNN_OK;
 }
@@ -794,18 +823,48 @@ extern "C" int tmpnn_graph_append(const tmpnn_graph* g, const tmpnn_frames* fr, 
   return TMPNN_OK;
 }
 
+// shared-memory capacity (detection rows, a power of two) the walk is launched with for windows of up to max_dets
+// detection rows (max_dets <= 0: unknown)
+static int walk_smem_cap(int max_dets) {
+  if (max_dets <= 0 || max_dets > WALK_SMEM_MAX) return WALK_SMEM_DEFAULT;
+  return max(256, pow2_ceil(max_dets));
+}
+extern "C" size_t tmpnn_graph_decode_scratch_ints(int num_seqs, int max_dets) {
+  size_t n = (size_t)max(num_seqs, 1) + 4;
+  if (max_dets > WALK_SMEM_MAX) n += (size_t)6 * pow2_ceil(max_dets) * max(num_seqs, 1);
+  return n;
+}
+
 extern "C" int tmpnn_graph_decode(const tmpnn_graph* g, const tmpnn_index* ix, const tmpnn_frames* fr,
                                   int32_t* y_out_track, int32_t* next_track_id, const int32_t* t_upto_seq,
-                                  int t_upto_host, const int32_t* active, int ret_win_size, uint8_t* keep,
+                                  int t_upto_host, const int32_t* active, int ret_win_size, uint8_t* keep, int max_dets,
                                   int32_t* scratch, void* stream) {
   TMPNN_REQUIRE(g && ix && fr && y_out_track && next_track_id && keep && scratch, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (!g_graph_init_done) { int rc0 = tmpnn_init_graph_ops(); if (rc0) return rc0; }
-  k_decode<<<g->num_seqs, 256, sizeof(WalkSmem), st>>>(*g, ix->seq_det_ptr, ix->det_rows, fr->det_ptr, y_out_track,
-                                                      next_track_id, t_upto_seq, t_upto_host, active, ret_win_size, keep,
-                                                      scratch);
+  const int smem_cap = walk_smem_cap(max_dets);
+  const bool spill = max_dets > WALK_SMEM_MAX;
+  int32_t* gwalk = spill ? scratch + g->num_seqs + 4 : nullptr;
+  k_decode<<<g->num_seqs, 256, (size_t)6 * 4 * smem_cap, st>>>(*g, ix->seq_det_ptr, ix->det_rows, fr->det_ptr, y_out_track,
+                                                             next_track_id, t_upto_seq, t_upto_host, active, ret_win_size,
+                                                             keep, scratch, smem_cap, gwalk, spill ? pow2_ceil(max_dets) : 0);
   TMPNN_LAUNCH_CHECK();
   k_keep_edges<<<stride_grid(g), 256, 0, st>>>(*g, scratch, keep);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_graph_force_det_scores(const tmpnn_graph* g, const tmpnn_index* ix, void* stream) {
+  TMPNN_REQUIRE(g && ix, "null argument");
+  k_force_det_scores<<<max(1, min(tmpnn_div_up(ix->cap_dets, 256), 148)), 256, 0, (cudaStream_t)stream>>>(ix->n_dets, ix->det_rows,
+                                                                                                        g->score);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_status_ack(const tmpnn_graph* g, int from_bits, int to_bits, void* stream) {
+  TMPNN_REQUIRE(g && g->status, "null argument");
+  k_status_ack<<<1, 1, 0, (cudaStream_t)stream>>>(g->status, from_bits, to_bits);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

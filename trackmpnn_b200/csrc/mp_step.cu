@@ -438,9 +438,10 @@ k_mp_edge(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, in
           int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const float* __restrict__ pack,
           float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
           float* __restrict__ gates, const int32_t* __restrict__ phys, const int32_t* __restrict__ psrc,
-          const int32_t* __restrict__ pdst) {
+          const int32_t* __restrict__ pdst, const int32_t* __restrict__ run_if_status, int run_if_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<KX>& s = *reinterpret_cast<StepSmem<KX>*>(smem_raw);
+  if (run_if_status && !(*run_if_status & run_if_mask)) return;  // conditional re-run (tmpnn_mp_edge_fwd_on_flag)
   const int total = tile_ptr[num_seqs];
   if ((int)blockIdx.x >= total) return;
   load_pack<KX>(s, pack);
@@ -544,7 +545,8 @@ extern "C" int tmpnn_init(void) {
 }
 
 static int mp_edge_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
-                          int num_groups, int concat, const float* edge_pack, float* gates, void* stream) {
+                          int num_groups, int concat, const float* edge_pack, float* gates, void* stream,
+                          int run_if_mask = 0) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_pack, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
@@ -555,11 +557,11 @@ static int mp_edge_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
   if (concat)
     k_mp_edge<2 * H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<2 * H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last, gates, g->phys, g->psrc, g->pdst);
+        g->score, first, last, gates, g->phys, g->psrc, g->pdst, run_if_mask ? g->status : nullptr, run_if_mask);
   else
     k_mp_edge<H><<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), st>>>(
         h_in, h_out, ldh, col, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile_ptr, edge_pack, g->logit,
-        g->score, first, last, gates, g->phys, g->psrc, g->pdst);
+        g->score, first, last, gates, g->phys, g->psrc, g->pdst, run_if_mask ? g->status : nullptr, run_if_mask);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -580,6 +582,13 @@ static int mp_det_launch(const tmpnn_graph* g, const tmpnn_index* ix, const floa
 extern "C" int tmpnn_mp_edge_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
                                  int group, int num_groups, int concat, const float* edge_pack, void* stream) {
   return mp_edge_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, nullptr, stream);
+}
+
+extern "C" int tmpnn_mp_edge_fwd_on_flag(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                         int group, int num_groups, int concat, const float* edge_pack, int flag_mask,
+                                         void* stream) {
+  TMPNN_REQUIRE(flag_mask != 0, "flag_mask must name at least one status bit");
+  return mp_edge_launch(g, ix, h_in, h_out, ldh, group, num_groups, concat, edge_pack, nullptr, stream, flag_mask);
 }
 
 extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,

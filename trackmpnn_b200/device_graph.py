@@ -47,6 +47,8 @@ class SlabGraph:
     def check_status(self):
         """Host read of the sticky flags (synchronises)."""
         flags = int(self.status.item())
+        self.notes = flags & L.NOTE_TC_RANGE_RERUN   # handled on the device (the step was re-run on the FMA kernel)
+        flags &= ~L.NOTE_TC_RANGE_RERUN
         if flags:
             msgs = [m for b, m in L.FLAG_NAMES.items() if flags & b]
             if flags & 16:

@@ -36,13 +36,14 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='auto'):
+                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
         through the position maps the compaction emits (tmpnn_graph.phys / psrc / pdst) and writes its output
         densely, so the state only ever crosses HBM once per step in each direction."""
         self.model = model
+        self.tp_classifier = bool(tp_classifier)   # False: infer.py's --no-tp-classifier
         self.dev = device if device is not None else next(model.parameters()).device
         if self.dev.type != 'cuda':
             raise L.TmpnnError('TrackEngine needs a CUDA device; there is no CPU path')
@@ -92,7 +93,6 @@ class TrackEngine:
         self.n_appended = z(self.S)
         self.append_scratch = z(int(L.lib().tmpnn_graph_append_scratch_ints(self.S, self.cap_rows)))
         self.compact_scratch = z(int(L.lib().tmpnn_graph_compact_scratch_ints(self.S, self.cap_rows)))
-        self.decode_scratch = z(self.S + 4)
         self.keep = torch.zeros(n_all, dtype=torch.uint8, device=dev)
         self.new_of_old = z(n_all)
         self.agg = torch.empty((self.index.cap_dets, H), dtype=torch.float32, device=dev)
@@ -107,6 +107,7 @@ class TrackEngine:
         # --hungarian (infer.py:143): optimal assignment per timestep instead of the greedy arg-max
         self.use_hungarian = bool(use_hungarian)
         self.max_dets = max_dets
+        self.decode_scratch = z(int(L.lib().tmpnn_graph_decode_scratch_ints(self.S, max_dets)))
         self.hung_scratch = None
         if self.use_hungarian:
             nbytes = int(L.lib().tmpnn_hungarian_scratch_bytes(self.S, max_dets))
@@ -120,12 +121,13 @@ class TrackEngine:
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self._tc_scratch = {}
         self._gat_scratch = {}
-        self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end) per step
+        self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end, new edge rows) per step
         self.profile_compact = None  # when a list: (start, end, rows before, rows after) per window slide
         # when a list: four events per tick bracketing the reference's three phases -- update_graph (append) |
         # forward (input transform, index, aggregation, both row types) | decode_tracks (associate, walk, window slide)
         self.profile_phases = None
         self._graph = None
+        self._graph_key = None
         self.ticks = 0
 
     # ---- one engine tick --------------------------------------------------------------------
@@ -167,9 +169,14 @@ class TrackEngine:
                        L.ptr(packs[grp][0]), st)
             if self.profile is not None:
                 e1.record()
-                self.profile.append((e0, e1, self.index.n_edges.clone(), a0, a1))
+                self.profile.append((e0, e1, self.index.n_edges.clone(), a0, a1, self.n_new[1:2].clone()))
             L.call('tmpnn_mp_det_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
                    L.ptr(packs[grp][1]), L.ptr(self.agg), st)
+        if self.tensor:
+            F_.rerun_edges_if_out_of_range(model, g, self.index, h_in, h_out, self.ldh, packs)
+        if not self.tp_classifier:
+            # --no-tp-classifier (infer.py:54-57, 77-80): detections count as true positives in association and decoding
+            L.call('tmpnn_graph_force_det_scores', g.c, self.index.c, st)
         self.edge_updates += self.index.n_edges
         self.det_updates += self.index.n_dets
 
@@ -221,7 +228,7 @@ class TrackEngine:
         self._associate(g)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
-               L.ptr(self.keep), L.ptr(self.decode_scratch), st)
+               L.ptr(self.keep), self.max_dets, L.ptr(self.decode_scratch), st)
         # plain: move the survivors h_alt -> h_cur; deferred: emit the maps only (sequences that sat the step out
         # are copied h_in -> h_out)
         if self.profile_compact is not None:
@@ -260,6 +267,12 @@ class TrackEngine:
         ``results()`` (which synchronises) for the decoded tracks."""
         self.reset()
         self._start()
+        # the captured ticks bake in the device pointers of the packed weight images (functional.packed_cells*), which
+        # _start() has just re-packed if a parameter changed in place (optimizer.step, load_state_dict), and of every
+        # parameter / buffer tensor: a changed key means the captured graph reads freed or stale memory -> re-capture
+        key = self._weights_key()
+        if self._graph is not None and key != self._graph_key:
+            self._graph = None
         n_ticks = self.t_hi if max_ticks is None else min(self.t_hi, int(max_ticks))
         # the two graph sets swap roles every tick -> capture two ticks per CUDA graph replay
         t = 0
@@ -289,6 +302,13 @@ class TrackEngine:
             self._tick(flip=True)
             self.ga, self.gb = self.gb, self.ga
         self._graph = g
+        self._graph_key = self._weights_key()
+
+    def _weights_key(self):
+        """Identity of everything a captured tick reads from the model: parameter / buffer storage, their versions (the
+        packed images are rebuilt when a version changes) and the train / eval switch."""
+        ts = list(self.model.parameters()) + list(self.model.buffers())
+        return tuple((t.data_ptr(), t._version) for t in ts) + (self.model.training,)
 
     def results(self):
         """Synchronises; returns (list of y_out [ND_s, 2] int64 arrays, stats dict)."""

@@ -209,6 +209,20 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
            L.ptr(img), L.ptr(dp), L.ptr(tab), st)
 
 
+def rerun_edges_if_out_of_range(model, graph, index, h_in, h_out, ldh, packs):
+    """Behind the tensor-core edge step: if an activation left the range of the fp16 split (|h| > 6e4, e.g. a trained
+    input transform with large outputs; TMPNN_FLAG_TC_RANGE), the association rows of every feature group are re-run by
+    the fp32 FMA kernel.  The test happens on the device (the launches exit at once otherwise), so this sits inside the
+    engine's CUDA graph; the flag then becomes the note NOTE_TC_RANGE_RERUN."""
+    st = L.stream()
+    G = len(model.feature_idx)
+    for g in range(G):
+        concat = int(model.factor_grus[g].msg_type == 'concat')
+        L.call('tmpnn_mp_edge_fwd_on_flag', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]),
+               L.FLAG_TC_RANGE, st)
+    L.call('tmpnn_status_ack', graph.c, L.FLAG_TC_RANGE, L.NOTE_TC_RANGE_RERUN, st)
+
+
 def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=False):
     """One message-passing step over all feature groups (K1-det, edge rows, detection rows).
     Returns the per-group attention (list of per-head alpha tensors, or None)."""
@@ -228,6 +242,8 @@ def mp_step(model, graph, index, h_in, h_out, ldh, agg, tensor, keep_attention=F
         else:
             L.call('tmpnn_mp_edge_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]), st)
         L.call('tmpnn_mp_det_fwd', g_c, ix_c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]), L.ptr(agg), st)
+    if tensor:
+        rerun_edges_if_out_of_range(model, graph, index, h_in, h_out, ldh, packs)
     return att
 
 
@@ -263,7 +279,11 @@ def input_transform_rows(model, g, x, x_idx, n, n_edge_rows, h, ldh, out_rows, n
 
 def track_mpnn_forward(model, x, h_in, node_adj, edge_adj):
     """``TrackMPNN.forward`` (reference ``models/track_mpnn.py:54-75``) on the CUDA library."""
-    if torch.is_grad_enabled() and (any(p.requires_grad for p in model.parameters())
+    # The autograd Function (FMA kernel, stored gates) runs only where a backward pass can follow: grad mode on AND
+    # (train mode with trainable parameters, or a state that already carries a graph).  The reference's infer.py never
+    # enters torch.no_grad() but never calls backward either: in eval mode it gets the inference path (tensor-core
+    # kernel on large graphs, nothing saved).  Gradients in eval mode: pass an h_in that requires grad, or call .train().
+    if torch.is_grad_enabled() and ((model.training and any(p.requires_grad for p in model.parameters()))
                                     or (h_in is not None and h_in.requires_grad)):
         scores, logits, h_out, *alphas = _MPStepFn.apply(model, node_adj, x, h_in, *_param_list(model))
         # attention slots: per group None or one SparseAttention per head (after dropout, as the reference returns it)

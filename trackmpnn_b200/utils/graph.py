@@ -223,10 +223,11 @@ def decode_tracks(states, node_adj, labels, scores, y_pred, y_out, t_upto, ret_w
     det_ptr = torch.tensor([0, nd_seq], dtype=_I32, device=dev)
     fr = L.Frames(0, 0, None, None, L.ptr(det_ptr), None)
     keep = torch.empty(wg.g.cap_rows, dtype=torch.uint8, device=dev)
-    scratch = torch.empty(4, dtype=_I32, device=dev)
+    max_dets = max(1, wg.n)   # bound of the window's detection rows known without a read-back: its row count
+    scratch = torch.empty(int(L.lib().tmpnn_graph_decode_scratch_ints(1, max_dets)), dtype=_I32, device=dev)
     import ctypes as C
     L.call('tmpnn_graph_decode', wg.g.c, wg.index().c, C.byref(fr), L.ptr(track), L.ptr(next_id), None, int(t_upto),
-           None, int(ret_win_size), L.ptr(keep), L.ptr(scratch), L.stream())
+           None, int(ret_win_size), L.ptr(keep), max_dets, L.ptr(scratch), L.stream())
     wg.g.check_status()
     y_out[:, 1] = track.cpu().numpy().astype(y_out.dtype)
     out, new_states, new_scores = _compact(wg, keep, states, scores)
