@@ -767,12 +767,21 @@ def main():
                'frames_per_s': stc['frames'] / dtc, 'seconds': dtc,
                'sample': f'1 sequence of the workload, first {frames_cap} frames (oracle port: numpy BLAS threads for '
                          f'the GEMMs, one thread for graph bookkeeping)'}
+    def side(fn):   # a side leg that fails must not take the headline line with it: its error is reported in its place
+        try:
+            return fn(a, dev)
+        except Exception as e:   # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            torch.cuda.empty_cache()
+            return {'error': f'{type(e).__name__}: {e}'}
+
     if rank == 0 and world == 1 and not a.skip_train:
-        train = run_train_leg(a, dev)
-        c1 = run_c1_leg(a, dev)
+        train = side(run_train_leg)
+        c1 = side(run_c1_leg)
     c4 = None
     if rank == 0 and world == 1 and not a.skip_c4:
-        c4 = run_c4_leg(a, dev)
+        c4 = side(run_c4_leg)
     train_ddp = None
     if world > 1 and not a.skip_train:
         train_ddp = run_train_ddp_leg(a, dev, rank, world, barrier, reduce_)

@@ -396,6 +396,8 @@ typedef struct tmpnn_seq_state {
   int32_t *active;     /* [S] out: 1 if the sequence takes part in this tick */
   int32_t *t_upto;     /* [S] out: decode_tracks' t_upto for this tick */
   int32_t *fresh;      /* [S] out: 1 if the graph was (re-)initialised this tick (states = None) */
+  int32_t *last_new;   /* [S] rows the sequence's last executed iteration added (infer.py's feats.size()[0]): the loop
+                          re-initialises when the graph AND that are both empty (infer.py:64-69) */
 } tmpnn_seq_state;
 
 /* Hungarian association (utils/graph.py:33-93 driven by :247-249 / :433-435): resets ass, then for every

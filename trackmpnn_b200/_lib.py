@@ -57,9 +57,12 @@ class Frames(C.Structure):
                 ('det_ptr', C.c_void_p), ('det_track', C.c_void_p)]
 
 
+SEQ_STATE_FIELDS = ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh', 'last_new')
+
+
 class SeqState(C.Structure):
     _fields_ = [('phase', C.c_void_p), ('skip_until', C.c_void_p), ('t_end', C.c_void_p), ('active', C.c_void_p),
-                ('t_upto', C.c_void_p), ('fresh', C.c_void_p)]
+                ('t_upto', C.c_void_p), ('fresh', C.c_void_p), ('last_new', C.c_void_p)]
 
 
 class TmpnnError(RuntimeError):

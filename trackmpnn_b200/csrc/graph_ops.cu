@@ -227,8 +227,9 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
         kind = 0;
         st.active[s] = 0;
       } else {
-        const int nt = (t <= fr.t_max) ? fp[t + 1] - fp[t] : 0;
-        kind = (n == 0 && nt == 0) ? 2 : 1;  // infer.py:64-69
+        // infer.py:64-69: "feats.size()[0] == 0 and states.size()[0] == 0" -- the rows the PREVIOUS executed iteration
+        // added and the graph its decode left behind; the current frame's size does not enter
+        kind = (n == 0 && st.last_new[s] == 0) ? 2 : 1;
         st.active[s] = 1;
         st.t_upto[s] = (t == st.t_end[s] - 1) ? st.t_end[s] : t - cur_win + 2;  // infer.py:82-87
       }
@@ -285,6 +286,7 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
         d[0] = 0; d[1] = n0; d[2] = n1; d[3] = fp[t1]; d[4] = slot; d[5] = 2; d[6] = fp[t]; d[7] = t1; d[8] = t;
         n_appended[s] = (int)total;
         g.n_rows[s] = (int)total;
+        if (has_state) st.last_new[s] = (int)total;
       }
     }
     return;
@@ -354,7 +356,9 @@ k_append_plan(tmpnn_graph g, tmpnn_frames fr, tmpnn_seq_state st, int has_state,
       d[5] = 0; n_appended[s] = 0;
     } else if (nt == 0) {  // graph unchanged (utils/graph.py:284,295)
       d[5] = 0; n_appended[s] = 0;
+      if (has_state) st.last_new[s] = 0;
     } else {
+      if (has_state) st.last_new[s] = (int)add;
       atomicAdd(&n_new[1], A * nt);
       d[0] = n; d[1] = A; d[2] = nt; d[3] = fp[t]; d[4] = slot; d[5] = 1; d[6] = 0; d[7] = t;
       n_appended[s] = (int)add;

@@ -82,8 +82,8 @@ class TrackEngine:
         self.index = SlabIndex(self.ga, cap_dets=self.S * max_dets, cap_inc=2 * n_all)
         z = lambda n: torch.zeros(n, dtype=_I32, device=dev)
         self.st = dict(phase=z(self.S), skip_until=z(self.S), t_end=z(self.S), active=z(self.S), t_upto=z(self.S),
-                       fresh=z(self.S))
-        self.st_c = L.SeqState(*[L.ptr(self.st[k]) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')])
+                       fresh=z(self.S), last_new=z(self.S))
+        self.st_c = L.SeqState(*[L.ptr(self.st[k]) for k in L.SEQ_STATE_FIELDS])
         self.y_out_track = torch.full((max(1, self.frames.total_dets),), -1, dtype=_I32, device=dev)
         self.next_track_id = z(self.S)
         self.t_dev = z(1)

@@ -86,8 +86,8 @@ class TrainBatch:
         max_dets = int(counts.sum(1).max())
         index = SlabIndex(g, cap_dets=B * max_dets, cap_inc=2 * B * cap)
         z = lambda n: torch.zeros(n, dtype=_I32, device=dev)
-        st = {k: z(B) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')}
-        st_c = L.SeqState(*[L.ptr(st[k]) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')])
+        st = {k: z(B) for k in L.SEQ_STATE_FIELDS}
+        st_c = L.SeqState(*[L.ptr(st[k]) for k in L.SEQ_STATE_FIELDS])
         cap_new = 2 * B * int(counts.max())
         new_rows, new_x, n_new, n_app = z(cap_new), z(cap_new), z(2), z(B)
         scratch = z(int(L.lib().tmpnn_graph_append_scratch_ints(B, cap)))

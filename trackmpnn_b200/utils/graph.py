@@ -39,8 +39,8 @@ def _place(t, cuda, device):
 
 def _seq_state(device):
     z = lambda: torch.zeros(1, dtype=_I32, device=device)
-    t = dict(phase=z(), skip_until=z(), t_end=z(), active=z(), t_upto=z(), fresh=z())
-    c = L.SeqState(*[L.ptr(t[k]) for k in ('phase', 'skip_until', 't_end', 'active', 't_upto', 'fresh')])
+    t = dict(phase=z(), skip_until=z(), t_end=z(), active=z(), t_upto=z(), fresh=z(), last_new=z())
+    c = L.SeqState(*[L.ptr(t[k]) for k in L.SEQ_STATE_FIELDS])
     return t, c
 
 
