@@ -429,9 +429,11 @@ def run_c4_leg(a, dev):
 
 def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     """BASELINE.json configs[4]: data-parallel training.  Every rank runs forward + losses + backward of its own
-    batch of chunks (batched trainer), the ranks all-reduce ONE flat buffer of all parameter gradients over NCCL
-    (trackmpnn_b200.parallel.allreduce_gradients), then every rank takes the same Adam step.  BatchNorm statistics
-    stay per chunk (no SyncBN), as in the reference."""
+    batch of chunks (batched trainer); the backward kernels accumulate into views of ONE flat gradient buffer
+    (trackmpnn_b200.parallel.FlatGradients), which the ranks all-reduce over NCCL as it is -- no pack / unpack -- then every
+    rank takes the same Adam step.  BatchNorm statistics stay per chunk (no SyncBN), as in the reference.
+    Gradient check: the all-reduced gradient of a small per-rank batch equals the gradient rank 0
+    computes alone for the union of all ranks' chunks."""
     import torch
     import torch.distributed as dist
     from trackmpnn_b200 import parallel, synth
@@ -440,24 +442,39 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories('kitti'), 64, 0, 'diff').to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
+    flat = parallel.FlatGradients(model)
     params = list(model.parameters())
     B, n_steps = a.train_batch, a.train_chunks
-    chunks = []
-    for i in range(B):
-        ts = synth.train_chunk_timestamps(2000 + rank * 1000 + i, 5, 2)
-        Xn, yn = synth.make_sequence(2000 + rank * 1000 + i, None, a.train_dets, 'kitti', timestamps=ts)
-        chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
-    batch = TrainBatch(chunks, dev)
+
+    def chunk(seed):
+        ts = synth.train_chunk_timestamps(seed, 5, 2)
+        Xn, yn = synth.make_sequence(seed, None, a.train_dets, 'kitti', timestamps=ts)
+        return torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)
+
+    # ---- gradient check: sum over ranks of the per-rank gradients == single-GPU gradient of the summed loss -------------
+    Bc = 4
+    flat.zero()
+    batch_loss(model, TrainBatch([chunk(5000 + rank * Bc + i) for i in range(Bc)], dev)).backward()
+    flat.allreduce(average=False)
+    g_ddp = flat.flat.clone()
+    flat.zero()
+    batch_loss(model, TrainBatch([chunk(5000 + i) for i in range(Bc * world)], dev)).backward()   # every rank: the union
+    g_one = flat.flat.clone()
+    err = float((g_ddp - g_one).abs().max() / g_one.abs().max())
+    err = reduce_(err, dist.ReduceOp.MAX)
+    # BatchNorm running statistics moved during the check: every rank did the same two forward passes -> still identical
+    # ---- timed steps ----------------------------------------------------------------------------------------------------
+    batch = TrainBatch([chunk(2000 + rank * 1000 + i) for i in range(B)], dev)
     ar_ms = 0.0
     for i in range(n_steps + 2):
         if i == 2:
             barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-        opt.zero_grad()
+        flat.zero()
         batch_loss(model, batch).backward()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        nfl = parallel.allreduce_gradients(params, average=True)
+        nfl = flat.allreduce(average=True)
         a1.record()
         opt.step()
         if i >= 2:
@@ -471,11 +488,14 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     lo, hi = reduce_(float(chk), dist.ReduceOp.MIN), reduce_(float(chk), dist.ReduceOp.MAX)
     return {'workload': f'C5 data-parallel training: {world} ranks x {n_steps} optimizer steps x {B} kitti-shaped chunks per rank '
                         f'(~Poisson({a.train_dets}) dets/frame), batched forward + CE/BCE + backward per rank, one NCCL all-reduce of '
-                        'the flat gradient buffer, Adam',
+                        'the flat gradient buffer the backward kernels wrote (no pack / unpack), Adam',
             'value': tot_edges / dt, 'unit': 'edge-updates/s (forward+backward+allreduce+optimizer, all ranks)',
             'chunks_per_s': world * n_steps * B / dt, 'allreduce_floats': int(nfl),
             'allreduce_ms_avg_incl_peer_wait': ar_ms / max(1, n_steps),
-            'replicas_in_sync': bool(abs(hi - lo) <= 1e-9 * max(1.0, abs(hi)))}
+            'replicas_in_sync': bool(abs(hi - lo) <= 1e-9 * max(1.0, abs(hi))),
+            'ddp_gradient_vs_single_gpu': {'max_abs_err_over_max_abs_grad': err, 'ok': bool(err <= 1e-4),
+                                           'what': f'all-reduced sum of {world} x {Bc}-chunk gradients vs one GPU over the {Bc * world} chunks '
+                                                   '(float atomics in the weight-gradient sums: not bit-identical)'}}
 
 
 def prepare_passes(eng):

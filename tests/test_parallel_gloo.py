@@ -43,6 +43,23 @@ def _worker(rank, world, port, out):
         assert n == 18
         assert torch.allclose(lin.weight.grad, want_w)
         assert torch.allclose(lin.bias.grad, torch.full((3,), 4.0 * (world - 1)))
+        # the flat gradient buffer of the training path: p.grad are views, the all-reduce exchanges the buffer itself
+        from trackmpnn_b200.models.track_mpnn import TrackMPNN
+        torch.manual_seed(5)
+        model = TrackMPNN('2d', 3, 64, 0, 'diff')
+        flat = parallel.FlatGradients(model)
+        assert flat.flat.numel() == sum(p.numel() for p in model.parameters()) == 54914
+        for k, p in enumerate(model.parameters()):
+            assert flat.view_of(p) is not None
+            p.grad.add_(float(rank + 1) * (k + 1))        # in place: what the backward kernels do
+        assert flat.allreduce(average=True) == 54914
+        for k, p in enumerate(model.parameters()):
+            assert p.grad.data_ptr() == flat.views[id(p)].data_ptr()
+            assert torch.allclose(p.grad, torch.full_like(p, (k + 1) * sum(r + 1 for r in range(world)) / world))
+        flat.zero()
+        assert float(flat.flat.abs().max()) == 0.0
+        model.zero_grad()                                 # set_to_none: the views are gone -> the Function falls back to autograd
+        assert all(flat.view_of(p) is None for p in model.parameters())
         costs = [parallel.sequence_cost([5 + (i % 3)] * 10) for i in range(9)]
         mine = parallel.partition_sequences(costs, world)[rank]
         tot = parallel.reduce_sum(len(mine))

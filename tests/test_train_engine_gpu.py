@@ -113,3 +113,72 @@ def test_training_steps_do_not_accumulate_device_memory():
         assert used[-1] <= used[1] + (1 << 20), used   # steady after the optimizer state exists
     finally:
         gc.enable()
+
+
+def _kitti_chunks(dev, seeds, dets):
+    chunks, host = [], []
+    for sd in seeds:
+        ts = synth.train_chunk_timestamps(sd, 5, 2)
+        Xn, yn = synth.make_sequence(sd, None, dets, 'kitti', timestamps=ts)
+        host.append((Xn, yn))
+        chunks.append((torch.from_numpy(Xn).to(dev), torch.from_numpy(yn).to(dev)))
+    return chunks, host
+
+
+def test_flat_gradient_buffer_equals_autograd():
+    """parallel.FlatGradients: the backward kernels accumulate straight into views of ONE flat buffer (what the data-parallel
+    all-reduce exchanges, no pack / unpack); the result equals the gradients returned through autograd, over two
+    accumulated batches, and zero() resets them."""
+    from trackmpnn_b200 import parallel
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev).train()
+    ref = copy.deepcopy(model)
+    chunks, _ = _kitti_chunks(dev, [70, 71, 72, 73], 9)
+    batch = TrainBatch(chunks, dev)
+    for _ in range(2):
+        batch_loss(ref, batch).backward()
+    flat = parallel.FlatGradients(model)
+    assert flat.flat.numel() == sum(p.numel() for p in model.parameters())
+    for _ in range(2):
+        batch_loss(model, batch).backward()
+    gmax = max(float(p.grad.abs().max()) for p in ref.parameters())
+    for (name, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert p.grad.data_ptr() == flat.views[id(p)].data_ptr(), name   # still the view: nothing was re-allocated
+        tol = 1e-4 * float(q.grad.abs().max()) + 1e-6 * gmax               # float atomics: sums differ in their last bits
+        np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.cpu().numpy(), atol=tol, rtol=0, err_msg=name)
+    assert float(flat.flat.abs().sum()) > 0
+    flat.zero()
+    assert all(float(p.grad.abs().max()) == 0.0 for p in model.parameters())
+
+
+def test_batched_trainer_against_training_oracle_at_bench_size():
+    """The bench's training workload (BASELINE configs[1]: KITTI-shaped chunks, ~40 detections / frame), 8 chunks in one batch:
+    loss and every parameter gradient against oracle/train_ref.py (torch fp32 ops on edge lists + autograd, itself pinned to
+    the live reference's backward pass) run chunk by chunk and summed."""
+    from oracle import train_ref as T
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev).train()
+    params = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    chunks, host = _kitti_chunks(dev, list(range(1000, 1008)), 40)
+    loss_ref, grads_ref = 0.0, None
+    for Xn, yn in host:
+        r = T.train_chunk(params, Xn, yn)
+        loss_ref += r['loss']
+        grads_ref = r['grads'] if grads_ref is None else {k: grads_ref[k] + v for k, v in r['grads'].items()}
+    batch = TrainBatch(chunks, dev)
+    assert batch.edge_rows > 300000
+    loss = batch_loss(model, batch)
+    loss.backward()
+    assert abs(float(loss) - loss_ref) <= 1e-4 * abs(loss_ref)
+    # the golden bar (tests/golden_util.assert_grads_close): per parameter 2e-3 of its own largest entry + 1e-6 of the model's
+    gmax = max(float(np.abs(v).max()) for v in grads_ref.values())
+    for name, p in model.named_parameters():
+        want = grads_ref[name]
+        atol = 2e-3 * float(np.abs(want).max()) + 1e-6 * gmax + 1e-9
+        np.testing.assert_allclose(p.grad.detach().cpu().numpy().reshape(want.shape), want, atol=atol, rtol=0, err_msg=name)

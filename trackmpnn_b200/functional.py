@@ -521,7 +521,15 @@ class _MPStepFn(torch.autograd.Function):
         st = L.stream()
         f32 = dict(dtype=torch.float32, device=dev)
         P = ctx.param_vals
-        grads = [torch.zeros_like(p) for p in P]
+        # parallel.FlatGradients: every p.grad is a view of one flat buffer and the kernels below accumulate straight into
+        # it (nothing is returned through autograd for the parameters: no per-parameter zero-fill, add or copy)
+        flat = model.__dict__.get('_tmpnn_flat_grads')
+        direct = None
+        if flat is not None:
+            direct = [flat.view_of(p) for p in _param_list(model)]
+            if len(direct) != len(P) or any(v is None for v in direct):
+                direct = None
+        grads = direct if direct is not None else [torch.zeros_like(p) for p in P]
         cont = lambda t: None if t is None else t.detach().to(**f32).contiguous()
         dscores, dlogits, dh_out = cont(dscores), cont(dlogits), cont(dh_out)
         dh_cur = torch.zeros((n, ldh), **f32)
@@ -609,4 +617,4 @@ class _MPStepFn(torch.autograd.Function):
                        L.ptr(grads[b + 0]), L.ptr(grads[b + 1]), L.ptr(grads[b + 2]), L.ptr(grads[b + 3]),
                        L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), st)
         dh_in = dh_cur[:ctx.n_old] if ctx.has_h_in else None
-        return (None, None, None, dh_in) + tuple(grads)
+        return (None, None, None, dh_in) + (tuple(None for _ in grads) if direct is not None else tuple(grads))

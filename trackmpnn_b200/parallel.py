@@ -39,6 +39,52 @@ def partition_sequences(costs, world_size):
     return [sorted(b) for b in bins]
 
 
+class FlatGradients:
+    """ONE flat fp32 buffer holding every parameter gradient of a model; ``p.grad`` of every parameter is a view into it.
+
+    The backward kernels of the message-passing step (``functional._MPStepFn.backward``) accumulate straight into these
+    views, so a data-parallel step is: ``flat.zero()`` -> forward / backward -> ``flat.allreduce()`` (a single
+    ``all_reduce`` of the buffer itself: no pack, no unpack, no per-parameter copies) -> ``optimizer.step()``.
+    Use ``flat.zero()`` instead of ``optimizer.zero_grad()`` (whose default drops the views)."""
+
+    def __init__(self, model):
+        from .functional import _param_list
+        step_params = _param_list(model)            # the order the autograd Function receives them in
+        seen = {id(p) for p in step_params}
+        self.params = step_params + [p for p in model.parameters() if id(p) not in seen]
+        self.params = [p for p in self.params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = {}
+        off = 0
+        for p in self.params:
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views[id(p)] = v
+            off += p.numel()
+        model.__dict__['_tmpnn_flat_grads'] = self
+
+    def view_of(self, p):
+        """The gradient view of parameter ``p`` while ``p.grad`` still is that view (None otherwise: the caller falls back
+        to returning the gradient through autograd)."""
+        v = self.views.get(id(p))
+        if v is None or p.grad is None or p.grad.data_ptr() != v.data_ptr():
+            return None
+        return v
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, group=None, average=False):
+        """Sums the buffer over the ranks in place; returns the number of floats exchanged."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.mul_(1.0 / dist.get_world_size(group))
+        return int(self.flat.numel())
+
+
 def allreduce_gradients(params, group=None, average=False):
     """One all-reduce(sum) of a flat buffer holding every parameter gradient (missing grads count as 0),
     then scatter back into ``p.grad``.  Returns the number of floats exchanged."""
