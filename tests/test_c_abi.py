@@ -72,3 +72,21 @@ def test_host_only_entry_points_answer_without_a_gpu():
     lib.tmpnn_aggregate_dets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     rc = lib.tmpnn_aggregate_dets(None, None, None, 64, 0, None, None)
     assert rc < 0 and b'null' in lib.tmpnn_last_error().lower()
+
+
+def test_every_entry_point_has_an_nvtx_family():
+    """NVTX ranges are named tmpnn/<family>/<entry point>; no C-ABI call may fall into 'misc' (SURVEY.md section 5)."""
+    from trackmpnn_b200 import _lib as L
+    skip = {'tmpnn_version', 'tmpnn_init', 'tmpnn_last_error'}
+    sizes = {n for n in L.exported_symbols() if n.endswith(('_bytes', '_ints', '_floats'))}
+    for name in L.exported_symbols():
+        if name in skip or name in sizes:
+            continue
+        assert L.family_of(name) != 'misc', name
+    assert not L.nvtx_enabled()
+    L.enable_nvtx(True)
+    try:
+        with L.nvtx_range('phase/forward'):   # works without a GPU or a profiler attached
+            pass
+    finally:
+        L.enable_nvtx(False)

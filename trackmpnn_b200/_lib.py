@@ -200,6 +200,56 @@ KERNELS_PER_CALL = {
 }
 
 
+# NVTX ranges per kernel family (SURVEY.md section 5 "tracing"): set TMPNN_NVTX=1 (or call enable_nvtx()) and every C-ABI
+# call is bracketed by a range "tmpnn/<family>/<entry point>" -- families: input, index, aggregate, mp_step, graph, loss,
+# backward, pack, convert -- which a profiler with NVTX support groups the launch list by; off by default (two extra
+# Python calls per launch otherwise).  TrackEngine adds the reference's three phases (update / forward / decode) on top.
+_FAMILY_PREFIXES = (('tmpnn_input_', 'input'), ('tmpnn_index_', 'index'), ('tmpnn_aggregate', 'aggregate'),
+                    ('tmpnn_gat_', 'aggregate'), ('tmpnn_mp_', 'mp_step'), ('tmpnn_graph_', 'graph'), ('tmpnn_status_', 'graph'),
+                    ('tmpnn_loss_', 'loss'), ('tmpnn_gate_bwd', 'backward'), ('tmpnn_rows_', 'backward'),
+                    ('tmpnn_scatter_bwd', 'backward'), ('tmpnn_pack_', 'pack'), ('tmpnn_ypred_', 'convert'),
+                    ('tmpnn_coo_', 'convert'), ('tmpnn_edges_', 'convert'), ('tmpnn_build_features', 'input'),
+                    ('tmpnn_lsap_', 'graph'))
+_NVTX = [os.environ.get('TMPNN_NVTX', '0') not in ('', '0')]
+
+
+def enable_nvtx(on=True):
+    _NVTX[0] = bool(on)
+
+
+def nvtx_enabled():
+    return _NVTX[0]
+
+
+def family_of(name):
+    for prefix, fam in _FAMILY_PREFIXES:
+        if name.startswith(prefix):
+            return fam
+    return 'misc'
+
+
+class nvtx_range:
+    """``with nvtx_range('forward'):`` -- a no-op unless NVTX ranges are enabled."""
+
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if _NVTX[0]:
+            torch.cuda.nvtx.range_push('tmpnn/' + self.label)
+
+    def __exit__(self, *exc):
+        if _NVTX[0]:
+            torch.cuda.nvtx.range_pop()
+
+
 def call(name, *args):
     _LAUNCHES[0] += KERNELS_PER_CALL.get(name, 0)
+    if _NVTX[0]:
+        torch.cuda.nvtx.range_push(f'tmpnn/{family_of(name)}/{name}')
+        try:
+            check(getattr(lib(), name)(*args))
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     check(getattr(lib(), name)(*args))

@@ -217,14 +217,18 @@ class TrackEngine:
             # unlike the greedy choice it is not invariant under the deletion, so it is recomputed here
             self.index.build(g, self.st['active'], structured=self.structured_index)
             self._associate(g)
-        L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
-               L.ptr(h_in), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
-               L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
+        with L.nvtx_range('phase/update_graph'):
+            L.call('tmpnn_graph_append', g.c, self.frames.c, C.byref(self.st_c), L.ptr(self.t_dev), 0, self.W, 0,
+                   L.ptr(h_in), self.ldh, L.ptr(self.new_rows), L.ptr(self.new_x), L.ptr(self.n_new), self.cap_new,
+                   L.ptr(self.n_appended), L.ptr(self.append_scratch), st)
         if ph:
             ph[1].record()
-        self._forward(g, h_in, h_out)
+        with L.nvtx_range('phase/forward'):
+            self._forward(g, h_in, h_out)
         if ph:
             ph[2].record()
+        if L.nvtx_enabled():
+            torch.cuda.nvtx.range_push('tmpnn/phase/decode_tracks')
         self._associate(g)
         L.call('tmpnn_graph_decode', g.c, self.index.c, self.frames.c, L.ptr(self.y_out_track),
                L.ptr(self.next_track_id), L.ptr(self.st['t_upto']), 0, L.ptr(self.st['active']), self.R,
@@ -240,6 +244,8 @@ class TrackEngine:
         if self.profile_compact is not None:
             c1.record()
             self.profile_compact.append((c0, c1, g.n_rows.sum(), go.n_rows.sum()))
+        if L.nvtx_enabled():
+            torch.cuda.nvtx.range_pop()
         if ph:
             ph[3].record()
             self.profile_phases.append(ph)

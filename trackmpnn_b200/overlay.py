@@ -6,7 +6,7 @@ library without edits.
     import runpy; runpy.run_path('/path/to/TrackMPNN/infer.py', run_name='__main__')
 
 ``install`` registers this package's modules under the names the reference imports -- ``models.track_mpnn``,
-``models.layers``, ``models.loss``, ``utils.graph`` -- so that ``from models.track_mpnn import TrackMPNN`` and
+``models.layers``, ``models.loss``, ``utils.graph``, ``utils.metrics`` -- so that ``from models.track_mpnn import TrackMPNN`` and
 ``from utils.graph import initialize_graph, ...`` resolve here while everything else (datasets, option parsing,
 metrics) still comes from the reference tree on ``sys.path``.  The reference's drivers unpack three values from
 ``model(...)`` although its module returns four; ``three_outputs=True`` (default) makes the
@@ -24,6 +24,7 @@ _NAMES = {
     'models.layers': 'trackmpnn_b200.models.layers',
     'models.loss': 'trackmpnn_b200.models.loss',
     'utils.graph': 'trackmpnn_b200.utils.graph',
+    'utils.metrics': 'trackmpnn_b200.metrics',   # create_mot_accumulator / calc_mot_metrics without motmetrics
 }
 _OPTIONAL = ('matplotlib', 'matplotlib.pyplot', 'motmetrics', 'models.dla.DCNv2', 'models.dla.DCNv2.dcn_v2')
 
