@@ -479,3 +479,33 @@ def test_step_at_workload_size_with_decision_exercising_weights(kernel):
         L.call('tmpnn_graph_phys_identity', g.c, L.stream())   # the state now sits at the logical rows of h_out
         h_in, h_out = h_out, h_in
     assert worst_h <= 1e-4 and worst_l <= 1e-4, (worst_h, worst_l)
+
+
+@pytest.mark.parametrize('kernel', ['gather', 'pre'])
+def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
+    """fp16 hi / lo split of the weights: the image is pre-scaled by a power of two (k_pack_gru_tc), so the residuals of small
+    weights are normal fp16 numbers.  GRU weights of sigma = 1e-4 (100x below the stock init: every residual w - fp16(w) would
+    be below the fp16 subnormal step without the scale, i.e. an 8-bit weight): the tensor-core step agrees with the fp32 FMA
+    step to 2e-6 of the largest state -- it would be ~5e-4 unscaled."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    model = _model(dev, scale=1.0, edge_bias=None)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'factor_grus' in name and p.dim() >= 2:
+                p.mul_(0.01)
+    seqs = _sequences([30, 34, 48, 58, 65])
+    a = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=True, tensor_kernel=kernel)
+    b = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=False)
+    a.run(max_ticks=3); b.run(max_ticks=3)
+    a.results(); b.results()
+    n = a.ga.n_rows.cpu().numpy()
+    np.testing.assert_array_equal(n, b.ga.n_rows.cpu().numpy())
+    for s in range(len(seqs)):
+        rows = slice(s * a.cap_rows, s * a.cap_rows + int(n[s]))
+        edge = (a.ga.ts[rows] < 0).cpu().numpy()
+        ha = a.h_alt[a.ga.phys[rows].long()].cpu().numpy()[edge]     # 3 ticks: the last step wrote h_alt
+        hb = b.h_alt[b.ga.phys[rows].long()].cpu().numpy()[edge]
+        assert edge.sum() > 50
+        scale = float(np.abs(hb).max())
+        assert scale > 0 and float(np.abs(ha - hb).max()) <= 2e-6 * scale, (float(np.abs(ha - hb).max()), scale)

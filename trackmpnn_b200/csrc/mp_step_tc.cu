@@ -49,6 +49,10 @@ extern "C" int tmpnn_debug_set_tc_trace(long long* buf, int cap) {
 #define TC_TRACE(it_, slot_, cond_) do { } while (0)
 #endif
 
+// -log2e 2^-k and 2 log2e 2^-k of the launch's weight image (k_pack_gru_tc), refreshed by a device-to-symbol copy in front of
+// every launch: constant-bank operands cost the epilogue no registers
+__constant__ float c_tc_expo[4];
+
 namespace {
 
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
@@ -60,10 +64,41 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
                               const float* __restrict__ head_w, const float* __restrict__ head_b,
                               int ldw, int xcol0, unsigned char* __restrict__ img) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // Power-of-two pre-scale of the tensor-core weights (exact in fp32 and fp16): with the stock N(0, 0.01) init the residuals
+  // w - fp16(w) are ~5e-6, i.e. fp16 SUBNORMALS (6e-8 steps, ~6 significant bits): the split would carry ~17 bits instead of
+  // 22.  Scaling by 2^k with max |w| 2^k in [8192, 16384) keeps every residual of a weight within 2^17 of the largest one
+  // a normal number; the epilogues multiply the accumulators by 2^-k (folded into constants they apply anyway).  Every
+  // block computes the same maximum (37 k loads, once per weight change).
+  __shared__ float s_max[32];
+  __shared__ float s_scale;
+  {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < 2 * 192 * 64; i += blockDim.x) {
+      const int mm = i / (192 * 64), n = (i / 64) % 192, k = i % 64;
+      m = fmaxf(m, fabsf(mm == 0 ? w_ih[n * ldw + xcol0 + k] : w_hh[n * 64 + k]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mx = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, s_max[w]);
+      int k = 0;
+      if (mx > 0.f && isfinite(mx)) {
+        int e;
+        frexpf(mx, &e);            // mx = f 2^e, f in [0.5, 1)
+        k = min(max(14 - e, 0), 40);  // mx 2^k in [8192, 16384); never scale down (large weights keep k = 0)
+      }
+      s_scale = ldexpf(1.0f, k);
+    }
+    __syncthreads();
+  }
+  const float wscale = s_scale;
   for (int i = tid; i < 2 * 192 * 64; i += nth) {  // element (matrix m, row n, col k)
     const int m = i / (192 * 64), n = (i / 64) % 192, k = i % 64;
     // msg_type 'concat': the tensor cores take the far-endpoint half W_ih[:, 64:128] (xcol0 = 64)
-    const float w = m == 0 ? w_ih[n * ldw + xcol0 + k] : w_hh[n * 64 + k];
+    const float w = wscale * (m == 0 ? w_ih[n * ldw + xcol0 + k] : w_hh[n * 64 + k]);
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
     const uint32_t off = sw128(n, k >> 3) + (k & 7) * 2;
@@ -73,7 +108,8 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
   float* bias = reinterpret_cast<float*>(img + OFF_BIAS);
   for (int i = tid; i < 4 * H; i += nth) {
     const int g = i / H, j = i % H;
-    bias[i] = g < 2 ? -LOG2E * (b_ih[g * H + j] + b_hh[g * H + j]) : g == 2 ? b_ih[2 * H + j] : b_hh[2 * H + j];
+    // the n-gate biases live in the accumulators' scale (x 2^k), see the epilogues
+    bias[i] = g < 2 ? -LOG2E * (b_ih[g * H + j] + b_hh[g * H + j]) : wscale * (g == 2 ? b_ih[2 * H + j] : b_hh[2 * H + j]);
   }
   float* hw = reinterpret_cast<float*>(img + OFF_HEADW);
   for (int i = tid; i < H; i += nth) hw[i] = head_w[i];
@@ -88,7 +124,9 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
   for (int n = tid; n < 192; n += nth) bs[n] = b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f);
   if (tid == 0) {
     float* hb = reinterpret_cast<float*>(img + OFF_HEADB);
-    hb[0] = head_b[0]; hb[1] = hb[2] = hb[3] = 0.f;
+    // hb[1], hb[3]: the epilogues' two exponent constants with 2^-k folded in (copied into constant memory per launch, so
+    // that they stay instruction operands); hb[2]: 2^k for k_det_prepare
+    hb[0] = head_b[0]; hb[1] = -LOG2E / wscale; hb[2] = wscale; hb[3] = 2.0f * LOG2E / wscale;
   }
 }
 
@@ -271,7 +309,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
     const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
     float* dot_part = reinterpret_cast<float*>(sm + OFF_DOT);
-    const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
+    const f32x2 NLOG2E2 = pk2(c_tc_expo[1], c_tc_expo[1]), TWOLOG2E2 = pk2(c_tc_expo[3], c_tc_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
     // this row's coordinates and its source (< 0: not an edge row) are fetched two tiles ahead, the source's
     int seq = 0, it = 0;
@@ -356,6 +394,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
             const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(ar[i], ar[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
             const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(az[i], az[i + 1]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
             // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + b_in + r (h_n + b_hn)
+            // u is kept in the accumulators' scale (x 2^k: b_in, b_hn and P_n arrive pre-multiplied), TWOLOG2E2 undoes it
             const f32x2 u = fma2(rg, add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), add2(pk2u(an[i], an[i + 1]), e ? bi.y : bi.x));
             const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
             const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[4 * ch + 2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
@@ -435,6 +474,7 @@ k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* _
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float wscale = *reinterpret_cast<const float*>(image + OFF_HEADB + 8);  // 2^k of the weight pre-scale: P_n joins i_n scaled
   float* hw = hr + w * 64;
   for (int k = blockIdx.x * 8 + w; k < nd; k += gridDim.x * 8) {
     const int row = det_rows[k];
@@ -461,7 +501,7 @@ k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* _
     for (int q = 0; q < 6; ++q) {
       const int n = lane + 32 * q;
       const float val = acc[q] + bs[n];
-      det_p[(size_t)k * 192 + n] = q < 4 ? -LOG2E * val : val;
+      det_p[(size_t)k * 192 + n] = q < 4 ? -LOG2E * val : wscale * val;
     }
     __syncwarp();
   }
@@ -494,6 +534,8 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   int rc = tmpnn_init();
   if (rc) return rc;
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc_expo, (const unsigned char*)edge_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice,
+                                         (cudaStream_t)stream));
   k_mp_edge_tc<<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
       (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,

@@ -35,6 +35,11 @@ extern "C" int tmpnn_debug_set_tc3_trace(long long* buf, int cap) {
 #define TC3_TRACE(it_, slot_, cond_) do { } while (0)
 #endif
 
+// -log2e 2^-k and 2 log2e 2^-k of the launch's weight image (k_pack_gru_tc's power-of-two pre-scale), refreshed by a
+// device-to-symbol copy in front of every launch: constant-bank operands cost the epilogue no registers (it sits at the
+// 72-register ceiling; the same constants read from shared memory added 28 bytes of spills)
+__constant__ float c_tc3_expo[4];
+
 namespace {
 
 constexpr int EPI3 = 16, PROD3 = 8;
@@ -222,7 +227,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
     const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
     float* dot_part = reinterpret_cast<float*>(sm + (team ? OFF_DOT : OFF_BIAS));
-    const f32x2 NLOG2E2 = pk2(-LOG2E, -LOG2E), TWOLOG2E2 = pk2(2.0f * LOG2E, 2.0f * LOG2E), ONE2 = pk2(1.0f, 1.0f);
+    const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
     unsigned char* tbuf = a_stage + w8 * 4096;  // [32 rows x 32 floats], 16 B chunks XOR-swizzled by row, in the x images
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
@@ -289,6 +294,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
             const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(ar[i], ar[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
             const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(az[i], az[i + 1]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
             // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + P_n + b_in + r (h_n + b_hn)
+            // u is kept in the accumulators' scale (x 2^k: b_in, b_hn and P_n arrive pre-multiplied), TWOLOG2E2 undoes it
             const f32x2 u = fma2(rg, add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), add2(pk2u(an[i], an[i + 1]), e ? bi.y : bi.x));
             const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
             const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
@@ -361,6 +367,7 @@ int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
     k_tile_table<<<grid, 256, 0, st>>>(g->n_rows, ix->tile128_ptr, g->cap_rows, (int4*)tile_table);
     TMPNN_LAUNCH_CHECK();
   }
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_expo, (const unsigned char*)edge_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice, st));
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, ix->tile128_ptr + g->num_seqs, (const int4*)tile_table,
