@@ -484,9 +484,10 @@ def test_step_at_workload_size_with_decision_exercising_weights(kernel):
 @pytest.mark.parametrize('kernel', ['gather', 'pre'])
 def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
     """fp16 hi / lo split of the weights: the image is pre-scaled by a power of two (k_pack_gru_tc), so the residuals of small
-    weights are normal fp16 numbers.  GRU weights of sigma = 1e-4 (100x below the stock init: every residual w - fp16(w) would
-    be below the fp16 subnormal step without the scale, i.e. an 8-bit weight): the tensor-core step agrees with the fp32 FMA
-    step to 2e-6 of the largest state -- it would be ~5e-4 unscaled."""
+    weights are normal fp16 numbers.  GRU weights of sigma = 1e-4 (100x below the stock init: without the scale every weight
+    itself is an fp16 subnormal, ~8 significant bits, and the residual is zero) against detection states of O(10) (input
+    transform x 1000), so that the gate pre-activations are O(0.01 - 0.1): the tensor-core step agrees with the fp32 FMA step
+    to 3e-6 absolute (the ex2 / rcp gate formulation's own floor is ~3e-7) -- an 8-bit weight would be off by ~1e-4."""
     from trackmpnn_b200.engine import TrackEngine
     dev = torch.device('cuda:0')
     model = _model(dev, scale=1.0, edge_bias=None)
@@ -494,6 +495,7 @@ def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
         for name, p in model.named_parameters():
             if 'factor_grus' in name and p.dim() >= 2:
                 p.mul_(0.01)
+        model.input_transforms[0][3].weight.mul_(1000.0)
     seqs = _sequences([30, 34, 48, 58, 65])
     a = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=True, tensor_kernel=kernel)
     b = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=False, tensor_cores=False)
@@ -508,4 +510,4 @@ def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
         hb = b.h_alt[b.ga.phys[rows].long()].cpu().numpy()[edge]
         assert edge.sum() > 50
         scale = float(np.abs(hb).max())
-        assert scale > 0 and float(np.abs(ha - hb).max()) <= 2e-6 * scale, (float(np.abs(ha - hb).max()), scale)
+        assert scale > 3e-3 and float(np.abs(ha - hb).max()) <= 3e-6, (float(np.abs(ha - hb).max()), scale)
