@@ -292,6 +292,22 @@ int tmpnn_rows_times_w(const int32_t *r_dev, int r_host, const int32_t *a_rows, 
 int tmpnn_rows_outer(const int32_t *r_dev, int r_host, const int32_t *a_rows, const int32_t *b_rows,
                      const int32_t *mask, const float *A, const float *B, int ldb, int n, float *G, void *stream);
 
+/* Both contractions above for one operand A in ONE pass on the tensor cores (csrc/train_tc.cu: tcgen05.mma kind::f16 on a
+ * 3-term bf16 split, accumulators in TMEM; the [128 rows x 64] shared-memory images of A and X serve as K-major operands of
+ * C = A W and, read as MN-major, as the operands of G = A^T X, so nothing is transposed):
+ *   C[rc(i)][0:64] (+)= A[ra(i)][0:192] . W[192][col0:col0+64],   G[192][0:64] (leading dimension ldg) += sum_i A[ra(i)]^T X[rx(i)][0:64]
+ * for i < R (= *r_dev or r_host) with mask[ra(i)] >= 0; ra / rc / rx = a_rows / c_rows / x_rows[i] or i.  w_image: W packed
+ * by tmpnn_pack_w_tc (tmpnn_bwd_tc_image_bytes() bytes); partials: scratch of tmpnn_bwd_tc_partial_floats() floats (one G
+ * partial per SM, summed in a fixed order: the weight gradients are reproducible bit for bit, unlike tmpnn_rows_outer's float
+ * atomics).  A 128-wide W (msg_type concat) takes two calls, col0 = 0 and 64.  status: a device word for the bounded
+ * barrier waits (TMPNN_FLAG_TC_TIMEOUT). */
+size_t tmpnn_bwd_tc_image_bytes(void);
+size_t tmpnn_bwd_tc_partial_floats(void);
+int tmpnn_pack_w_tc(const float *W, int ldw, int col0, void *image, void *stream);
+int tmpnn_rows_gemm_tc(const int32_t *r_dev, int r_host, const int32_t *a_rows, const int32_t *c_rows, const int32_t *x_rows,
+                       const int32_t *mask, const float *A, const void *w_image, float *C, int ldc, int accumulate,
+                       const float *X, int ldx, float *partials, float *G, int ldg, int32_t *status, void *stream);
+
 /* Transpose of the gather / segmented sum (models/layers.py:90-95,103) in gather form:
  * edge row e: dh_in[e] = dhself[e] + dagg[det(src)] - dagg[det(dst)];
  * detection d: dh_in[d] = dhself[d] + sum over its future edges of dx[e][0:64] -/+ sum over its past edges of

@@ -10,7 +10,7 @@ if [ "$mode" = build ]; then
   for spec in "$@"; do
     name=${spec%%:*}; flags=${spec#*:}
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -I include $flags \
-      trackmpnn_b200/csrc/{mp_step,mp_step_tc,mp_step_tc3,graph_index,graph_ops,train,hungarian,gat,features}.cu -o build/lib_$name.so 2>/dev/null
+      trackmpnn_b200/csrc/{mp_step,mp_step_tc,mp_step_tc3,graph_index,graph_ops,train,train_tc,hungarian,gat,features}.cu -o build/lib_$name.so 2>/dev/null
     echo built build/lib_$name.so "($flags)"
   done
 else

@@ -106,6 +106,10 @@ _PROTOS = {
     'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 16, _I),
     'tmpnn_rows_times_w': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _VP], _I),
     'tmpnn_rows_outer': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP], _I),
+    'tmpnn_bwd_tc_image_bytes': ([], C.c_size_t),
+    'tmpnn_bwd_tc_partial_floats': ([], C.c_size_t),
+    'tmpnn_pack_w_tc': ([_VP, _I, _I, _VP, _VP], _I),
+    'tmpnn_rows_gemm_tc': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _VP, _VP], _I),
     'tmpnn_scatter_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _VP, _I, _VP, _VP, _I, _I, _VP], _I),
     'tmpnn_input_bwd': ([_VP, _I, _I, _I] + [_VP] * 9 + [_I, _I, _VP, _I, _I, _I] + [_VP] * 8, _I),
     'tmpnn_input_bn_groups_fwd': ([C.POINTER(InputGroup), _I] + [_VP] * 8 + [_I, _I, _VP], _I),
@@ -194,7 +198,7 @@ KERNELS_PER_CALL = {
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1, 'tmpnn_mp_edge_fwd_on_flag': 1, 'tmpnn_graph_force_det_scores': 1,
     'tmpnn_status_ack': 1,
-    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_scatter_bwd': 2,
+    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_rows_gemm_tc': 2, 'tmpnn_pack_w_tc': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_build_features': 1, 'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 1, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }
@@ -206,7 +210,7 @@ KERNELS_PER_CALL = {
 # Python calls per launch otherwise).  TrackEngine adds the reference's three phases (update / forward / decode) on top.
 _FAMILY_PREFIXES = (('tmpnn_input_', 'input'), ('tmpnn_index_', 'index'), ('tmpnn_aggregate', 'aggregate'),
                     ('tmpnn_gat_', 'aggregate'), ('tmpnn_mp_', 'mp_step'), ('tmpnn_graph_', 'graph'), ('tmpnn_status_', 'graph'),
-                    ('tmpnn_loss_', 'loss'), ('tmpnn_gate_bwd', 'backward'), ('tmpnn_rows_', 'backward'),
+                    ('tmpnn_loss_', 'loss'), ('tmpnn_gate_bwd', 'backward'), ('tmpnn_rows_', 'backward'), ('tmpnn_pack_w_tc', 'backward'),
                     ('tmpnn_scatter_bwd', 'backward'), ('tmpnn_pack_', 'pack'), ('tmpnn_ypred_', 'convert'),
                     ('tmpnn_coo_', 'convert'), ('tmpnn_edges_', 'convert'), ('tmpnn_build_features', 'input'),
                     ('tmpnn_lsap_', 'graph'))

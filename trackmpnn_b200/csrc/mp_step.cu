@@ -525,6 +525,7 @@ k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int
 int tmpnn_init_graph_ops();  // graph_ops.cu
 int tmpnn_init_tc();         // mp_step_tc.cu
 int tmpnn_init_tc3();        // mp_step_tc3.cu
+int tmpnn_init_train_tc();   // train_tc.cu
 static bool g_init_done = false;
 
 // Opts the big-shared-memory kernels in (once per process / device).  Called lazily by the
@@ -539,6 +540,8 @@ extern "C" int tmpnn_init(void) {
   rc = tmpnn_init_tc();
   if (rc) return rc;
   rc = tmpnn_init_tc3();
+  if (rc) return rc;
+  rc = tmpnn_init_train_tc();
   if (rc) return rc;
   g_init_done = true;
   return TMPNN_OK;

@@ -442,6 +442,28 @@ def _input_groups_forward(model, x, h_cur, ldh):
     return [(x.xd, xi, orow, nd, ne, per[k]) for k, (xi, orow, nd, ne) in enumerate(groups)]
 
 
+def _bwd_tc_partials(model, dev):
+    """Scratch of the tensor-core backward contraction: one weight-gradient partial per SM."""
+    sc = model.__dict__.setdefault('_tmpnn_bwd_tc', {})
+    t = sc.get('partials')
+    if t is None or t.device != dev:
+        t = sc['partials'] = torch.empty(int(L.lib().tmpnn_bwd_tc_partial_floats()), dtype=torch.float32, device=dev)
+    return t
+
+
+def _bwd_tc_image(model, w, col0):
+    """bf16 hi / lo UMMA image of columns [col0, col0 + 64) of a GRU weight, re-packed when the weight changes."""
+    sc = model.__dict__.setdefault('_tmpnn_bwd_tc', {})
+    key = ('img', w.data_ptr(), col0)
+    ent = sc.get(key)
+    if ent is None or ent[0] != w._version:
+        img = ent[1] if ent is not None else torch.empty(int(L.lib().tmpnn_bwd_tc_image_bytes()), dtype=torch.uint8, device=w.device)
+        L.call('tmpnn_pack_w_tc', L.ptr(w), int(w.shape[1]), int(col0), L.ptr(img), L.stream())
+        sc[key] = (w._version, img)
+        return img
+    return ent[1]
+
+
 class _MPStepFn(torch.autograd.Function):
     """One ``TrackMPNN.forward`` with everything its backward needs kept on the device: the state the
     step consumed, the GRU gates of every row, the detection aggregates, Linear1 outputs and the
@@ -557,13 +579,25 @@ class _MPStepFn(torch.autograd.Function):
             grads[b + 12] += gb_d[0]; grads[b + 13] += gb_d[1]
             # edge cell: rows with src >= 0
             dx = torch.empty((n, kx), **f32)
-            L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(e_wih), kx, L.ptr(dx), kx, 0, st)
-            L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(e_whh), H, L.ptr(dhself), H, 1, st)
             xbuf = torch.empty((n, kx), **f32)
             L.call('tmpnn_aggregate_edges', wg.g.c, ix.c, L.ptr(h_cur), ldh, col, concat, L.ptr(xbuf), st)
-            L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(xbuf), kx, kx, L.ptr(grads[b + 6]), st)
-            L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
-                   L.ptr(grads[b + 7]), st)
+            if use_tensor_path(model, n):
+                # tcgen05 (csrc/train_tc.cu): dx = dgi W_ih and dW_ih += dgi^T x in one pass over dgi, then dh_self += dgh W_hh
+                # and dW_hh += dgh^T h in one pass over dgh; a 128-wide W_ih (concat) is two 64-column passes
+                part = _bwd_tc_partials(model, dev)
+                for c0 in range(0, kx, H):
+                    L.call('tmpnn_rows_gemm_tc', None, n, None, None, None, L.ptr(wg.g.src), L.ptr(dgi),
+                           L.ptr(_bwd_tc_image(model, e_wih, c0)), L.ptr(dx) + 4 * c0, kx, 0, L.ptr(xbuf) + 4 * c0, kx,
+                           L.ptr(part), L.ptr(grads[b + 6]) + 4 * c0, kx, L.ptr(wg.g.status), st)
+                L.call('tmpnn_rows_gemm_tc', None, n, None, None, None, L.ptr(wg.g.src), L.ptr(dgh),
+                       L.ptr(_bwd_tc_image(model, e_whh, 0)), L.ptr(dhself), H, 1, L.ptr(h_cur) + 4 * col, ldh,
+                       L.ptr(part), L.ptr(grads[b + 7]), H, L.ptr(wg.g.status), st)
+            else:
+                L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(e_wih), kx, L.ptr(dx), kx, 0, st)
+                L.call('tmpnn_rows_times_w', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(e_whh), H, L.ptr(dhself), H, 1, st)
+                L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(xbuf), kx, kx, L.ptr(grads[b + 6]), st)
+                L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
+                       L.ptr(grads[b + 7]), st)
             # node cell: the detection list
             nd_dev, det_rows = L.ptr(ix.n_dets), L.ptr(ix.det_rows)
             dagg = torch.zeros((ix.cap_dets, H), **f32)
