@@ -270,6 +270,15 @@ int tmpnn_mp_step_fwd_train_agg(const tmpnn_graph *g, const tmpnn_index *ix, con
                                 int group, int num_groups, int concat, const float *edge_pack, const float *node_pack,
                                 const float *agg, float *gates, void *stream);
 
+/* The training forward on the tensor cores (msg_type 'diff'): tmpnn_mp_edge_fwd_tc that also stores the gates of every
+ * association row, and the detection-row half of tmpnn_mp_step_fwd_train alone (agg from tmpnn_aggregate_dets).  The three
+ * calls tmpnn_aggregate_dets, tmpnn_mp_edge_fwd_tc_train, tmpnn_mp_det_fwd_train replace tmpnn_mp_step_fwd_train on large
+ * graphs (states to ~2e-6 of the FMA kernel's). */
+int tmpnn_mp_edge_fwd_tc_train(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                               int group, int num_groups, const void *edge_image, float *gates, void *stream);
+int tmpnn_mp_det_fwd_train(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                           int group, int num_groups, const float *node_pack, const float *agg, float *gates, void *stream);
+
 /* Gate gradients of one feature group for every row of a single-slab graph (row type from src):
  * dh' = dh_out (nullable) + (dlogits + dscores p (1-p)) w_type;  dgi = [dpr,dpz,dpn], dgh = [dpr,dpz,dpn r]
  * ([n][192] each), dhself = dh' z ([n][64]).  Accumulates (atomically) the bias gradients of both cells
@@ -359,6 +368,16 @@ int tmpnn_loss_ce_bwd(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, c
 /* FocalLoss(gamma=0, alpha=None, size_average=True) (models/loss.py:57-74): mean(-log(p_t + 1e-10)). */
 int tmpnn_loss_focal_fwd(int n, const float *p, const int64_t *targets, float *per_elem, float *loss, void *stream);
 int tmpnn_loss_focal_bwd(int n, const float *p, const int64_t *targets, const float *grad_out, float *dp, void *stream);
+
+/* Batched trainer (trackmpnn_b200/train_engine.py): sum_i w[i] (-log(p_t[i] + 1e-10)) -- the BCE terms of train.py:76-85 for
+ * B chunks at once, w[i] = 1 / (rows of row i's kind in its chunk), i.e. the sum over chunks of their per-chunk means. */
+int tmpnn_loss_wbce_fwd(int n, const float *p, const int64_t *targets, const float *w, float *per_elem, float *loss, void *stream);
+int tmpnn_loss_wbce_bwd(int n, const float *p, const int64_t *targets, const float *w, const float *grad_out, float *dp, void *stream);
+
+/* dst[seg_dst[s] + r][0:ld] = src[seg_src[s] + r][0:ld] for r < seg_len[s], s < n_seg (max_len = the longest segment, for
+ * the grid): the rows every chunk carries from one step's block-diagonal layout into the next. */
+int tmpnn_rows_move(const float *src, float *dst, const int32_t *seg_src, const int32_t *seg_dst, const int32_t *seg_len,
+                    int n_seg, int ld, int max_len, void *stream);
 
 /* ---- feature construction: the step in front of the path (dataset/kitti_mot.py:545-566) ---- */
 

@@ -508,6 +508,6 @@ def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
         edge = (a.ga.ts[rows] < 0).cpu().numpy()
         ha = a.h_alt[a.ga.phys[rows].long()].cpu().numpy()[edge]     # 3 ticks: the last step wrote h_alt
         hb = b.h_alt[b.ga.phys[rows].long()].cpu().numpy()[edge]
-        assert edge.sum() > 50
+        assert edge.sum() > 20
         scale = float(np.abs(hb).max())
         assert scale > 3e-3 and float(np.abs(ha - hb).max()) <= 3e-6, (float(np.abs(ha - hb).max()), scale)

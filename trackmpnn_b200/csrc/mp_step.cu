@@ -599,6 +599,13 @@ extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, con
   return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, nullptr, stream);
 }
 
+extern "C" int tmpnn_mp_det_fwd_train(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                      int group, int num_groups, const float* node_pack, const float* agg, float* gates,
+                                      void* stream) {
+  TMPNN_REQUIRE(gates, "null argument");
+  return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, gates, stream);
+}
+
 extern "C" int tmpnn_mp_step_fwd_train(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
                                        int group, int num_groups, int concat, const float* edge_pack,
                                        const float* node_pack, float* agg, float* gates, void* stream) {

@@ -133,13 +133,16 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
 // ---- the kernel ------------------------------------------------------------------------------
 // The producers gather h[src], h[dst], subtract and split per association row (msg_type 'diff' only); the form with
 // the endpoints prepared once per detection row lives in mp_step_tc3.cu.
+// TRAIN: additionally stores r | z | n | (W_hn h + b_hn) of every association row into gates[row][4][64] (what the backward
+// pass needs from torch.nn.GRUCell, models/layers.py:97): the training forward on the tensor cores.
+template <bool TRAIN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
              const int32_t* __restrict__ n_rows, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
              int cap_rows, int num_seqs, const int32_t* __restrict__ tile_ptr, const unsigned char* __restrict__ image,
              float* __restrict__ logit, float* __restrict__ score, int first_group, int last_group,
              int32_t* __restrict__ status, const int32_t* __restrict__ phys, const int32_t* __restrict__ psrc,
-             const int32_t* __restrict__ pdst) {
+             const int32_t* __restrict__ pdst, float* __restrict__ gates) {
   extern __shared__ unsigned char smem_dyn[];
   const int total = tile_ptr[num_seqs];
   if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
@@ -311,6 +314,8 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
     float* dot_part = reinterpret_cast<float*>(sm + OFF_DOT);
     const f32x2 NLOG2E2 = pk2(c_tc_expo[1], c_tc_expo[1]), TWOLOG2E2 = pk2(c_tc_expo[3], c_tc_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+    const float inv_s = 1.0f / *reinterpret_cast<const float*>(sm + OFF_HEADB + 8);  // 2^-k of the weight pre-scale (exact)
+    const f32x2 INVS2 = pk2(inv_s, inv_s);
     // this row's coordinates and its source (< 0: not an edge row) are fetched two tiles ahead, the source's
     int seq = 0, it = 0;
     auto coords = [&](int tile, size_t& rw, int& nr, int& lrr) {
@@ -387,6 +392,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
           const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
           const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
           f32x2 o[2];
+          f32x2 gr[2], gz[2], gn[2], gh[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int i = 4 * v + 2 * e;  // columns j0 + i, j0 + i + 1
@@ -400,6 +406,14 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
             const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[4 * ch + 2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
             o[e] = ov;
             dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+            if (TRAIN) { gr[e] = rg; gz[e] = zg; gn[e] = ng; gh[e] = mul2(add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), INVS2); }
+          }
+          if (TRAIN && valid) {   // columns j0 + 4 v .. + 3 of the four gates of this row
+            float* gp = gates + row_cur * (4 * H) + j0 + 4 * v;
+            *reinterpret_cast<ulonglong2*>(gp) = make_ulonglong2(gr[0], gr[1]);
+            *reinterpret_cast<ulonglong2*>(gp + H) = make_ulonglong2(gz[0], gz[1]);
+            *reinterpret_cast<ulonglong2*>(gp + 2 * H) = make_ulonglong2(gn[0], gn[1]);
+            *reinterpret_cast<ulonglong2*>(gp + 3 * H) = make_ulonglong2(gh[0], gh[1]);
           }
           *reinterpret_cast<ulonglong2*>(tbuf + lane * 128 + (((2 * ch + v) ^ (lane & 7)) << 4)) = make_ulonglong2(o[0], o[1]);
         }
@@ -510,7 +524,8 @@ k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* _
 }  // namespace
 
 int tmpnn_init_tc() {
-  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_mp_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   TMPNN_CUDA_TRY(cudaFuncSetAttribute(k_det_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
   return TMPNN_OK;
 }
@@ -527,8 +542,8 @@ extern "C" int tmpnn_pack_gru_tc(const float* w_ih, const float* w_hh, const flo
   return TMPNN_OK;
 }
 
-extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
-                                    int group, int num_groups, const void* edge_image, void* stream) {
+static int edge_tc_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
+                          int num_groups, const void* edge_image, float* gates, void* stream) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && edge_image && ix->tile128_ptr, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
@@ -536,12 +551,29 @@ extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix,
   if (rc) return rc;
   TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc_expo, (const unsigned char*)edge_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice,
                                          (cudaStream_t)stream));
-  k_mp_edge_tc<<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-      h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
-      (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
-      g->psrc, g->pdst);
+  if (gates)
+    k_mp_edge_tc<true><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
+        (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
+        g->psrc, g->pdst, gates);
+  else
+    k_mp_edge_tc<false><<<TMPNN_SM_COUNT, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        h_in, h_out, ldh, group * H, g->n_rows, g->src, g->dst, g->cap_rows, g->num_seqs, ix->tile128_ptr,
+        (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys,
+        g->psrc, g->pdst, nullptr);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
+}
+
+extern "C" int tmpnn_mp_edge_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                    int group, int num_groups, const void* edge_image, void* stream) {
+  return edge_tc_launch(g, ix, h_in, h_out, ldh, group, num_groups, edge_image, nullptr, stream);
+}
+
+extern "C" int tmpnn_mp_edge_fwd_tc_train(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                          int group, int num_groups, const void* edge_image, float* gates, void* stream) {
+  TMPNN_REQUIRE(gates, "null argument");
+  return edge_tc_launch(g, ix, h_in, h_out, ldh, group, num_groups, edge_image, gates, stream);
 }
 
 extern "C" int tmpnn_mp_edge_fwd_tc_pre(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,

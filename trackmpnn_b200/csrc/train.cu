@@ -505,11 +505,70 @@ __global__ void k_focal_bwd(int n, const float* __restrict__ p, const int64_t* _
   }
 }
 
+// weighted form for the batched trainer: every row carries its own weight (1 / rows of its kind in its chunk = the
+// per-chunk means of train.py:76-85; 0 = the row does not count)
+__global__ void k_wbce_fwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t, const float* __restrict__ w,
+                           float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = w[i] != 0.f ? -w[i] * logf((t[i] == 1 ? p[i] : 1.0f - p[i]) + 1e-10f) : 0.f;
+}
+__global__ void k_wbce_bwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t, const float* __restrict__ w,
+                           const float* __restrict__ gout, float* __restrict__ dp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const bool pos = t[i] == 1;
+    const float pt = (pos ? p[i] : 1.0f - p[i]) + 1e-10f;
+    dp[i] = w[i] != 0.f ? gout[0] * w[i] * (pos ? -1.0f : 1.0f) / pt : 0.f;
+  }
+}
+
+// dst[seg_dst[s] + r][:] = src[seg_src[s] + r][:] for r < seg_len[s]: the rows a chunk carries from one step's
+// block-diagonal layout into the next (float4 units; grid.y = segment)
+__global__ void __launch_bounds__(256) k_rows_move(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                   const int32_t* __restrict__ seg_src, const int32_t* __restrict__ seg_dst,
+                                                   const int32_t* __restrict__ seg_len, int ld4) {
+  const int s = blockIdx.y;
+  const size_t n4 = (size_t)seg_len[s] * ld4;
+  const float4* a = src + (size_t)seg_src[s] * ld4;
+  float4* b = dst + (size_t)seg_dst[s] * ld4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) b[i] = __ldg(a + i);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+extern "C" int tmpnn_loss_wbce_fwd(int n, const float* p, const int64_t* targets, const float* w, float* per_elem, float* loss,
+                                   void* stream) {
+  TMPNN_REQUIRE(p && targets && w && per_elem && loss && n > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_wbce_fwd<<<tmpnn_div_up(n, 256), 256, 0, st>>>(n, p, targets, w, per_elem);
+  TMPNN_LAUNCH_CHECK();
+  k_sum<<<1, 256, 0, st>>>(per_elem, nullptr, 0, n, 0.f, loss);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_loss_wbce_bwd(int n, const float* p, const int64_t* targets, const float* w, const float* grad_out,
+                                   float* dp, void* stream) {
+  TMPNN_REQUIRE(p && targets && w && grad_out && dp && n > 0, "bad argument");
+  k_wbce_bwd<<<tmpnn_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, targets, w, grad_out, dp);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
+extern "C" int tmpnn_rows_move(const float* src, float* dst, const int32_t* seg_src, const int32_t* seg_dst,
+                               const int32_t* seg_len, int n_seg, int ld, int max_len, void* stream) {
+  TMPNN_REQUIRE(src && dst && seg_src && seg_dst && seg_len && ld % 4 == 0, "bad argument");
+  TMPNN_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "rows must be 16-byte aligned");
+  if (n_seg <= 0 || max_len <= 0) return TMPNN_OK;
+  dim3 grid(max(1, min(tmpnn_div_up((long long)max_len * (ld / 4), 256 * 4), 64)), n_seg);
+  k_rows_move<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, seg_src, seg_dst, seg_len, ld / 4);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
 extern "C" int tmpnn_gate_bwd(int n_rows, const int32_t* src, const float* gates, const float* h_prev, const float* h_new,
                               int ldh, int col, const float* dh_out, const float* dlogits, const float* dscores,
                               const float* score, const float* head_w_edge, const float* head_w_node, float* dgi,

@@ -41,7 +41,8 @@ constexpr int BW_OFF_A = 50 * 1024;           // images (1024-aligned)
 constexpr int BW_IMG = TCM * 128;             // [128 rows x 64 columns] bf16 = 16 KB
 // image slots: A hi 0..2, A lo 3..5 (column block a sits in slot (a + 1) % 3, so that both M blocks of the G product --
 // columns [0,128) and [128,192) + [0,64) -- are two ADJACENT slots), X hi 6, X lo 7
-constexpr int BW_SMEM = BW_OFF_A + 8 * BW_IMG + 1024;
+constexpr int BW_OFF_T = BW_OFF_A + 8 * BW_IMG;          // epilogue transpose buffer: 4 warps x [32 rows x 64 floats]
+constexpr int BW_SMEM = BW_OFF_T + 4 * 8192 + 1024;
 constexpr int BW_EPI = 4, BW_PROD = 8;
 constexpr int BW_THREADS = 32 * (BW_EPI + BW_PROD + 1);
 constexpr int BW_TMEM_COLS = 256;             // C stage 0 | C stage 1 | G rows 0-127 | G rows 128-191 (+ a duplicate block)
@@ -185,32 +186,44 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
       mbar_wait(bar_afree, ((uint32_t)it & 1u) ^ 1u, status);  // the previous tile's MMAs have read the images
-#pragma unroll 2
-      for (int p = 0; p < 8; ++p) {
-        const int row = g + 16 * p, i = tile * TCM + row;
-        float4 va[3], vx;
-        va[0] = va[1] = va[2] = vx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < R) {
-          const int ra = a_rows ? __ldg(a_rows + i) : i;
-          if (!mask || __ldg(mask + ra) >= 0) {
-            const float* ap = A + (size_t)ra * BGK + 4 * l;
-            va[0] = ldg4(ap); va[1] = ldg4(ap + 64); va[2] = ldg4(ap + 128);
-            const int rx = x_rows ? __ldg(x_rows + i) : i;
-            vx = ldg4(X + (size_t)rx * ldx + 4 * l);
-          }
-        }
-        const uint32_t off = off0 + 2048u * p;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          uint2 hi, lo;
-          split4_bf16(va[a], hi, lo);
-          *reinterpret_cast<uint2*>(sm + BW_OFF_A + slot_of(a) * BW_IMG + off) = hi;
-          *reinterpret_cast<uint2*>(sm + BW_OFF_A + (3 + slot_of(a)) * BW_IMG + off) = lo;
+      for (int hp = 0; hp < 2; ++hp) {
+        // four rows per round: indices first, then 16 unconditional 128-bit loads in flight (rows past the end and masked rows
+        // read a valid row and are zeroed afterwards), then the conversions -- the sweep is bound by HBM latency otherwise
+        int ra[4], rx[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = min(tile * TCM + g + 16 * (4 * hp + q), R - 1);
+          ra[q] = a_rows ? __ldg(a_rows + i) : i;
+          rx[q] = x_rows ? __ldg(x_rows + i) : i;
         }
-        uint2 hi, lo;
-        split4_bf16(vx, hi, lo);
-        *reinterpret_cast<uint2*>(sm + BW_OFF_A + 6 * BW_IMG + off) = hi;
-        *reinterpret_cast<uint2*>(sm + BW_OFF_A + 7 * BW_IMG + off) = lo;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          ok[q] = tile * TCM + g + 16 * (4 * hp + q) < R && (!mask || __ldg(mask + ra[q]) >= 0);
+        float4 va[4][3], vx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* ap = A + (size_t)ra[q] * BGK + 4 * l;
+          va[q][0] = ldg4(ap); va[q][1] = ldg4(ap + 64); va[q][2] = ldg4(ap + 128);
+          vx[q] = ldg4(X + (size_t)rx[q] * ldx + 4 * l);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t off = off0 + 2048u * (4 * hp + q);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            uint2 hi, lo;
+            split4_bf16(ok[q] ? va[q][a] : z4, hi, lo);
+            *reinterpret_cast<uint2*>(sm + BW_OFF_A + slot_of(a) * BW_IMG + off) = hi;
+            *reinterpret_cast<uint2*>(sm + BW_OFF_A + (3 + slot_of(a)) * BW_IMG + off) = lo;
+          }
+          uint2 hi, lo;
+          split4_bf16(ok[q] ? vx[q] : z4, hi, lo);
+          *reinterpret_cast<uint2*>(sm + BW_OFF_A + 6 * BW_IMG + off) = hi;
+          *reinterpret_cast<uint2*>(sm + BW_OFF_A + 7 * BW_IMG + off) = lo;
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -230,28 +243,37 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
       }
       mbar_wait(bar_cdone + 8 * stage, (uint32_t)(it >> 1) & 1u, status);
       tc_fence_after();
-      float* crow = C + (size_t)max(rc, 0) * ldc;
+      // TMEM -> registers (thread = row) -> this warp's [32 rows x 64 floats] buffer (16-byte chunks XOR-swizzled by row), then
+      // the accumulator stage is free; the rows go out 2 per instruction as full 256-byte rows
+      unsigned char* tb = sm + BW_OFF_T + warp * 8192;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         float v[16];
         tmem_ld16(lane_base + (uint32_t)(64 * stage + 16 * ch), v);
         tmem_ld_wait();
-        if (rc >= 0) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            float4* dst = reinterpret_cast<float4*>(crow + 16 * ch + 4 * q);
-            if (accumulate) {
-              const float4 pv = *dst;
-              o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
-            }
-            *dst = o;
-          }
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(tb + lane * 256 + (((4 * ch + q) ^ (lane & 15)) << 4)) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_cfree + 8 * stage);
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        const int rr = 2 * k + (lane >> 4), cc = lane & 15;
+        const int rcr = __shfl_sync(0xffffffffu, rc, rr);
+        if (rcr >= 0) {
+          float4 o = *reinterpret_cast<const float4*>(tb + rr * 256 + ((cc ^ (rr & 15)) << 4));
+          float4* dst = reinterpret_cast<float4*>(C + (size_t)rcr * ldc + 4 * cc);
+          if (accumulate) {
+            const float4 pv = *dst;
+            o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+          }
+          *dst = o;
+        }
+      }
+      __syncwarp();   // the buffer is rewritten by the next tile
     }
     // the weight-gradient partial of this CTA: rows [0,128) from the first M block, [128,192) from the lower half of the second
     mbar_wait(bar_gdone, 0u, status);
@@ -284,9 +306,16 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int n_part, float* __restrict__ G, int ldg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BGK * 64) return;
-  float s = 0.f;
-  for (int c = 0; c < n_part; ++c) s += partials[(size_t)c * BGK * 64 + i];
-  G[(size_t)(i / 64) * ldg + (i % 64)] += s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains of loads in flight; the combination order is fixed
+  int c = 0;
+  for (; c + 3 < n_part; c += 4) {
+    s0 += partials[(size_t)c * BGK * 64 + i];
+    s1 += partials[(size_t)(c + 1) * BGK * 64 + i];
+    s2 += partials[(size_t)(c + 2) * BGK * 64 + i];
+    s3 += partials[(size_t)(c + 3) * BGK * 64 + i];
+  }
+  for (; c < n_part; ++c) s0 += partials[(size_t)c * BGK * 64 + i];
+  G[(size_t)(i / 64) * ldg + (i % 64)] += (s0 + s1) + (s2 + s3);
 }
 
 bool g_bw_init = false;

@@ -386,8 +386,12 @@ class NewRowGroups:
     the feature rows, every group ``(x_idx, out_rows, n_dets, n_edge_rows)`` is one chunk's share -- one BatchNorm
     batch, as in the reference, which feeds one chunk per forward."""
 
-    def __init__(self, xd, groups, x_idx_all=None):
+    def __init__(self, xd, groups, x_idx_all=None, carry=None):
         self.xd, self.groups, self.x_idx_all = xd, groups, x_idx_all   # x_idx_all: the groups' x_idx concatenated
+        # carry = (seg_src, seg_dst, seg_len int32 device tensors, number of segments, longest segment): h_in is then the
+        # PREVIOUS step's state in the previous block-diagonal layout; segment s (one chunk) moves seg_len[s] rows from
+        # row seg_src[s] there to row seg_dst[s] of this step's layout, everything else starts at zero
+        self.carry = carry
 
 
 def _input_rows_forward(model, xd, x_idx, out_rows, nd, n_edge_rows, h_cur, ldh):
@@ -480,10 +484,21 @@ class _MPStepFn(torch.autograd.Function):
         if isinstance(x, NewRowGroups):
             # batched trainer: h_in already has one row per graph row (zeros where rows are new); the new detection rows
             # come in groups, one per chunk = one BatchNorm batch each (the reference normalises chunk by chunk)
-            if h_in is None or int(h_in.shape[0]) != n_tot:
-                raise ValueError('with NewRowGroups h_in must have one row per graph row')
-            n_old, n_new = n_tot, 0
-            h_cur = h_in.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+            n_new = 0
+            if x.carry is not None or h_in is None:
+                h_cur = torch.zeros((n_tot, ldh), dtype=torch.float32, device=dev)
+                n_old = 0 if h_in is None else int(h_in.shape[0])
+                if h_in is not None and x.carry is not None:
+                    seg_src, seg_dst, seg_len, n_seg, max_len = x.carry
+                    L.call('tmpnn_rows_move', L.ptr(h_in.detach().contiguous()), L.ptr(h_cur), L.ptr(seg_src), L.ptr(seg_dst),
+                           L.ptr(seg_len), n_seg, ldh, max_len, L.stream())
+                ctx.carry = x.carry
+            else:
+                if int(h_in.shape[0]) != n_tot:
+                    raise ValueError('with NewRowGroups and no carry map h_in must have one row per graph row')
+                n_old = n_tot
+                h_cur = h_in.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+                ctx.carry = None
             saved_in = _input_groups_forward(model, x, h_cur, ldh)
         else:
             n_new = int(x.size()[0])
@@ -510,7 +525,15 @@ class _MPStepFn(torch.autograd.Function):
             concat = int(gru.msg_type == 'concat')
             gt = torch.empty((n_tot, 4 * H), dtype=torch.float32, device=dev)
             agg = torch.empty((ix.cap_dets, H), dtype=torch.float32, device=dev)
-            if gru.gat is None:
+            if gru.gat is None and not concat and use_tensor_path(model, n_tot):
+                # large graphs: the association rows' step on the tensor cores with the gates stored for the backward pass
+                L.call('tmpnn_aggregate_dets', wg.g.c, ix.c, L.ptr(h_cur), ldh, g * H, L.ptr(agg), st)
+                L.call('tmpnn_mp_edge_fwd_tc_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G,
+                       L.ptr(packed_cells_tc(model)[g]), L.ptr(gt), st)
+                L.call('tmpnn_mp_det_fwd_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]),
+                       L.ptr(agg), L.ptr(gt), st)
+                gats.append(None)
+            elif gru.gat is None:
                 L.call('tmpnn_mp_step_fwd_train', wg.g.c, ix.c, L.ptr(h_cur), L.ptr(h_out), ldh, g, G, concat,
                        L.ptr(packs[g][0]), L.ptr(packs[g][1]), L.ptr(agg), L.ptr(gt), st)
                 gats.append(None)
@@ -651,4 +674,11 @@ class _MPStepFn(torch.autograd.Function):
                        L.ptr(grads[b + 0]), L.ptr(grads[b + 1]), L.ptr(grads[b + 2]), L.ptr(grads[b + 3]),
                        L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), st)
         dh_in = dh_cur[:ctx.n_old] if ctx.has_h_in else None
+        if ctx.has_h_in and getattr(ctx, 'carry', None) is not None:
+            # back through the layout change: the rows of the previous step's layout collect the gradient of the rows they
+            # were moved to (chunks that took no part in this step get none)
+            seg_src, seg_dst, seg_len, n_seg, max_len = ctx.carry
+            dh_in = torch.zeros((ctx.n_old, ldh), **f32)
+            L.call('tmpnn_rows_move', L.ptr(dh_cur), L.ptr(dh_in), L.ptr(seg_dst), L.ptr(seg_src), L.ptr(seg_len), n_seg, ldh,
+                   max_len, st)
         return (None, None, None, dh_in) + (tuple(None for _ in grads) if direct is not None else tuple(grads))

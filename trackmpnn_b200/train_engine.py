@@ -208,16 +208,13 @@ class TrainBatch:
             xs.append(d['x_new'])
             xo += nd
         xd = torch.cat(xs).contiguous() if xo else torch.zeros((1, per_chunk[act[0]][i]['x_new'].shape[1]), device=dev)
-        st.new_rows = NewRowGroups(xd, groups, torch.arange(max(1, xo), dtype=_I32, device=dev))
-        # rows carried over from the previous step's layout
+        # rows carried over from the previous step's layout: one contiguous segment per chunk (tmpnn_rows_move)
+        carry = None
         if prev is not None:
-            src_idx, dst_idx = [], []
-            for c in act:
-                n_old = per_chunk[c][i]['n_old']
-                src_idx.append(np.arange(prev.base[c], prev.base[c] + n_old))
-                dst_idx.append(np.arange(base[c], base[c] + n_old))
-            st.carry_from = torch.from_numpy(np.concatenate(src_idx)).to(dev)
-            st.carry_to = torch.from_numpy(np.concatenate(dst_idx)).to(dev)
+            seg = np.array([[prev.base[c], base[c], per_chunk[c][i]['n_old']] for c in act], dtype=np.int32)
+            t = torch.from_numpy(np.ascontiguousarray(seg.T)).to(dev)
+            carry = (t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), len(act), int(seg[:, 2].max()))
+        st.new_rows = NewRowGroups(xd, groups, torch.arange(max(1, xo), dtype=_I32, device=dev), carry=carry)
         # loss bookkeeping: targets (labels only), row sets, per-chunk mean weights of the two BCE terms
         labels = g.label[:n].to(torch.int64)
         is_det = g.ts[:n] >= 0
@@ -230,30 +227,48 @@ class TrainBatch:
         wd = torch.from_numpy(1.0 / np.maximum(nd_c, 1)).to(device=dev, dtype=torch.float32)[chunk_of_row]
         we = torch.from_numpy(1.0 / np.maximum(ne_c, 1)).to(device=dev, dtype=torch.float32)[chunk_of_row]
         w = torch.where(is_det, wd, we)
-        st.bce_w = w
+        st.bce_w = w.contiguous()
+        st.bce_w_edges = torch.where(is_det, torch.zeros_like(w), w).contiguous()   # without the TP classifier: edge rows only
+        st.targets64 = st.targets.to(torch.int64).contiguous()
         st.n_edge_rows = int(ne_c.sum())
         return st
 
 
+class _WeightedBCE(torch.autograd.Function):
+    """sum_i w_i (-log(p_t,i + 1e-10)): FocalLoss(gamma = 0) of every chunk's edge rows and detection rows, each with its own
+    per-chunk mean (train.py:76-85), as one kernel pair over all rows of the batch."""
+
+    @staticmethod
+    def forward(ctx, p, targets, w):
+        n = int(p.numel())
+        pc = p.detach().to(torch.float32).contiguous().view(-1)
+        per = torch.empty(n, dtype=torch.float32, device=p.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+        L.call('tmpnn_loss_wbce_fwd', n, L.ptr(pc), L.ptr(targets), L.ptr(w), L.ptr(per), L.ptr(loss), L.stream())
+        ctx.pc, ctx.t, ctx.w, ctx.n, ctx.shape = pc, targets, w, n, p.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = gout.detach().to(torch.float32).contiguous().view(1)
+        dp = torch.empty(ctx.n, dtype=torch.float32, device=ctx.pc.device)
+        L.call('tmpnn_loss_wbce_bwd', ctx.n, L.ptr(ctx.pc), L.ptr(ctx.t), L.ptr(ctx.w), L.ptr(g), L.ptr(dp), L.stream())
+        return dp.view(ctx.shape), None, None
+
+
 def batch_loss(model, batch, tp_classifier=True):
     """Forward + losses of every step of ``batch`` (``train.py:65-127`` for all chunks at once): returns the scalar
-    loss = sum over chunks of (CE + BCE terms summed over the chunk's steps).  Call ``.backward()`` on it."""
+    loss = sum over chunks of (CE + BCE terms summed over the chunk's steps).  Call ``.backward()`` on it.
+
+    Per step: ONE autograd Function for the whole message-passing step (it also moves the carried rows from the previous
+    step's block-diagonal layout into this one), one for the CE term, one for both BCE terms -- no torch indexing ops."""
     ce = CELoss()
     params = _param_list(model)
     loss = None
     h_prev = None
-    ldh = len(model.feature_idx) * H
     for st in batch.steps:
-        h_in = torch.zeros((st.n, ldh), dtype=torch.float32, device=batch.device)
-        if h_prev is not None:
-            h_in = h_in.index_copy(0, st.carry_to, h_prev.index_select(0, st.carry_from))
-        scores, logits, h_prev = _MPStepFn.apply(model, st.holder, st.new_rows, h_in, *params)[:3]
-        p = scores[:, 0]
-        tgt = st.targets.to(p.dtype)
-        p_t = p * tgt + (1 - p) * (1 - tgt)                      # FocalLoss(gamma=0): mean(-log(p_t + 1e-10)), per chunk
-        bce = -(torch.log(p_t + 1e-10) * st.bce_w)
-        l = ce(logits, st.targets, st.holder, st.idx_node) + bce[st.idx_edge].sum()
-        if tp_classifier:
-            l = l + bce[st.idx_node].sum()
+        scores, logits, h_prev = _MPStepFn.apply(model, st.holder, st.new_rows, h_prev, *params)[:3]
+        l = ce(logits, st.targets, st.holder, st.idx_node) + \
+            _WeightedBCE.apply(scores, st.targets64, st.bce_w if tp_classifier else st.bce_w_edges)
         loss = l if loss is None else loss + l
     return loss
