@@ -233,15 +233,18 @@ def train_chunk_cuda(model, opt, X, y):
     return edges, float(loss.item())
 
 
-def run_train_batched(a, dev, model, opt, chunk, steps=9):
+def run_train_batched(a, dev, model, chunk, steps=9):
     """The same training step for B chunks at once (trackmpnn_b200/train_engine.py): per message-passing step ONE
     block-diagonal graph, so every kernel runs once for the whole batch; BatchNorm statistics and the BCE means stay
     per chunk, the batch loss is the sum of the chunk losses (verified against the chunk-by-chunk path in
-    tests/test_train_engine_gpu.py).  The graphs depend on the labels only (teacher forcing), so a batch is built once
-    and replayed; `value` times the optimizer steps, `value_incl_graph_build` charges a full rebuild of the batch's
-    graphs to every step, which is what the reference's loop does (train.py:92-104)."""
+    tests/test_train_engine_gpu.py and against oracle/train_ref.py at this size).  Forward of the association rows and the two
+    backward contractions run on tcgen05; the backward kernels accumulate into one flat gradient buffer; the whole optimizer
+    step (zero, forward, CE + BCE, backward, Adam) is replayed as CUDA graphs (GraphedTrainStep).  The graphs depend on the
+    labels only (teacher forcing), so a batch is built once and replayed; `value` times the optimizer steps,
+    `value_incl_graph_build` charges a full rebuild of the batch's graphs to every step, which is what the reference's loop does
+    (train.py:92-104)."""
     import torch
-    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    from trackmpnn_b200.train_engine import GraphedTrainStep, TrainBatch
     B = a.train_batch
     chunks = []
     for i in range(B):
@@ -253,31 +256,29 @@ def run_train_batched(a, dev, model, opt, chunk, steps=9):
     batch = TrainBatch(chunks, dev)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
+    step = GraphedTrainStep(model, batch, lr=1e-4, weight_decay=5e-4)
 
-    def step():
-        opt.zero_grad()
-        loss = batch_loss(model, batch)
-        loss.backward()
-        opt.step()
-        return loss
-
-    step(); step(); step()
-    torch.cuda.synchronize()
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        loss = step()
+    def timed(fn):
+        fn(); fn(); fn()
         torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    lv = float(loss.item())
-    # a step allocates and frees a few GB of per-step buffers (gates, gradients): the caching allocator occasionally
-    # stalls one step; the median is the steady state, the mean is reported beside it
-    dt = float(np.median(times))
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        return float(np.median(times)), float(np.mean(times))
+
+    dt_eager, _ = timed(step.eager)
+    step.capture()
+    dt, dt_mean = timed(step.replay)
+    lv = float(step.loss.item())
     return {'chunks_per_batch': B, 'message_passing_steps': len(batch.steps), 'edge_rows_per_batch': int(batch.edge_rows),
             'value': batch.edge_rows / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': B / dt,
-            'ms_per_batch': 1e3 * dt, 'ms_per_batch_mean': 1e3 * float(np.mean(times)), 'graph_build_ms_per_chunk': 1e3 * t_build / B, 'loss': lv,
+            'ms_per_batch': 1e3 * dt, 'ms_per_batch_mean': 1e3 * dt_mean, 'ms_per_batch_eager_launches': 1e3 * dt_eager,
+            'graph_build_ms_per_chunk': 1e3 * t_build / B, 'loss': lv,
             'value_incl_graph_build': batch.edge_rows / (dt + t_build), 'chunks_per_s_incl_graph_build': B / (dt + t_build),
-            'graph_builder': batch.builder}
+            'graph_builder': batch.builder, 'api': 'GraphedTrainStep.replay() (CUDA graphs: zero + forward + losses + backward | Adam)'}
 
 
 def run_train_leg(a, dev):
@@ -309,7 +310,7 @@ def run_train_leg(a, dev):
                        f'tp_classifier, teacher forcing, BPTT over all steps, CE+BCE, Adam), drop-in modules, 1 chunk at a time',
            'value': edges / dt, 'unit': 'edge-updates/s (forward+backward+optimizer)', 'chunks_per_s': a.train_chunks / dt,
            'ms_per_chunk': 1e3 * dt / a.train_chunks, 'edge_rows_per_chunk': edges // max(1, a.train_chunks)}
-    out['batched'] = run_train_batched(a, dev, model, opt, chunk)
+    out['batched'] = run_train_batched(a, dev, model, chunk)
     if not a.skip_cpu:
         from oracle import train_ref as T, trackmpnn_oracle as O
         params = O.init_params('2d', 3, 64, 'diff', seed=5)
@@ -438,10 +439,9 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     import torch.distributed as dist
     from trackmpnn_b200 import parallel, synth
     from trackmpnn_b200.models.track_mpnn import TrackMPNN
-    from trackmpnn_b200.train_engine import TrainBatch, batch_loss
+    from trackmpnn_b200.train_engine import GraphedTrainStep, TrainBatch, batch_loss
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories('kitti'), 64, 0, 'diff').to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=5e-4)
     flat = parallel.FlatGradients(model)
     params = list(model.parameters())
     B, n_steps = a.train_batch, a.train_chunks
@@ -465,18 +465,20 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
     # BatchNorm running statistics moved during the check: every rank did the same two forward passes -> still identical
     # ---- timed steps ----------------------------------------------------------------------------------------------------
     batch = TrainBatch([chunk(2000 + rank * 1000 + i) for i in range(B)], dev)
+    step = GraphedTrainStep(model, batch, lr=1e-4, weight_decay=5e-4, allreduce=True)
+    step.capture()          # three real (all-reduced) steps on every rank, then [zero + forward + backward] | [Adam] as graphs
+    flat, nfl = step.flat, int(step.flat.flat.numel())
     ar_ms = 0.0
     for i in range(n_steps + 2):
         if i == 2:
             barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-        flat.zero()
-        batch_loss(model, batch).backward()
+        step._g_fb.replay()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        nfl = flat.allreduce(average=True)
+        flat.allreduce(average=True)
         a1.record()
-        opt.step()
+        step._g_opt.replay()
         if i >= 2:
             torch.cuda.synchronize()
             ar_ms += a0.elapsed_time(a1)

@@ -182,3 +182,36 @@ def test_batched_trainer_against_training_oracle_at_bench_size():
         want = grads_ref[name]
         atol = 2e-3 * float(np.abs(want).max()) + 1e-6 * gmax + 1e-9
         np.testing.assert_allclose(p.grad.detach().cpu().numpy().reshape(want.shape), want, atol=atol, rtol=0, err_msg=name)
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """GraphedTrainStep: [zero + forward + losses + backward] and [Adam] replayed as CUDA graphs (the weight images are
+    re-packed inside the captured work).  Five optimizer steps -- three eager ones during capture, two replays -- leave the
+    same parameters and loss as five eager steps of a second model (float atomics in a few small gradient sums: 1e-5)."""
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import GraphedTrainStep, TrainBatch
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    model = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev).train()
+    ref = copy.deepcopy(model)
+    chunks, _ = _kitti_chunks(dev, [80, 81, 82, 83, 84, 85], 30)     # > 8192 rows per step: the tcgen05 kernels run
+    batch = TrainBatch(chunks, dev)
+    a = GraphedTrainStep(model, batch, lr=1e-3, weight_decay=5e-4)
+    b = GraphedTrainStep(ref, batch, lr=1e-3, weight_decay=5e-4)
+    a.capture(warmup=3)
+    a.replay(); a.replay()
+    for _ in range(5):
+        b.eager()
+    torch.cuda.synchronize()
+    assert abs(float(a.loss) - float(b.loss)) <= 1e-5 * abs(float(b.loss))
+    moved = 0.0
+    for (name, p), q in zip(model.named_parameters(), ref.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-5, atol=1e-7, err_msg=name)
+    torch.manual_seed(5)
+    fresh = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev)
+    for p, q in zip(model.parameters(), fresh.parameters()):
+        moved = max(moved, float((p - q).abs().max()))
+    assert moved > 1e-3     # the replays really trained
+    for bm, br in zip(model.input_transforms, ref.input_transforms):   # BatchNorm bookkeeping advanced inside the graph too
+        np.testing.assert_allclose(bm[1].running_mean.cpu().numpy(), br[1].running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
+        assert int(bm[1].num_batches_tracked) == int(br[1].num_batches_tracked)

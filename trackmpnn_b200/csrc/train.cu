@@ -26,8 +26,12 @@ namespace {
 constexpr int H = TMPNN_HIDDEN;
 
 // ------------------------------------------------------------------------------------------
-// gate gradients: one thread per (row, hidden unit); block = 4 rows x 64
+// gate gradients: 16 lanes x float4 per row (128-bit loads / stores: the kernel moves ~3.5 KB per row and nothing else),
+// block = 16 rows
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_acc(float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+
 __global__ void __launch_bounds__(256)
 k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict__ gates,
            const float* __restrict__ h_prev, const float* __restrict__ h_new, int ldh, int col,
@@ -38,40 +42,60 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
            float* __restrict__ ghw_e, float* __restrict__ ghw_d, // [64] head weight slices
            float* __restrict__ ghb_e, float* __restrict__ ghb_d) // [1] head biases (group 0 only, else null)
 {
-  __shared__ float red[4][H];
-  const int j = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  float acc[2][5] = {{0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f}};  // per type: dpr, dpz, dpn, dpnr, dhw
+  __shared__ float4 red[16][16];
+  __shared__ float redb[16];
+  const int l = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  float4 acc[2][5];  // per row type: dpr, dpz, dpn, dpnr, dl * h'
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) acc[t][q] = f4_zero();
   float accb[2] = {0.f, 0.f};
-  const float we = hw_e[j], wd = hw_d[j];
-  for (int row = blockIdx.x * 4 + rl; row < n_rows; row += gridDim.x * 4) {
-    const int t = src[row] >= 0 ? 0 : 1;  // 0 = edge row, 1 = detection row
-    const float p = score[row];
-    const float dl = (dlogits ? dlogits[row] : 0.f) + (dscores ? dscores[row] * p * (1.0f - p) : 0.f);
-    const float* gr = gates + (size_t)row * 4 * H;
-    const float r = gr[j], z = gr[H + j], n = gr[2 * H + j], hn = gr[3 * H + j];
-    const size_t o = (size_t)row * ldh + col + j;
-    const float h = h_prev[o];
-    const float dh = (dh_out ? dh_out[o] : 0.f) + dl * (t ? wd : we);
-    const float dn = dh * (1.0f - z), dz = dh * (h - n);
-    const float dpn = dn * (1.0f - n * n), dpz = dz * z * (1.0f - z), dpr = dpn * hn * r * (1.0f - r);
-    const float dpnr = dpn * r;
-    float* gi = dgi + (size_t)row * 3 * H;
-    float* gh = dgh + (size_t)row * 3 * H;
-    gi[j] = dpr; gi[H + j] = dpz; gi[2 * H + j] = dpn;
-    gh[j] = dpr; gh[H + j] = dpz; gh[2 * H + j] = dpnr;
-    dhself[(size_t)row * H + j] = dh * z;
-    acc[t][0] += dpr; acc[t][1] += dpz; acc[t][2] += dpn; acc[t][3] += dpnr; acc[t][4] += dl * h_new[o];
-    if (j == 0) accb[t] += dl;
+  const float4 we = ldg4(hw_e + 4 * l), wd = ldg4(hw_d + 4 * l);
+  for (int row = blockIdx.x * 16 + rl; row < n_rows; row += gridDim.x * 16) {
+    const int t = __ldg(src + row) >= 0 ? 0 : 1;  // 0 = edge row, 1 = detection row
+    const float p = __ldg(score + row);
+    const float dl = (dlogits ? __ldg(dlogits + row) : 0.f) + (dscores ? __ldg(dscores + row) * p * (1.0f - p) : 0.f);
+    const float* gr = gates + (size_t)row * 4 * H + 4 * l;
+    const float4 r = ldg4(gr), z = ldg4(gr + H), n = ldg4(gr + 2 * H), hn = ldg4(gr + 3 * H);
+    const size_t o = (size_t)row * ldh + col + 4 * l;
+    const float4 h = ldg4(h_prev + o), hnew = ldg4(h_new + o);
+    const float4 dho = dh_out ? ldg4(dh_out + o) : f4_zero();
+    const float4 w = t ? wd : we;
+    float4 dpr, dpz, dpn, dpnr, dhz;
+#define TMPNN_GATE1(c)                                                             \
+    {                                                                              \
+      const float dh = dho.c + dl * w.c;                                           \
+      const float dn = dh * (1.0f - z.c), dz = dh * (h.c - n.c);                   \
+      dpn.c = dn * (1.0f - n.c * n.c);                                             \
+      dpz.c = dz * z.c * (1.0f - z.c);                                             \
+      dpr.c = dpn.c * hn.c * r.c * (1.0f - r.c);                                   \
+      dpnr.c = dpn.c * r.c;                                                        \
+      dhz.c = dh * z.c;                                                            \
+    }
+    TMPNN_GATE1(x) TMPNN_GATE1(y) TMPNN_GATE1(z) TMPNN_GATE1(w)
+#undef TMPNN_GATE1
+    float* gi = dgi + (size_t)row * 3 * H + 4 * l;
+    float* gh = dgh + (size_t)row * 3 * H + 4 * l;
+    *reinterpret_cast<float4*>(gi) = dpr; *reinterpret_cast<float4*>(gi + H) = dpz; *reinterpret_cast<float4*>(gi + 2 * H) = dpn;
+    *reinterpret_cast<float4*>(gh) = dpr; *reinterpret_cast<float4*>(gh + H) = dpz; *reinterpret_cast<float4*>(gh + 2 * H) = dpnr;
+    *reinterpret_cast<float4*>(dhself + (size_t)row * H + 4 * l) = dhz;
+    f4_acc(acc[t][0], dpr); f4_acc(acc[t][1], dpz); f4_acc(acc[t][2], dpn); f4_acc(acc[t][3], dpnr);
+    f4_acc(acc[t][4], make_float4(dl * hnew.x, dl * hnew.y, dl * hnew.z, dl * hnew.w));
+    if (l == 0) accb[t] += dl;
   }
   for (int t = 0; t < 2; ++t) {
     float* gb = t ? gb_d : gb_e;
     float* ghw = t ? ghw_d : ghw_e;
     for (int q = 0; q < 5; ++q) {
       __syncthreads();
-      red[rl][j] = acc[t][q];
+      red[rl][l] = acc[t][q];
       __syncthreads();
-      if (rl == 0) {
-        const float v = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+      if (threadIdx.x < 64) {   // thread j sums hidden unit j over the 16 row lanes (fixed order)
+        const int j = threadIdx.x;
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v += reinterpret_cast<const float*>(&red[k][j >> 2])[j & 3];
         if (v != 0.f) {
           if (q < 3) atomicAdd(&gb[q * H + j], v);                  // d bias_ih
           if (q < 2) atomicAdd(&gb[3 * H + q * H + j], v);          // d bias_hh (r, z)
@@ -81,11 +105,12 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
       }
     }
     __syncthreads();
-    if (j == 0) red[rl][0] = accb[t];
+    if (l == 0) redb[rl] = accb[t];
     __syncthreads();
     float* ghb = t ? ghb_d : ghb_e;
     if (threadIdx.x == 0 && ghb) {
-      const float v = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+      float v = 0.f;
+      for (int k = 0; k < 16; ++k) v += redb[k];
       if (v != 0.f) atomicAdd(ghb, v);
     }
   }
@@ -576,7 +601,7 @@ extern "C" int tmpnn_gate_bwd(int n_rows, const int32_t* src, const float* gates
                               float* ghw_node, float* ghb_edge, float* ghb_node, void* stream) {
   TMPNN_REQUIRE(src && gates && h_prev && h_new && score && dgi && dgh && dhself, "null argument");
   if (n_rows <= 0) return TMPNN_OK;
-  const int blocks = min(tmpnn_div_up(n_rows, 16), TMPNN_SM_COUNT * 2);
+  const int blocks = min(tmpnn_div_up(n_rows, 16), TMPNN_SM_COUNT * 8);
   k_gate_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, src, gates, h_prev, h_new, ldh, col, dh_out, dlogits, dscores,
                                                       score, head_w_edge, head_w_node, dgi, dgh, dhself, gbias_edge,
                                                       gbias_node, ghw_edge, ghw_node, ghb_edge, ghb_node);

@@ -577,7 +577,7 @@ class _MPStepFn(torch.autograd.Function):
         grads = direct if direct is not None else [torch.zeros_like(p) for p in P]
         cont = lambda t: None if t is None else t.detach().to(**f32).contiguous()
         dscores, dlogits, dh_out = cont(dscores), cont(dlogits), cont(dh_out)
-        dh_cur = torch.zeros((n, ldh), **f32)
+        dh_cur = torch.empty((n, ldh), **f32)   # every row / column block is assigned by tmpnn_scatter_bwd
         g_hw_node, g_hb_node, g_hw_edge, g_hb_edge = grads[-4], grads[-3], grads[-2], grads[-1]
         hw_node, hw_edge = P[-4], P[-2]
         h_cur, h_out = ctx.h_cur, ctx.h_out
@@ -591,15 +591,20 @@ class _MPStepFn(torch.autograd.Function):
             dgi = torch.empty((n, 3 * H), **f32)
             dgh = torch.empty((n, 3 * H), **f32)
             dhself = torch.empty((n, H), **f32)
-            gb_e = torch.zeros((2, 3 * H), **f32)
-            gb_d = torch.zeros((2, 3 * H), **f32)
+            # bias gradients as [2][192] = d bias_ih | d bias_hh: in the flat gradient buffer the two vectors of a cell are
+            # adjacent, so the kernel accumulates into them in place
+            adj = lambda i: direct is not None and grads[i + 1].data_ptr() == grads[i].data_ptr() + 4 * 3 * H
+            gb_e = grads[b + 8] if adj(b + 8) else torch.zeros((2, 3 * H), **f32)
+            gb_d = grads[b + 12] if adj(b + 12) else torch.zeros((2, 3 * H), **f32)
             L.call('tmpnn_gate_bwd', n, L.ptr(wg.g.src), L.ptr(ctx.gates[g]), L.ptr(h_cur), L.ptr(h_out), ldh, col,
                    L.ptr(dh_out), L.ptr(dlogits), L.ptr(dscores), L.ptr(ctx.p), L.ptr(hw_edge) + 4 * col,
                    L.ptr(hw_node) + 4 * col, L.ptr(dgi), L.ptr(dgh), L.ptr(dhself), L.ptr(gb_e), L.ptr(gb_d),
                    L.ptr(g_hw_edge) + 4 * col, L.ptr(g_hw_node) + 4 * col,
                    L.ptr(g_hb_edge) if g == 0 else None, L.ptr(g_hb_node) if g == 0 else None, st)
-            grads[b + 8] += gb_e[0]; grads[b + 9] += gb_e[1]
-            grads[b + 12] += gb_d[0]; grads[b + 13] += gb_d[1]
+            if not adj(b + 8):
+                grads[b + 8] += gb_e[0]; grads[b + 9] += gb_e[1]
+            if not adj(b + 12):
+                grads[b + 12] += gb_d[0]; grads[b + 13] += gb_d[1]
             # edge cell: rows with src >= 0
             dx = torch.empty((n, kx), **f32)
             xbuf = torch.empty((n, kx), **f32)
@@ -623,7 +628,7 @@ class _MPStepFn(torch.autograd.Function):
                        L.ptr(grads[b + 7]), st)
             # node cell: the detection list
             nd_dev, det_rows = L.ptr(ix.n_dets), L.ptr(ix.det_rows)
-            dagg = torch.zeros((ix.cap_dets, H), **f32)
+            dagg = (torch.empty if ctx.gats[g] is None else torch.zeros)((ix.cap_dets, H), **f32)
             L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(n_wih), H, L.ptr(dagg), H, 0, st)
             L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(n_whh), H, L.ptr(dhself), H, 1, st)
             L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(ctx.aggs[g]), H, H, L.ptr(grads[b + 10]), st)

@@ -23,7 +23,7 @@ import torch
 from . import _lib as L
 from .device_graph import WindowGraph
 from .functional import H, NewRowGroups, _MPStepFn, _param_list
-from .models.loss import CELoss, create_targets
+from .models.loss import _CEFn, create_targets
 
 _I32 = torch.int32
 
@@ -262,13 +262,84 @@ def batch_loss(model, batch, tp_classifier=True):
 
     Per step: ONE autograd Function for the whole message-passing step (it also moves the carried rows from the previous
     step's block-diagonal layout into this one), one for the CE term, one for both BCE terms -- no torch indexing ops."""
-    ce = CELoss()
     params = _param_list(model)
     loss = None
     h_prev = None
     for st in batch.steps:
         scores, logits, h_prev = _MPStepFn.apply(model, st.holder, st.new_rows, h_prev, *params)[:3]
-        l = ce(logits, st.targets, st.holder, st.idx_node) + \
+        l = _CEFn.apply(logits, st.targets, st.wg) + \
             _WeightedBCE.apply(scores, st.targets64, st.bce_w if tp_classifier else st.bce_w_edges)
         loss = l if loss is None else loss + l
     return loss
+
+
+def invalidate_weight_caches(model):
+    """Drops the packed weight images cached on ``model`` (functional.packed_cells*, the backward images).  They are keyed by
+    the parameters' version counters, which a CUDA-graph replay of an optimizer step does not advance."""
+    for k in ('_tmpnn_pack_cache', '_tmpnn_pack_cache_tc'):
+        model.__dict__.pop(k, None)
+    sc = model.__dict__.get('_tmpnn_bwd_tc')
+    if sc:
+        for k in [k for k in sc if isinstance(k, tuple)]:
+            sc.pop(k)
+
+
+class GraphedTrainStep:
+    """One optimizer step of the batched trainer -- zero the flat gradient buffer, forward + losses of every message-passing
+    step, backward through autograd (the kernels accumulate straight into the flat buffer), Adam -- replayed as CUDA
+    graphs: ~650 launches and ~12 ms of host time per step become two replays.
+
+    The step is captured in two graphs so that the data-parallel all-reduce of the flat buffer (NCCL, ``allreduce=True``)
+    sits between them: [zero, forward, losses, backward] -> all-reduce -> [Adam].  ``capture()`` first runs three REAL steps
+    eagerly (on a side stream, as PyTorch requires before capturing autograd work); the weight images are re-packed inside
+    the captured work, so every replay sees the weights the previous replay's optimizer step left.  Training graphs do not
+    depend on the model (teacher forcing), so one ``TrainBatch`` can be replayed for any number of steps."""
+
+    def __init__(self, model, batch, lr=1e-4, weight_decay=5e-4, tp_classifier=True, allreduce=False):
+        from . import parallel
+        self.model, self.batch, self.tp, self.allreduce = model, batch, bool(tp_classifier), bool(allreduce)
+        self.flat = parallel.FlatGradients(model)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, capturable=True)  # train.py:329
+        self.loss = torch.zeros((), dtype=torch.float32, device=batch.device)
+        self._g_fb = self._g_opt = None
+
+    def _forward_backward(self):
+        self.flat.zero()
+        loss = batch_loss(self.model, self.batch, self.tp)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def eager(self):
+        self._forward_backward()
+        if self.allreduce:
+            self.flat.allreduce(average=True)
+        self.opt.step()
+        return self.loss
+
+    def capture(self, warmup=3):
+        L.check(L.lib().tmpnn_init())
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.eager()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        invalidate_weight_caches(self.model)      # the captured forward must contain the re-packing of the weights
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._forward_backward()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self.opt.step()
+        self._g_fb, self._g_opt = g1, g2
+        invalidate_weight_caches(self.model)      # the cached images belong to the graph now
+
+    def replay(self):
+        if self._g_fb is None:
+            self.capture()
+        self._g_fb.replay()
+        if self.allreduce:
+            self.flat.allreduce(average=True)
+        self._g_opt.replay()
+        return self.loss
