@@ -503,11 +503,13 @@ def test_tensor_core_split_keeps_precision_for_small_weights(kernel):
     a.results(); b.results()
     n = a.ga.n_rows.cpu().numpy()
     np.testing.assert_array_equal(n, b.ga.n_rows.cpu().numpy())
+    n_edge, scale, err = 0, 0.0, 0.0
     for s in range(len(seqs)):
         rows = slice(s * a.cap_rows, s * a.cap_rows + int(n[s]))
         edge = (a.ga.ts[rows] < 0).cpu().numpy()
         ha = a.h_alt[a.ga.phys[rows].long()].cpu().numpy()[edge]     # 3 ticks: the last step wrote h_alt
         hb = b.h_alt[b.ga.phys[rows].long()].cpu().numpy()[edge]
-        assert edge.sum() > 20
-        scale = float(np.abs(hb).max())
-        assert scale > 3e-3 and float(np.abs(ha - hb).max()) <= 3e-6, (float(np.abs(ha - hb).max()), scale)
+        n_edge += int(edge.sum())
+        scale = max(scale, float(np.abs(hb).max()))
+        err = max(err, float(np.abs(ha - hb).max()))
+    assert n_edge > 100 and scale > 3e-3 and err <= 3e-6, (n_edge, scale, err)

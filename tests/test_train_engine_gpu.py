@@ -206,7 +206,12 @@ def test_graphed_train_step_equals_eager_steps():
     assert abs(float(a.loss) - float(b.loss)) <= 1e-5 * abs(float(b.loss))
     moved = 0.0
     for (name, p), q in zip(model.named_parameters(), ref.parameters()):
-        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-5, atol=1e-7, err_msg=name)
+        if name.endswith('.0.bias'):
+            # Linear bias in front of the train-mode BatchNorm: its gradient is analytically zero, what the kernels (and the
+            # reference) produce is round-off, and Adam turns any round-off into steps of +-lr
+            continue
+        # 5 steps of lr 1e-3 move a weight by up to 5e-3; float atomics in a few gradient sums + Adam's normalisation: 2e-5
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=0, atol=2e-5, err_msg=name)
     torch.manual_seed(5)
     fresh = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev)
     for p, q in zip(model.parameters(), fresh.parameters()):
