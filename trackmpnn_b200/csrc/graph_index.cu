@@ -220,6 +220,7 @@ constexpr int MAXSEG = 128;  // segments per slab (2 per frame in the window)
 constexpr int MAXE = 64;     // edge segments per slab
 
 struct SlabSegs {            // per slab, in global scratch
+  int32_t nedge;             // number of edge segments (<= MAXE)
   int32_t nseg;              // number of segments
   int32_t start[MAXSEG + 1]; // slab-local first row of segment q; start[nseg] = n_rows
   int32_t eord[MAXSEG];      // ordinal among the edge segments, -1 for detection segments
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(32) k_block_segments(const int32_t* __restrict
     o.eord[q] = edge ? ne : -1;
     if (edge) ++ne;
   }
-  if (ne > MAXE) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; }
+  if (ne > MAXE) { atomicOr(status, TMPNN_FLAG_UNSTRUCTURED); m = 0; ne = 0; }
+  o.nedge = ne;
   o.nseg = m;
   o.start[m] = n;
 }
@@ -301,12 +303,15 @@ __global__ void __launch_bounds__(256) k_block_degree(const SlabSegs* __restrict
 
 // per detection: run lengths -> offsets inside its future list, total -> cnt[2k+1]
 __global__ void __launch_bounds__(256) k_block_futoff(const int32_t* __restrict__ n_dets, int32_t* __restrict__ futlen,
-                                                      int32_t* __restrict__ cnt) {
+                                                      int32_t* __restrict__ cnt, const SlabSegs* __restrict__ segs,
+                                                      const int32_t* __restrict__ det_rows, int cap_rows) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= *n_dets) return;
   int32_t* f = futlen + (size_t)k * MAXE;
+  // only the slab's own edge segments can hold a run (2 W - 1 at most, usually W): the other MAXE slots are never touched
+  const int ne = segs[det_rows[k] / cap_rows].nedge;
   int acc = 0;
-  for (int b = 0; b < MAXE; ++b) {
+  for (int b = 0; b < ne; ++b) {
     const int v = f[b];
     f[b] = acc;
     acc += v;
@@ -423,7 +428,7 @@ extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_in
   dim3 grid_d(4, S);
   k_block_degree<<<grid_d, 256, 0, st>>>(segs, g->src, g->cap_rows, ix->det_of_row, ix->n_dets, cnt, futlen, g->status);
   TMPNN_LAUNCH_CHECK();
-  k_block_futoff<<<tmpnn_div_up(ix->cap_dets, 256), 256, 0, st>>>(ix->n_dets, futlen, cnt);
+  k_block_futoff<<<tmpnn_div_up(ix->cap_dets, 256), 256, 0, st>>>(ix->n_dets, futlen, cnt, segs, ix->det_rows, g->cap_rows);
   TMPNN_LAUNCH_CHECK();
   TMPNN_CUDA_TRY(scan_exclusive(cnt, ix->seg_ptr, ix->n_dets, 2, 0, 2 * (long long)ix->cap_dets, sums, st));
   dim3 grid_e(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 8), 64)), S);

@@ -469,17 +469,18 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
 // h: 64 hi halves then 64 lo halves in the row's 256 B), which is what the producers copy for the far endpoint of
 // an association row; (b) P'[k] = the row's source-side contribution to the input gates, fp32 FMA:
 //   P = h W_ih[:, 0:64]^T,  P'[0:128) = -log2e (P + b_ih + b_hh),  P'[128:192) = P + b_ih.
-constexpr int PREP_SMEM = (64 * 192 + 8 * 64 + 192) * 4;
+constexpr int PREP_D = 4;  // detections per warp pass: every weight read from shared memory feeds 4 FMAs
+constexpr int PREP_SMEM = (64 * 192 + 8 * PREP_D * 64 + 192) * 4;
 __global__ void __launch_bounds__(256)
 k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* __restrict__ n_dets,
               const int32_t* __restrict__ det_rows, const int32_t* __restrict__ phys, const unsigned char* __restrict__ image,
               float* __restrict__ det_img, float* __restrict__ det_p, int32_t* __restrict__ status) {
   extern __shared__ float prep_sm[];
   float* wt = prep_sm;             // [64][192]: W_ih^T (source half)
-  float* hr = prep_sm + 64 * 192;  // [8][64]
-  float* bs = hr + 8 * 64;         // [192]
+  float* hr = prep_sm + 64 * 192;  // [8 warps][PREP_D][64]
+  float* bs = hr + 8 * PREP_D * 64;  // [192]
   const int nd = *n_dets;
-  if ((int)blockIdx.x * 8 >= nd) return;
+  if ((int)blockIdx.x * 8 * PREP_D >= nd) return;
   {
     const float4* gw = reinterpret_cast<const float4*>(image + OFF_WT);
     for (int i = threadIdx.x; i < 64 * 192 / 4; i += blockDim.x) reinterpret_cast<float4*>(wt)[i] = __ldg(gw + i);
@@ -489,33 +490,55 @@ k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* _
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float wscale = *reinterpret_cast<const float*>(image + OFF_HEADB + 8);  // 2^k of the weight pre-scale: P_n joins i_n scaled
-  float* hw = hr + w * 64;
-  for (int k = blockIdx.x * 8 + w; k < nd; k += gridDim.x * 8) {
-    const int row = det_rows[k];
-    const size_t pr = phys ? (size_t)phys[row] : (size_t)row;  // deferred compaction: the state sits at the physical row
-    const float2 v = *reinterpret_cast<const float2*>(h_in + pr * ldh + col + 2 * lane);
-    hw[2 * lane] = v.x;
-    hw[2 * lane + 1] = v.y;
-    const __half2 hi = __floats2half2_rn(v.x, v.y);
-    const float2 f = __half22float2(hi);
-    const __half2 lo = __floats2half2_rn(v.x - f.x, v.y - f.y);
-    uint32_t* ib = reinterpret_cast<uint32_t*>(det_img + (size_t)row * ldh + col);
-    ib[lane] = *reinterpret_cast<const uint32_t*>(&hi);
-    ib[32 + lane] = *reinterpret_cast<const uint32_t*>(&lo);
-    if (fmaxf(fabsf(v.x), fabsf(v.y)) > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
-    __syncwarp();
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int c = 0; c < 64; ++c) {
-      const float hv = hw[c];
+  float* hw = hr + w * PREP_D * 64;
+  for (int k0 = (blockIdx.x * 8 + w) * PREP_D; k0 < nd; k0 += gridDim.x * 8 * PREP_D) {
+    const int cnt = min(PREP_D, nd - k0);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) acc[q] = fmaf(hv, wt[c * 192 + lane + 32 * q], acc[q]);
+    for (int d = 0; d < PREP_D; ++d) {
+      float2 v = make_float2(0.f, 0.f);
+      if (d < cnt) {
+        const int row = det_rows[k0 + d];
+        const size_t pr = phys ? (size_t)phys[row] : (size_t)row;  // deferred compaction: the state sits at the physical row
+        v = *reinterpret_cast<const float2*>(h_in + pr * ldh + col + 2 * lane);
+        const __half2 hi = __floats2half2_rn(v.x, v.y);
+        const float2 f = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(v.x - f.x, v.y - f.y);
+        uint32_t* ib = reinterpret_cast<uint32_t*>(det_img + (size_t)row * ldh + col);
+        ib[lane] = *reinterpret_cast<const uint32_t*>(&hi);
+        ib[32 + lane] = *reinterpret_cast<const uint32_t*>(&lo);
+        if (fmaxf(fabsf(v.x), fabsf(v.y)) > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
+      }
+      hw[d * 64 + 2 * lane] = v.x;
+      hw[d * 64 + 2 * lane + 1] = v.y;
+    }
+    __syncwarp();
+    float acc[PREP_D][6];
+#pragma unroll
+    for (int d = 0; d < PREP_D; ++d)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[d][q] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 64; ++c) {
+      float wv[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) wv[q] = wt[c * 192 + lane + 32 * q];
+#pragma unroll
+      for (int d = 0; d < PREP_D; ++d) {
+        const float hv = hw[d * 64 + c];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[d][q] = fmaf(hv, wv[q], acc[d][q]);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int n = lane + 32 * q;
-      const float val = acc[q] + bs[n];
-      det_p[(size_t)k * 192 + n] = q < 4 ? -LOG2E * val : wscale * val;
+    for (int d = 0; d < PREP_D; ++d) {
+      if (d < cnt) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int n = lane + 32 * q;
+          const float val = acc[d][q] + bs[n];
+          det_p[(size_t)(k0 + d) * 192 + n] = q < 4 ? -LOG2E * val : wscale * val;
+        }
+      }
     }
     __syncwarp();
   }
