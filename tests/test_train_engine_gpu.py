@@ -218,5 +218,7 @@ def test_graphed_train_step_equals_eager_steps():
         moved = max(moved, float((p - q).abs().max()))
     assert moved > 1e-3     # the replays really trained
     for bm, br in zip(model.input_transforms, ref.input_transforms):   # BatchNorm bookkeeping advanced inside the graph too
-        np.testing.assert_allclose(bm[1].running_mean.cpu().numpy(), br[1].running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
+        # the running mean follows Linear1's bias, which only moves by Adam-normalised round-off (see above): +-lr per step
+        np.testing.assert_allclose(bm[1].running_mean.cpu().numpy(), br[1].running_mean.cpu().numpy(), rtol=0, atol=5e-3)
+        np.testing.assert_allclose(bm[1].running_var.cpu().numpy(), br[1].running_var.cpu().numpy(), rtol=1e-3, atol=1e-6)
         assert int(bm[1].num_batches_tracked) == int(br[1].num_batches_tracked)

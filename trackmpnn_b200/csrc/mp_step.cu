@@ -229,27 +229,21 @@ __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict_
                                                         const int32_t* __restrict__ n_dets,
                                                         const int32_t* __restrict__ seg_ptr,
                                                         const int32_t* __restrict__ inc, float* __restrict__ agg,
-                                                        const int32_t* __restrict__ phys,
-                                                        const int32_t* __restrict__ det_rows, int cap_rows) {
+                                                        const int32_t* __restrict__ phys) {
   __shared__ float4 part[16][16];
   const int nd = *n_dets;
   const int q = threadIdx.x >> 4, l16 = threadIdx.x & 15;  // half-warp, float4 within the row
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = blockIdx.x; k < nd; k += gridDim.x) {
     const int s0 = seg_ptr[2 * k], s1 = seg_ptr[2 * k + 1], s2 = seg_ptr[2 * k + 2];
-    // deferred compaction: association rows appended this frame all alias the slab's zero row (state exactly 0): they are
-    // ~40 % of a window and contribute nothing, so they are not loaded at all (the kernel is bound by L2 -> SM traffic, which
-    // the aliasing alone does not save)
-    const int zrow = phys ? (det_rows[k] / cap_rows) * cap_rows + cap_rows - 1 : -1;
-    float4 acc = z4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int i = s0 + q;
     for (; i + 48 < s2; i += 64) {
       int e0 = inc[i], e1 = inc[i + 16], e2 = inc[i + 32], e3 = inc[i + 48];
       if (phys) { e0 = phys[e0]; e1 = phys[e1]; e2 = phys[e2]; e3 = phys[e3]; }  // deferred compaction: physical rows
-      float4 v0 = e0 != zrow ? ldg4(h + (size_t)e0 * ldh + col + 4 * l16) : z4;
-      float4 v1 = e1 != zrow ? ldg4(h + (size_t)e1 * ldh + col + 4 * l16) : z4;
-      float4 v2 = e2 != zrow ? ldg4(h + (size_t)e2 * ldh + col + 4 * l16) : z4;
-      float4 v3 = e3 != zrow ? ldg4(h + (size_t)e3 * ldh + col + 4 * l16) : z4;
+      float4 v0 = ldg4(h + (size_t)e0 * ldh + col + 4 * l16);
+      float4 v1 = ldg4(h + (size_t)e1 * ldh + col + 4 * l16);
+      float4 v2 = ldg4(h + (size_t)e2 * ldh + col + 4 * l16);
+      float4 v3 = ldg4(h + (size_t)e3 * ldh + col + 4 * l16);
       float g0 = (i < s1) ? -1.f : 1.f, g1 = (i + 16 < s1) ? -1.f : 1.f;
       float g2 = (i + 32 < s1) ? -1.f : 1.f, g3 = (i + 48 < s1) ? -1.f : 1.f;
       acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
@@ -259,7 +253,7 @@ __global__ void __launch_bounds__(256) k_aggregate_dets(const float* __restrict_
     }
     for (; i < s2; i += 16) {
       const int e = phys ? phys[inc[i]] : inc[i];
-      float4 v = e != zrow ? ldg4(h + (size_t)e * ldh + col + 4 * l16) : z4;
+      float4 v = ldg4(h + (size_t)e * ldh + col + 4 * l16);
       float g = (i < s1) ? -1.f : 1.f;
       acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y); acc.z = fmaf(g, v.z, acc.z); acc.w = fmaf(g, v.w, acc.w);
     }
@@ -283,7 +277,7 @@ extern "C" int tmpnn_aggregate_dets(const tmpnn_graph* g, const tmpnn_index* ix,
   TMPNN_REQUIRE(g && ix && h && agg, "null argument");
   TMPNN_REQUIRE(ldh % 4 == 0 && col % 4 == 0, "h rows must be 16-byte aligned");
   k_aggregate_dets<<<TMPNN_SM_COUNT * 8, 256, 0, (cudaStream_t)stream>>>(h, ldh, col, ix->n_dets, ix->seg_ptr, ix->inc, agg,
-                                                                         g->phys, ix->det_rows, g->cap_rows);
+                                                                         g->phys);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
