@@ -370,7 +370,8 @@ int tmpnn_loss_focal_fwd(int n, const float *p, const int64_t *targets, float *p
 int tmpnn_loss_focal_bwd(int n, const float *p, const int64_t *targets, const float *grad_out, float *dp, void *stream);
 
 /* Batched trainer (trackmpnn_b200/train_engine.py): sum_i w[i] (-log(p_t[i] + 1e-10)) -- the BCE terms of train.py:76-85 for
- * B chunks at once, w[i] = 1 / (rows of row i's kind in its chunk), i.e. the sum over chunks of their per-chunk means. */
+ * B chunks at once, w[i] = 1 / (rows of row i's kind in its chunk), i.e. the sum over chunks of their per-chunk means.
+ * per_elem: scratch of n floats (holds block partials afterwards, not the per-row terms). */
 int tmpnn_loss_wbce_fwd(int n, const float *p, const int64_t *targets, const float *w, float *per_elem, float *loss, void *stream);
 int tmpnn_loss_wbce_bwd(int n, const float *p, const int64_t *targets, const float *w, const float *grad_out, float *dp, void *stream);
 

@@ -532,10 +532,17 @@ __global__ void k_focal_bwd(int n, const float* __restrict__ p, const int64_t* _
 
 // weighted form for the batched trainer: every row carries its own weight (1 / rows of its kind in its chunk = the
 // per-chunk means of train.py:76-85; 0 = the row does not count)
-__global__ void k_wbce_fwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t, const float* __restrict__ w,
-                           float* __restrict__ out) {
+// out[blockIdx.x] = the block's sum (fixed order): the final k_sum adds n / 256 partials instead of n terms
+__global__ void __launch_bounds__(256) k_wbce_fwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t,
+                                                  const float* __restrict__ w, float* __restrict__ out) {
+  __shared__ float red[8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = w[i] != 0.f ? -w[i] * logf((t[i] == 1 ? p[i] : 1.0f - p[i]) + 1e-10f) : 0.f;
+  float v = 0.f;
+  if (i < n && w[i] != 0.f) v = -w[i] * logf((t[i] == 1 ? p[i] : 1.0f - p[i]) + 1e-10f);
+  v = warp_sum_f(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }
 __global__ void k_wbce_bwd(int n, const float* __restrict__ p, const int64_t* __restrict__ t, const float* __restrict__ w,
                            const float* __restrict__ gout, float* __restrict__ dp) {
@@ -568,9 +575,9 @@ extern "C" int tmpnn_loss_wbce_fwd(int n, const float* p, const int64_t* targets
                                    void* stream) {
   TMPNN_REQUIRE(p && targets && w && per_elem && loss && n > 0, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  k_wbce_fwd<<<tmpnn_div_up(n, 256), 256, 0, st>>>(n, p, targets, w, per_elem);
+  k_wbce_fwd<<<tmpnn_div_up(n, 256), 256, 0, st>>>(n, p, targets, w, per_elem);   // per_elem[0 .. n / 256]: block partials
   TMPNN_LAUNCH_CHECK();
-  k_sum<<<1, 256, 0, st>>>(per_elem, nullptr, 0, n, 0.f, loss);
+  k_sum<<<1, 256, 0, st>>>(per_elem, nullptr, 0, tmpnn_div_up(n, 256), 0.f, loss);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

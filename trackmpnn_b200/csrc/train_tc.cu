@@ -180,54 +180,64 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
     }
   } else if (warp >= BW_EPI) {
     // ================= producers: 16 lanes per row, rows g + 16 p =================
+    // Software-pipelined in registers over "rounds" of two rows per thread (4 rounds per tile): the eight 128-bit loads of
+    // round r + 1 are issued before round r is converted and stored, and the wait for the previous tile's MMAs sits between
+    // the loads of a tile's first round and its first store -- the sweep is bound by HBM latency, so loads must stay in flight
+    // across tile boundaries and across the tensor-core phase.
     const int pt = threadIdx.x - 32 * BW_EPI;
     const int g = pt >> 4, l = pt & 15;
     const uint32_t off0 = sw128(g, l >> 1) + ((l & 1) << 3);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
-      mbar_wait(bar_afree, ((uint32_t)it & 1u) ^ 1u, status);  // the previous tile's MMAs have read the images
+    const int my_tiles = (total - (int)blockIdx.x + stride - 1) / stride;
+    const int rounds = 4 * my_tiles;
+    struct RoundRegs { float4 va[2][3]; float4 vx[2]; int mk[2]; };
+    auto issue = [&](RoundRegs& rr, int r) {
+      const int tile = blockIdx.x + (r >> 2) * stride;
 #pragma unroll
-      for (int hp = 0; hp < 2; ++hp) {
-        // four rows per round: indices first, then 16 unconditional 128-bit loads in flight (rows past the end and masked rows
-        // read a valid row and are zeroed afterwards), then the conversions -- the sweep is bound by HBM latency otherwise
-        int ra[4], rx[4];
-        bool ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = min(tile * TCM + g + 16 * (4 * hp + q), R - 1);
-          ra[q] = a_rows ? __ldg(a_rows + i) : i;
-          rx[q] = x_rows ? __ldg(x_rows + i) : i;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          ok[q] = tile * TCM + g + 16 * (4 * hp + q) < R && (!mask || __ldg(mask + ra[q]) >= 0);
-        float4 va[4][3], vx[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* ap = A + (size_t)ra[q] * BGK + 4 * l;
-          va[q][0] = ldg4(ap); va[q][1] = ldg4(ap + 64); va[q][2] = ldg4(ap + 128);
-          vx[q] = ldg4(X + (size_t)rx[q] * ldx + 4 * l);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const uint32_t off = off0 + 2048u * (4 * hp + q);
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            uint2 hi, lo;
-            split4_bf16(ok[q] ? va[q][a] : z4, hi, lo);
-            *reinterpret_cast<uint2*>(sm + BW_OFF_A + slot_of(a) * BW_IMG + off) = hi;
-            *reinterpret_cast<uint2*>(sm + BW_OFF_A + (3 + slot_of(a)) * BW_IMG + off) = lo;
-          }
-          uint2 hi, lo;
-          split4_bf16(ok[q] ? vx[q] : z4, hi, lo);
-          *reinterpret_cast<uint2*>(sm + BW_OFF_A + 6 * BW_IMG + off) = hi;
-          *reinterpret_cast<uint2*>(sm + BW_OFF_A + 7 * BW_IMG + off) = lo;
-        }
+      for (int q = 0; q < 2; ++q) {
+        const int i0 = tile * TCM + g + 16 * (2 * (r & 3) + q);
+        const int i = min(i0, R - 1);
+        const int ra = a_rows ? __ldg(a_rows + i) : i;
+        const int rx = x_rows ? __ldg(x_rows + i) : i;
+        const float* ap = A + (size_t)ra * BGK + 4 * l;
+        rr.va[q][0] = ldg4(ap); rr.va[q][1] = ldg4(ap + 64); rr.va[q][2] = ldg4(ap + 128);
+        rr.vx[q] = ldg4(X + (size_t)rx * ldx + 4 * l);
+        // validity, resolved when the round is processed: rows past the end and masked rows read a valid row and are zeroed
+        rr.mk[q] = i0 < R ? (mask ? __ldg(mask + ra) : 0) : -1;
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full);
+    };
+    auto process = [&](const RoundRegs& rr, int r) {
+      const int sub = r & 3;
+      if (sub == 0) mbar_wait(bar_afree, ((uint32_t)(r >> 2) & 1u) ^ 1u, status);  // the previous tile's MMAs have read the images
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool ok = rr.mk[q] >= 0;
+        const uint32_t off = off0 + 2048u * (2 * sub + q);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          uint2 hi, lo;
+          split4_bf16(ok ? rr.va[q][a] : z4, hi, lo);
+          *reinterpret_cast<uint2*>(sm + BW_OFF_A + slot_of(a) * BW_IMG + off) = hi;
+          *reinterpret_cast<uint2*>(sm + BW_OFF_A + (3 + slot_of(a)) * BW_IMG + off) = lo;
+        }
+        uint2 hi, lo;
+        split4_bf16(ok ? rr.vx[q] : z4, hi, lo);
+        *reinterpret_cast<uint2*>(sm + BW_OFF_A + 6 * BW_IMG + off) = hi;
+        *reinterpret_cast<uint2*>(sm + BW_OFF_A + 7 * BW_IMG + off) = lo;
+      }
+      if (sub == 3) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full);
+      }
+    };
+    RoundRegs ra0, ra1;
+    issue(ra0, 0);
+    for (int r = 0; r < rounds; r += 2) {   // rounds is a multiple of 4
+      issue(ra1, r + 1);
+      process(ra0, r);
+      if (r + 2 < rounds) issue(ra0, r + 2);
+      process(ra1, r + 1);
     }
   } else {
     // ================= epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) =================

@@ -626,14 +626,22 @@ class _MPStepFn(torch.autograd.Function):
                 L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgi), L.ptr(xbuf), kx, kx, L.ptr(grads[b + 6]), st)
                 L.call('tmpnn_rows_outer', None, n, None, None, L.ptr(wg.g.src), L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
                        L.ptr(grads[b + 7]), st)
-            # node cell: the detection list
+            # node cell: the detection list (A gathered through det_rows; the count lives on the device)
             nd_dev, det_rows = L.ptr(ix.n_dets), L.ptr(ix.det_rows)
             dagg = (torch.empty if ctx.gats[g] is None else torch.zeros)((ix.cap_dets, H), **f32)
-            L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(n_wih), H, L.ptr(dagg), H, 0, st)
-            L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(n_whh), H, L.ptr(dhself), H, 1, st)
-            L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(ctx.aggs[g]), H, H, L.ptr(grads[b + 10]), st)
-            L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
-                   L.ptr(grads[b + 11]), st)
+            if use_tensor_path(model, n):
+                part = _bwd_tc_partials(model, dev)
+                L.call('tmpnn_rows_gemm_tc', nd_dev, 0, det_rows, None, None, None, L.ptr(dgi), L.ptr(_bwd_tc_image(model, n_wih, 0)),
+                       L.ptr(dagg), H, 0, L.ptr(ctx.aggs[g]), H, L.ptr(part), L.ptr(grads[b + 10]), H, L.ptr(wg.g.status), st)
+                L.call('tmpnn_rows_gemm_tc', nd_dev, 0, det_rows, det_rows, det_rows, None, L.ptr(dgh),
+                       L.ptr(_bwd_tc_image(model, n_whh, 0)), L.ptr(dhself), H, 1, L.ptr(h_cur) + 4 * col, ldh, L.ptr(part),
+                       L.ptr(grads[b + 11]), H, L.ptr(wg.g.status), st)
+            else:
+                L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(n_wih), H, L.ptr(dagg), H, 0, st)
+                L.call('tmpnn_rows_times_w', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(n_whh), H, L.ptr(dhself), H, 1, st)
+                L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, None, None, L.ptr(dgi), L.ptr(ctx.aggs[g]), H, H, L.ptr(grads[b + 10]), st)
+                L.call('tmpnn_rows_outer', nd_dev, 0, det_rows, det_rows, None, L.ptr(dgh), L.ptr(h_cur) + 4 * col, ldh, H,
+                       L.ptr(grads[b + 11]), st)
             # through the gather / segmented sum, into the state this step consumed
             heads = ctx.gats[g]
             L.call('tmpnn_scatter_bwd', wg.g.c, ix.c, n, L.ptr(dhself), L.ptr(dx), kx,
