@@ -285,12 +285,31 @@ k_scatter_bwd_dets(const int32_t* __restrict__ n_dets, const int32_t* __restrict
     const int s0 = seg_ptr[2 * k], s1 = seg_ptr[2 * k + 1], s2 = seg_ptr[2 * k + 2];
     const int row = det_rows[k];
     float a0 = dhself[(size_t)row * H + lane], a1 = dhself[(size_t)row * H + lane + 32];
-    for (int i = s0; i < s1; ++i) {  // past edges: this detection is their dst
-      const float* d = dx + (size_t)inc[i] * kx + (concat ? H : 0);
-      if (concat) { a0 += d[lane]; a1 += d[lane + 32]; }
-      else { a0 -= d[lane]; a1 -= d[lane + 32]; }
+    // four rows of dx in flight per step (the loop is bound by load latency); the additions keep the list order, so the sum
+    // is the same bit for bit as one row at a time
+    const int po = concat ? H : 0;
+    const float ps = concat ? 1.f : -1.f;
+    int i = s0;
+    for (; i + 3 < s1; i += 4) {  // past edges: this detection is their dst
+      const float* d0 = dx + (size_t)inc[i] * kx + po; const float* d1 = dx + (size_t)inc[i + 1] * kx + po;
+      const float* d2 = dx + (size_t)inc[i + 2] * kx + po; const float* d3 = dx + (size_t)inc[i + 3] * kx + po;
+      const float u0 = d0[lane], v0 = d0[lane + 32], u1 = d1[lane], v1 = d1[lane + 32];
+      const float u2 = d2[lane], v2 = d2[lane + 32], u3 = d3[lane], v3 = d3[lane + 32];
+      a0 = fmaf(ps, u0, a0); a1 = fmaf(ps, v0, a1); a0 = fmaf(ps, u1, a0); a1 = fmaf(ps, v1, a1);
+      a0 = fmaf(ps, u2, a0); a1 = fmaf(ps, v2, a1); a0 = fmaf(ps, u3, a0); a1 = fmaf(ps, v3, a1);
     }
-    for (int i = s1; i < s2; ++i) {  // future edges: this detection is their src
+    for (; i < s1; ++i) {
+      const float* d = dx + (size_t)inc[i] * kx + po;
+      a0 = fmaf(ps, d[lane], a0); a1 = fmaf(ps, d[lane + 32], a1);
+    }
+    for (; i + 3 < s2; i += 4) {  // future edges: this detection is their src
+      const float* d0 = dx + (size_t)inc[i] * kx; const float* d1 = dx + (size_t)inc[i + 1] * kx;
+      const float* d2 = dx + (size_t)inc[i + 2] * kx; const float* d3 = dx + (size_t)inc[i + 3] * kx;
+      const float u0 = d0[lane], v0 = d0[lane + 32], u1 = d1[lane], v1 = d1[lane + 32];
+      const float u2 = d2[lane], v2 = d2[lane + 32], u3 = d3[lane], v3 = d3[lane + 32];
+      a0 += u0; a1 += v0; a0 += u1; a1 += v1; a0 += u2; a1 += v2; a0 += u3; a1 += v3;
+    }
+    for (; i < s2; ++i) {
       const float* d = dx + (size_t)inc[i] * kx;
       a0 += d[lane]; a1 += d[lane + 32];
     }

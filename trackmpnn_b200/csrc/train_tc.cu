@@ -97,10 +97,8 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
   const int R = r_dev ? *r_dev : r_host;
   const int total = (R + TCM - 1) / TCM;
   float* my_part = partials + (size_t)blockIdx.x * BGK * 64;
-  if ((int)blockIdx.x >= total) {  // no tile for this CTA: its partial is zero (uniform exit before any barrier / TMEM use)
-    for (int i = threadIdx.x; i < BGK * 64 / 4; i += BW_THREADS) reinterpret_cast<float4*>(my_part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
+  if ((int)blockIdx.x >= total) return;  // no tile for this CTA (uniform exit before any barrier / TMEM use); k_reduce_partials
+                                         // only reads the partials of the CTAs that had one
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,9 +311,13 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
 }
 
 // G[m][0:64] += sum over the CTA partials, CTA 0 first: a fixed order, so the weight gradients are reproducible bit for bit
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int n_part, float* __restrict__ G, int ldg) {
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int n_sm, const int32_t* __restrict__ r_dev,
+                                                         int r_host, float* __restrict__ G, int ldg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BGK * 64) return;
+  // only the CTAs that had a tile hold a partial (the others did not even write zeros)
+  const int R = r_dev ? *r_dev : r_host;
+  const int n_part = min(n_sm, (R + TCM - 1) / TCM);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains of loads in flight; the combination order is fixed
   int c = 0;
   for (; c + 3 < n_part; c += 4) {
@@ -365,7 +367,7 @@ extern "C" int tmpnn_rows_gemm_tc(const int32_t* r_dev, int r_host, const int32_
                                                              (const unsigned char*)w_image, C, ldc, accumulate, X, ldx, partials,
                                                              status);
   TMPNN_LAUNCH_CHECK();
-  k_reduce_partials<<<tmpnn_div_up(BGK * 64, 256), 256, 0, st>>>(partials, TMPNN_SM_COUNT, G, ldg);
+  k_reduce_partials<<<tmpnn_div_up(BGK * 64, 256), 256, 0, st>>>(partials, TMPNN_SM_COUNT, r_dev, r_host, G, ldg);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
