@@ -510,9 +510,10 @@ def prepare_passes(eng):
 
 
 def time_passes(eng, steps, clocks=None):
-    """K eager passes of `eng` bracketed by CUDA events on the current stream (the edge kernel, the aggregation and the
-    window slide are additionally bracketed launch by launch: eng.profile*).  Returns this rank's numbers.  No collective
-    in here: the caller puts a barrier + synchronize on both sides and reduces the numbers over the ranks."""
+    """K passes of `eng` bracketed by CUDA events on the current stream -- eager launches after prepare_passes() (the edge
+    kernel, the aggregation and the window slide are then additionally bracketed launch by launch: eng.profile*), CUDA-graph
+    replay otherwise.  Returns this rank's numbers.  No collective in here: the caller puts a barrier + synchronize on both
+    sides and reduces the numbers over the ranks."""
     import torch
     from trackmpnn_b200 import _lib as L
     if clocks is not None:
@@ -739,11 +740,14 @@ def main():
         for _ in range(max(a.warmup, 1)):
             eng.run()
         eng.results()
-        prepare_passes(eng)
+        # 32 sequences per GPU make a frame ~1 ms of ~45 launches: timed as the engine is used (CUDA-graph replay); the
+        # per-launch roofline of rank 0 comes from one more, eager, pass afterwards
         barrier(); torch.cuda.synchronize()
         rs = time_passes(eng, a.steps)
         barrier()
-        s_roof = rooflines(a, eng, rs, rs['ms'])[0]
+        prepare_passes(eng)
+        rp = time_passes(eng, 1)
+        s_roof = rooflines(a, eng, rp, rp['ms'])[0]
         del eng, all_seqs
         torch.cuda.empty_cache()
     else:
@@ -758,8 +762,8 @@ def main():
                   'value': s_edges / (s_ms * 1e-3), 'unit': 'edge-updates/s', 'frames_per_s': s_frames / (s_ms * 1e-3),
                   'ms_per_step': s_ms / a.steps, 'ms_per_step_fastest_rank': s_ms_min / a.steps,
                   'sequences_per_rank': [len(b) for b in bins], 'cost_imbalance': max(load) / (sum(load) / world),
-                  'rank0_edge_kernel_frac': s_roof['frac'], 'rank0_edge_kernel_share_of_step': s_roof['share_of_step'],
-                  'scaling': 'strong'}
+                  'rank0_edge_kernel_frac': s_roof['frac'], 'rank0_edge_kernel_share_of_eager_step': s_roof['share_of_step'],
+                  'timed_passes': 'CUDA-graph replay', 'scaling': 'strong'}
     del seqs
 
     # ---- the same sequence gives the same tracks on every GPU, in every batch --------------------------------------------
