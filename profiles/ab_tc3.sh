@@ -17,6 +17,6 @@ else
   for i in ${AB_ROUNDS:-1 2 3}; do for v in "$@"; do
     echo -n "$v "
     TMPNN_LIB=build/lib_$v.so timeout 100 python bench.py --steps 2 --warmup 2 --frames ${AB_FRAMES:-40} --skip-cpu --skip-e2e --skip-train --skip-c4 --skip-check 2>/dev/null |
-      python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e9,4), round(d['roofline']['avg_launch_ms'],4), 'agg ms', round(d['roofline_aggregation']['avg_launch_ms'],4), 'agg frac', round(d['roofline_aggregation']['frac'],3))"
+      python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e9,4), round(d['roofline']['avg_launch_ms'],4), 'edge GB/s', round(d['roofline']['achieved'],1), 'agg ms', round(d['roofline_aggregation']['avg_launch_ms'],4), 'agg frac', round(d['roofline_aggregation']['frac'],3))"
   done; done
 fi

@@ -33,7 +33,7 @@ def run():
     dev = torch.device('cuda:0')
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories(a.dataset), 64, 0, 'diff').to(dev).eval()
-    eng = TrackEngine(model, bench.make_sequences(a, 0), cur_win_size=a.win, use_cuda_graph=False)
+    eng = TrackEngine(model, bench.make_sequences(a, 0, a.seqs_per_gpu), cur_win_size=a.win, use_cuda_graph=False)
     eng.run(max_ticks=8); torch.cuda.synchronize()
     cap = 2048
     buf = torch.zeros((cap, 16), dtype=torch.int64, device=dev)

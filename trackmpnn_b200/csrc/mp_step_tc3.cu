@@ -17,6 +17,8 @@
 // mbarriers per stage: full (8 producer warps), done (tcgen05.commit), gfree (8 team warps: gates done ->
 // accumulators drained and h images read), xfree (8 team warps: stores done -> x images / transpose buffer free).
 // Tiles are located through a table {slab's first global row, tile's first slab row, rows left} (k_tile_table).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 #ifdef TMPNN_TC_TRACE
@@ -39,6 +41,10 @@ extern "C" int tmpnn_debug_set_tc3_trace(long long* buf, int cap) {
 // device-to-symbol copy in front of every launch: constant-bank operands cost the epilogue no registers (it sits at the
 // 72-register ceiling; the same constants read from shared memory added 28 bytes of spills)
 __constant__ float c_tc3_expo[4];
+// b_hn (x 2^k) | head weights of the launch's image, refreshed the same way.  The epilogue's chunk loop is instantiated
+// per column half, so every offset into this table is a compile-time constant and the values arrive as constant-bank
+// operands: no shared-memory broadcast loads (sixteen LDS.128 per warp and tile), no registers held across the math
+__constant__ float c_tc3_tail[128];
 
 namespace {
 
@@ -72,8 +78,8 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_hfull = sm_u + OFF_BAR, bar_xfull = bar_hfull + 16, bar_done = bar_hfull + 32, bar_gfree = bar_hfull + 48,
-                 bar_xfree = bar_hfull + 64;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 80);
+                 bar_xfree = bar_hfull + 64, bar_hfree = bar_hfull + 80;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 96);
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
   {
@@ -83,11 +89,12 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_hfull + 8 * s, PROD3);  // one arrive per producer warp: own rows written
+      mbar_init(bar_hfull + 8 * s, PROD3);       // one arrive per producer warp: own rows written
       mbar_init(bar_xfull + 8 * s, 32 * PROD3);  // one arrive per producer THREAD: its far-endpoint copies landed
-      mbar_init(bar_done + 8 * s, 1);      // tcgen05.commit
-      mbar_init(bar_gfree + 8 * s, 8);     // one arrive per warp of the stage's team
-      mbar_init(bar_xfree + 8 * s, 8);
+      mbar_init(bar_done + 8 * s, 1);            // tcgen05.commit behind the own-row MMAs: accumulators complete
+      mbar_init(bar_xfree + 8 * s, 1);           // tcgen05.commit behind the far-endpoint MMAs: x images reusable
+      mbar_init(bar_gfree + 8 * s, 8);           // one arrive per warp of the stage's team: accumulators drained
+      mbar_init(bar_hfree + 8 * s, 8);           // ... : h images (previous state + transpose buffer) read back
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -101,12 +108,6 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int stride = gridDim.x;
-  // the far-endpoint MMAs only ever accumulate: the i_n columns of both accumulator stages start at zero (each
-  // epilogue warp owns the 32 lanes x 32 columns it will later drain and re-zero)
-  if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 128 + 32 * ((warp & 7) >> 2)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   // tiles past the end repeat the last one (their loads are simply unused)
   auto ldtab = [&](int tile) { return __ldg(tab + min(tile, total - 1)); };
 
@@ -119,17 +120,21 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         const uint32_t phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
         TC3_TRACE(it, 5, true);
-        mbar_wait(bar_hfull + 8 * stage, phase, status);       // own rows written
+        mbar_wait(bar_xfull + 8 * stage, phase, status);       // far-endpoint images landed (issued two tiles ago)
         TC3_TRACE(it, 6, true);
-        tc_fence_after();
-        issue_tile_mma_h_first(sm_u, tmem_base, stage);
-        // the far-endpoint images arrive last: they share the stage's x images with the transpose buffer of the
-        // tile two back, which the epilogue holds until its stores are out
-        mbar_wait(bar_xfull + 8 * stage, phase, status);
-        TC3_TRACE(it, 10, true);
         fence_proxy_async();  // the copies were generic-proxy writes of other threads, observed through the barrier
         tc_fence_after();
-        issue_tile_mma_x_second(sm_u, tmem_base, stage, xflags);
+#ifndef ABL_NOXMMA
+        issue_tile_mma_x_first(sm_u, tmem_base, stage, xflags);
+#endif
+        umma_commit(bar_xfree + 8 * stage);  // x images reusable once these retire: the copies of tile it + 2 start here
+        // the own-row images come last: they are the previous tile's transpose buffer until its stores are out
+        mbar_wait(bar_hfull + 8 * stage, phase, status);
+        TC3_TRACE(it, 10, true);
+        tc_fence_after();
+#ifndef ABL_NOHMMA
+        issue_tile_mma_h_second(sm_u, tmem_base, stage);
+#endif
         umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
         TC3_TRACE(it, 7, true);
       }
@@ -160,19 +165,34 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       for (int p = 0; p < 8; ++p) {
         const int d = __shfl_sync(FULL, iv, gl0 + p);  // -1 for detection rows inside the tile: any valid row will do
         const unsigned char* sp = imgb + (size_t)(b + (uint32_t)max(d, 0)) * row_bytes;
+#ifndef ABL_NOXCOPY
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2048u * p), "l"(sp) : "memory");
+#else
+        if (sp == nullptr) atomicOr(status, 1);
+#endif
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      // completion is signalled by the copy engine itself (one arrival per thread once its copies have landed)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_xfull + 8 * st) : "memory");
     };
     int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride), T2 = ldtab(blockIdx.x + 2 * stride);
-    int i0 = ld_idx(T0), i1 = ld_idx(T1), pw1 = ld_phys(T1);
-    const int pw0 = ld_phys(T0);
-    float4 own[8];
+    int pw1 = ld_phys(T1);
+    uint2 hh[8], hl[8];
+    {
+      // far-endpoint images of the first two tiles; own rows of the first
+      const int i0 = ld_idx(T0), i1 = ld_idx(T1), pw0 = ld_phys(T0);
+      issue_x(0, (uint32_t)T0.x, i0);
+      issue_x(1, (uint32_t)T1.x, i1);
+      float amax = 0.f;
+      float4 own[8];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int sp = __shfl_sync(FULL, pw0, gl0 + p);
-      const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T0.x + T0.y + min(g + 16 * p, T0.z - 1));
-      own[p] = __ldg(h4p + orow * ldh4 + cl4);
+      for (int p = 0; p < 8; ++p) {
+        const int sp = __shfl_sync(FULL, pw0, gl0 + p);
+        const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T0.x + T0.y + min(g + 16 * p, T0.z - 1));
+        own[p] = __ldg(h4p + orow * ldh4 + cl4);
+      }
+#pragma unroll
+      for (int p = 0; p < 8; ++p) split4(own[p], hh[p], hl[p], amax);
+      if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
@@ -180,40 +200,46 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       const uint32_t phase = (uint32_t)(it >> 1) & 1u;
       unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
       const int4 T3 = ldtab(tile + 3 * stride);      // in flight for a whole tile
-      const int i2 = ld_idx(T2), pw2 = ld_phys(T2);  // T2 landed a tile ago; these are consumed a tile from now
-      float amax = 0.f;
+      const int i2 = ld_idx(T2), pw2 = ld_phys(T2);  // T2 landed a tile ago; i2 is consumed at the bottom of this iteration
       TC3_TRACE(it, 2, tr);
-      // h images: read (chunk by chunk) by the epilogue of the tile two back until its gates were done
-      mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);
+      // h images: previous state and transpose buffer of the tile two back until its stores were out.  The rows were
+      // split while waiting, so the hand-over to the tensor core is sixteen shared-memory stores
+      mbar_wait(bar_hfree + 8 * stage, phase ^ 1u, status);
       TC3_TRACE(it, 3, tr);
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        const float4 h4 = own[p];
-        // this row's slot of the next tile: HBM latency, one tile ahead (unconditional, clamped address)
-        const int sp = __shfl_sync(FULL, pw1, gl0 + p);
-        const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T1.x + T1.y + min(g + 16 * p, T1.z - 1));
-        own[p] = __ldg(h4p + orow * ldh4 + cl4);
-        uint2 hh, hl;
-        split4(h4, hh, hl, amax);
         const uint32_t off = h_off0 + 2048u * p;
-        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh;
-        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl;
+        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh[p];
+        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl[p];
       }
-      if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
       fence_proxy_async();
       __syncwarp();
-      TC3_TRACE(it, 4, tr);
       if (lane == 0) mbar_arrive(bar_hfull + 8 * stage);
-      // far-endpoint images: this stage's x images double as the transpose buffer of the tile two back
+      TC3_TRACE(it, 4, tr);
+      // own rows of the next tile: HBM latency overlaps the copy issue below (unconditional, clamped addresses)
+      float4 own[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int sp = __shfl_sync(FULL, pw1, gl0 + p);
+        const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T1.x + T1.y + min(g + 16 * p, T1.z - 1));
+#ifndef ABL_NOOWN
+        own[p] = __ldg(h4p + orow * ldh4 + cl4);
+#else
+        own[p] = make_float4((float)orow, 0.f, 1.f, (float)p);
+#endif
+      }
+      // far-endpoint images of tile it + 2 into this stage's x images, free as soon as this tile's MMAs on them retire
       TC3_TRACE(it, 0, tr);
-      mbar_wait(bar_xfree + 8 * stage, phase ^ 1u, status);
+      mbar_wait(bar_xfree + 8 * stage, phase, status);
       TC3_TRACE(it, 1, tr);
-      issue_x(stage, (uint32_t)T0.x, i0);
-      // completion is signalled by the copy engine itself (one arrival per thread once its copies have landed), so
-      // the producers go straight on to the next tile's own rows; the issuer fences the proxies after its wait
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_xfull + 8 * stage) : "memory");
-      T0 = T1; T1 = T2; T2 = T3; i0 = i1; i1 = i2; pw1 = pw2;
+      issue_x(stage, (uint32_t)T2.x, i2);
+      float amax = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) split4(own[p], hh[p], hl[p], amax);
+      if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
+      T0 = T1; T1 = T2; T2 = T3; pw1 = pw2;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // copies issued for tiles past the end
   } else {
     // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
     const int team = warp >> 3, w8 = warp & 7;
@@ -222,14 +248,14 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const int c0 = 32 * half;                 // this warp's columns of every gate: [c0, c0 + 32)
     const int stage = team;
     const bool tr = threadIdx.x == 0 || threadIdx.x == 256;
-    unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+    unsigned char* h_hi = sm + OFF_A + stage * A_STAGE + 2 * A_PART;
+    unsigned char* h_lo = h_hi + A_PART;
     const float* bias = reinterpret_cast<const float*>(sm + OFF_BIAS);
     const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
     const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
     float* dot_part = reinterpret_cast<float*>(sm + (team ? OFF_DOT : OFF_BIAS));
     const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
-    unsigned char* tbuf = a_stage + w8 * 4096;  // [32 rows x 32 floats], 16 B chunks XOR-swizzled by row, in the x images
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
     const int bar_id = 1 + team * 4 + quad;
     auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
@@ -245,29 +271,110 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
       const int4 T2 = ldtab(tile + 2 * step2);
       const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the team's next tile
+#ifdef TC3_PREFETCH_P
+      {
+        // the three 128-byte lines of the source's P' row this warp will read (r, z, n halves)
+        const float* q = det_p + (size_t)max(ks, 0) * 192 + c0;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + H));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 2 * H));
+      }
+#endif
       TC3_TRACE(it, 8, tr);
       mbar_wait(bar_done + 8 * stage, phase, status);
       tc_fence_after();
       TC3_TRACE(it, 9, tr);
+#ifdef ABL_PP0
+      const float* __restrict__ pp = det_p + (size_t)(ks == -12345 ? 7 : 0) * 192 + c0;
+#else
       const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
+#endif
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
       f32x2 dot2 = 0ull;
+      auto gate_chunks = [&](auto half_c) {
+      constexpr int HALF = decltype(half_c)::value;
+#ifndef TC3_NO_LDTM_PIPE
+      // software-pipelined accumulator drain: two sets of 4 columns x 4 gates; the TMEM loads of step s + 2 are issued
+      // as soon as step s has consumed its set, so they land during step s + 1 (same 32 accumulator registers)
+      uint32_t A[2][16];
+      auto ldstep = [&](int s, uint32_t* a) {
+        const uint32_t cb = t0 + (uint32_t)((s >> 1) * 8 + (s & 1) * 4);
+        tmem_ld4u(cb, a);
+        tmem_ld4u(cb + 64, a + 4);
+        tmem_ld4u(cb + 128, a + 8);
+        tmem_ld4u(cb + 192, a + 12);
+      };
+      ldstep(0, A[0]);
+      ldstep(1, A[1]);
+      f32x2 hp[4];
+      uint32_t off = 0;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int ch = s >> 1, v = s & 1;
+        uint32_t* a = A[s & 1];
+        if (v == 0) {
+          off = sw128(r, 4 * half + ch);
+          const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
+          const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
+          const __half2* ph = reinterpret_cast<const __half2*>(&vh);
+          const __half2* pl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
+            hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
+        const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
+        const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+        const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
+        const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
+        const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
+        f32x2 o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = 2 * e;
+          const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(a[i], a[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
+          const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(a[4 + i], a[5 + i]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
+          const f32x2 u = fma2(rg, add2(pk2u(a[12 + i], a[13 + i]), e ? bh.y : bh.x), add2(pk2u(a[8 + i], a[9 + i]), e ? bi.y : bi.x));
+          const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
+          const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);
+          o[e] = ov;
+          dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+        }
+        if (s + 2 < 8) ldstep(s + 2, a);
+        if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
+        else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
+      }
+#else
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t ar[8], az[8], an[8], ahn[8];
+#ifndef ABL_NOLDTM
         tmem_ld8u(t0 + ch * 8, ar);
         tmem_ld8u(t0 + 64 + ch * 8, az);
         tmem_ld8u(t0 + 128 + ch * 8, an);
         tmem_ld8u(t0 + 192 + ch * 8, ahn);
+#else
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ar[q] = srcv + q; az[q] = srcv ^ q; an[q] = ks + q; ahn[q] = ks ^ q; }
+#endif
         const int j0 = c0 + ch * 8;
-        // previous state of these 8 columns = hi + lo of the stage's h images (still intact: the transpose buffer
-        // lives in the x images)
+        // previous state of these 8 columns = hi + lo of the stage's h images.  The two 16-byte slots read here
+        // (this warp's own: nobody else touches the 32 rows x 64 B x 2 images of its quadrant and column half) are
+        // dead afterwards and take the new state: the h images are the transpose buffer, in place
+        const uint32_t off = sw128(r, 4 * half + ch);
         f32x2 hp[4];
         {
-          const uint32_t off = sw128(r, 4 * half + ch);
-          const uint4 vh = *reinterpret_cast<const uint4*>(a_stage + 2 * A_PART + off);
-          const uint4 vl = *reinterpret_cast<const uint4*>(a_stage + 3 * A_PART + off);
+#ifndef ABL_NOPREV
+          const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
+          const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
+#else
+          const uint4 vh = make_uint4(srcv, ks, srcv, ks), vl = make_uint4(ks, srcv, ks, srcv);
+#endif
           const __half2* ph = reinterpret_cast<const __half2*>(&vh);
           const __half2* pl = reinterpret_cast<const __half2*>(&vl);
 #pragma unroll
@@ -276,16 +383,29 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
             hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
           }
         }
+        __syncwarp();  // every lane has read its slots of this chunk before a neighbour's new state lands in them
         tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           // additive terms of the three input gates: the source's P' row, which already holds
           // -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
+#ifndef ABL_NOPP
           const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
           const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
           const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+#else
+          const ulonglong2 br = make_ulonglong2(ONE2, NTWO2), bz = make_ulonglong2(NTWO2, ONE2), bi = make_ulonglong2(ONE2, ONE2);
+#endif
+#if defined(TC3_BIAS_SMEM)
           const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
           const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
+#elif !defined(ABL_NOBIAS)
+          const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
+          const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
+          const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
+#else
+          const ulonglong2 bh = make_ulonglong2(ONE2, NTWO2), hw = make_ulonglong2(NTWO2, ONE2);
+#endif
           f32x2 o[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -301,30 +421,81 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
             o[e] = ov;
             dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
           }
-          *reinterpret_cast<ulonglong2*>(tbuf + lane * 128 + (((2 * ch + v) ^ (lane & 7)) << 4)) = make_ulonglong2(o[0], o[1]);
+          // columns j0 .. j0 + 3 go to the row's own slot of the hi image, columns j0 + 4 .. j0 + 7 to the slot of row
+          // r ^ 4 of the lo image (slot index ^ 4: the other half of the bank groups), so that the transposed read-back
+          // below -- eight lanes per row, hi and lo slots alternating -- touches every bank group exactly once per row
+#ifndef ABL_NOTRANS
+          if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
+          else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
+#endif
         }
       }
+#endif
+      };
+      if (half == 0) gate_chunks(std::integral_constant<int, 0>{});
+      else gate_chunks(std::integral_constant<int, 1>{});
       float dot;
       {
         float d0, d1;
         up2(dot2, d0, d1);
         dot = d0 + d1;
       }
-      // accumulator stage drained: re-zero this warp's i_n columns for the accumulate-only far-endpoint MMAs
-      tmem_zero32(t0 + 128);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained, h images read
+      if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start
       TC3_TRACE(it, 11, tr);
-      // transposed read-back: each store instruction writes 4 rows x 128 B (full lines)
+      // transposed read-back: each store instruction writes 4 rows x 128 B (full lines).  Lane (rr, cc): float4 cc of
+      // row rr; even cc from the hi image at the row's slot, odd cc from the lo image at row rr ^ 4
+#ifndef TC3_NO_PRED_STG
+      {
+        // all eight shared-memory reads first, then eight predicated stores off one running pointer (no branches, no
+        // 64-bit multiply per row)
+        const int cc = lane & 7, wh = cc & 1;
+        // row 4 k + (lane >> 3) of the quadrant: even k and odd k differ in bit 2 of the row (and of the swizzled slot)
+        const unsigned char* img = wh ? h_lo : h_hi;
+        const unsigned char* a0 = img + sw128(quad * 32 + (lane >> 3) + 4 * wh, 4 * half + (cc >> 1));
+        const unsigned char* a1 = img + sw128(quad * 32 + (lane >> 3) + 4 * (wh ^ 1), 4 * half + (cc >> 1));
+        float4 v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int rr = 4 * k + (lane >> 3), cc = lane & 7;
-        const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
+        for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(((k & 1) ? a1 : a0) + (k >> 1) * 1024);
+        float* op = out0 + (size_t)(lane >> 3) * ldh + 4 * cc;
+        const size_t step = (size_t)ldh * 4;
+        const uint32_t vm = vmask >> (lane >> 3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.u32 p, %0, 0;\n\t"
+              "@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+              ::"r"((vm >> (4 * k)) & 1u), "l"(op), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w)
+              : "memory");
+          op += step;
+        }
       }
+#else
+      {
+        const int cc = lane & 7, wh = cc & 1;
+        const unsigned char* img = wh ? h_lo : h_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = 4 * k + (lane >> 3);
+          const int rs = quad * 32 + (wh ? (rr ^ 4) : rr);
+#ifndef ABL_NOTRANS
+          const float4 v = *reinterpret_cast<const float4*>(img + sw128(rs, 4 * half + (cc >> 1)));
+#else
+          const float4 v = make_float4(dot, dot, (float)rs, dot);
+          if (img == nullptr) atomicOr(status, 1);
+#endif
+#ifndef ABL_NOSTG
+          if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
+#else
+          if (v.x == 123.456f) atomicOr(status, 1);
+#endif
+        }
+      }
+#endif
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xfree + 8 * stage);  // transpose buffer (the x images) read back: may be refilled
+      if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // h images read back: the producers may write the next own rows
       TC3_TRACE(it, 12, tr);
       // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
       if (half == 1) dot_part[r] = dot;
@@ -368,6 +539,7 @@ int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
     TMPNN_LAUNCH_CHECK();
   }
   TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_expo, (const unsigned char*)edge_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice, st));
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_tail, (const unsigned char*)edge_image + OFF_BIAS + 3 * H * 4, 512, 0, cudaMemcpyDeviceToDevice, st));
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, ix->tile128_ptr + g->num_seqs, (const int4*)tile_table,

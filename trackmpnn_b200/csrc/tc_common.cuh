@@ -20,8 +20,8 @@ constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // the part of the packed image
 constexpr int OFF_WT = IMAGE_BYTES;
 constexpr int OFF_BS = OFF_WT + 64 * 192 * 4;
 constexpr int IMAGE_TOTAL_BYTES = OFF_BS + 192 * 4;
-constexpr int OFF_BAR = IMAGE_BYTES;             // 10 mbarriers + tmem pointer, inside the alignment gap
-constexpr int OFF_DOT = OFF_BAR + 96;            // 128 floats: head partial sums of the upper column half
+constexpr int OFF_BAR = IMAGE_BYTES;             // 12 mbarriers + tmem pointer, inside the alignment gap
+constexpr int OFF_DOT = OFF_BAR + 112;           // 128 floats: head partial sums of the upper column half
 constexpr int OFF_A = 98 * 1024;                 // first A stage (1024-aligned)
 constexpr int A_PART = TCM * 128;                // [128 rows x 64 fp16] = 16 KB
 constexpr int A_STAGE = 4 * A_PART;              // x_hi, x_lo, h_hi, h_lo
@@ -184,16 +184,29 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
+#ifdef ABL_NOMUFU
+  return pk2(a * a, b * b);
+#else
   return pk2(ex2_approx(a), ex2_approx(b));
+#endif
 }
 __device__ __forceinline__ f32x2 rcp_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
+#ifdef ABL_NOMUFU
+  return pk2(a * 0.5f, b * 0.5f);
+#else
   return pk2(rcp_approx(a), rcp_approx(b));
+#endif
 }
 __device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4u(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -234,6 +247,39 @@ __device__ __forceinline__ void issue_tile_mma_x_second(uint32_t sm_u, uint32_t 
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, 1);
+}
+// ---- the two halves of the MMA issue, far-endpoint part FIRST (mp_step_tc3.cu, in-place transpose) --------
+// The x images are complete long before the stage's h images may be rewritten (those double as the epilogue's
+// transpose buffer), so the far-endpoint MMAs initialise r | z | i_n as soon as the accumulators are drained and
+// run while the previous tile's stores are still going out; only the own-row half waits for the h images.
+__device__ __forceinline__ void issue_tile_mma_x_first(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags) {
+  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
+  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
+  const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, acc);
+      acc = 1;
+    }
+}
+__device__ __forceinline__ void issue_tile_mma_h_second(uint32_t sm_u, uint32_t tmem_base, int stage) {
+  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
+  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
+  const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
+  uint32_t acc_n = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
+      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
+      acc_n = 1;
+    }
 }
 // 32 zero columns for this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
