@@ -1,5 +1,6 @@
 import numpy as np,sys
 t=np.load(sys.argv[1]).astype(np.float64)
+sh=int(sys.argv[2]) if len(sys.argv)>2 else 2   # epilogue's next tile: 2 (two teams) or 1 (one team)
 n=int((t[:,9]!=0).sum()); t=t[:n]; lo,hi=n//4,3*n//4; seg=t[lo:hi]
 print(n,'tiles; cycles/tile',(seg[-1,9]-seg[0,9])/(len(seg)-1))
 def d(a,b,shift=0):
@@ -18,12 +19,9 @@ print('E: top -> done                ',d(8,9))
 print('E: gates                      ',d(9,11))
 print('E: stores                     ',d(11,12))
 print('E: head                       ',d(12,13))
-print('E: team cycle (2 tiles)       ',d(8,8,2))
+print('E: cycle                      ',d(8,8,sh))
 print('gates end -> next same-stage done', d(11,9,2))
-print('stores end(hfree) -> P sees   ', d(12,3,2))
 print('stores end(hfree) -> hfull arrive', d(12,4,2))
-print('hfull arrive -> issuer saw (10)', d(4,10))
 print('issuer h commit(7) -> epi done(9)', d(7,9))
 t0=t[lo,2]
-print('  it     P:x0     x1    top  hfree  hfull | I:gfree xfull   done  hfullw | E:top   done  gates stores  head')
-for i in range(lo,lo+8): print(i,' '.join(f'{(v-t0):7.0f}' for v in t[i,:14]))
+for i in range(lo,lo+6): print(i,' '.join(f'{(v-t0):7.0f}' for v in t[i,:14]))

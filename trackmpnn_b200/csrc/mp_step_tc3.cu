@@ -93,9 +93,19 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       mbar_init(bar_xfull + 8 * s, 32 * PROD3);  // one arrive per producer THREAD: its far-endpoint copies landed
       mbar_init(bar_done + 8 * s, 1);            // tcgen05.commit behind the own-row MMAs: accumulators complete
       mbar_init(bar_xfree + 8 * s, 1);           // tcgen05.commit behind the far-endpoint MMAs: x images reusable
+#ifdef TC3_ONE_TEAM
+      mbar_init(bar_gfree + 8 * s, EPI3);        // one arrive per epilogue warp: accumulators drained
+      mbar_init(bar_hfree + 8 * s, EPI3);        // ... : h images (previous state + transpose buffer) read back
+#else
       mbar_init(bar_gfree + 8 * s, 8);           // one arrive per warp of the stage's team: accumulators drained
       mbar_init(bar_hfree + 8 * s, 8);           // ... : h images (previous state + transpose buffer) read back
+#endif
     }
+#ifdef TC3_GATE_TOKEN
+    for (int q = 0; q < 2; ++q) mbar_init(sm_u + OFF_DOT + 512 + 8 * q, 8);
+#else
+    for (int q = 0; q < 16; ++q) mbar_init(sm_u + OFF_DOT + 512 + 8 * q, 1);  // head hand-over, per team and quadrant
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -113,7 +123,11 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 
   if (warp == ISSUER3) {
     // ================= MMA issuer =================
+#ifdef TC3_ELECT
+    if (elect_one()) {
+#else
     if (lane == 0) {
+#endif
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
         const int stage = it & 1;
@@ -241,6 +255,165 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     }
     asm volatile("cp.async.wait_all;" ::: "memory");  // copies issued for tiles past the end
   } else {
+#ifdef TC3_ONE_TEAM
+    // ================= epilogue: all 16 warps on every tile, stages alternate =================
+    // Two concurrently draining teams leave no stage to prepare ahead: each team's next tile can only be loaded and
+    // multiplied after its own stores.  With every warp on every tile the other stage is filled while this one drains
+    // (true double buffering); warps run free between the barriers, so one warp's stores overlap another's gate math.
+    const int quad = warp & 3, cq = warp >> 2;  // quad == warp % 4: the TMEM lane quadrant this warp may read
+    const int r = quad * 32 + lane;             // row of the tile == TMEM lane
+    const int c0 = 16 * cq;                     // this warp's columns of every gate: [c0, c0 + 16)
+    const bool tr = threadIdx.x == 0;
+    const float headb = c_tc3_expo[0];
+    float* dot_p1 = reinterpret_cast<float*>(sm + OFF_BIAS);        // bias slots of the image: folded into P' / constants
+    float* dot_p3 = dot_p1 + 128;
+    float* dot_s2 = reinterpret_cast<float*>(sm + OFF_DOT);
+    const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
+    const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+    const uint32_t t00 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+    const int bar_id = 1 + quad;
+    auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
+    int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride);
+    int srcv = ld_src(T0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+      unsigned char* h_hi = sm + OFF_A + stage * A_STAGE + 2 * A_PART;
+      unsigned char* h_lo = h_hi + A_PART;
+      const uint32_t t0 = t00 + (uint32_t)(stage * 256);
+      const size_t row_cur = (size_t)T0.x + T0.y + r;
+      const bool valid = T0.z - r > 0 && srcv >= 0;
+      const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the previous tile
+      const int4 T2 = ldtab(tile + 2 * stride);
+      const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the next tile
+      TC3_TRACE(it, 8, tr);
+      mbar_wait(bar_done + 8 * stage, phase, status);
+      tc_fence_after();
+      TC3_TRACE(it, 9, tr);
+      const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
+      f32x2 dot2 = 0ull;
+      auto gate_steps = [&](auto cq_c) {
+        constexpr int CQ = decltype(cq_c)::value;
+        // software-pipelined accumulator drain: two sets of 4 columns x 4 gates
+        uint32_t A[2][16];
+        auto ldstep = [&](int s, uint32_t* a) {
+          const uint32_t cb = t0 + (uint32_t)(4 * s);
+          tmem_ld4u(cb, a);
+          tmem_ld4u(cb + 64, a + 4);
+          tmem_ld4u(cb + 128, a + 8);
+          tmem_ld4u(cb + 192, a + 12);
+        };
+        ldstep(0, A[0]);
+        ldstep(1, A[1]);
+        f32x2 hp[4];
+        uint32_t off = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int ch = s >> 1, v = s & 1;
+          uint32_t* a = A[s & 1];
+          if (v == 0) {
+            // previous state of these 8 columns = hi + lo of the stage's h images; the slots read here (this warp's own)
+            // are dead afterwards and take the new state: the h images are the transpose buffer, in place
+            off = sw128(r, 2 * CQ + ch);
+            const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
+            const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
+            const __half2* ph = reinterpret_cast<const __half2*>(&vh);
+            const __half2* pl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
+              hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
+            }
+            __syncwarp();  // every lane has read its slots of this chunk before a neighbour's new state lands in them
+          }
+          tmem_ld_wait();
+          // additive terms of the three input gates: the source's P' row, which already holds
+          // -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
+          const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + 4 * s));
+          const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + 4 * s));
+          const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + 4 * s));
+          const int jc = 16 * CQ + 4 * s;  // compile-time after unrolling
+          const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
+          const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
+          f32x2 o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * e;
+            // r, z = 1 / (1 + 2^(-log2e (acc + P + b)))   (2^x -> inf gives exactly 0, no clamp needed)
+            const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(a[i], a[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
+            const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(a[4 + i], a[5 + i]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
+            // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + P_n + b_in + r (h_n + b_hn), in the accumulators' scale
+            const f32x2 u = fma2(rg, add2(pk2u(a[12 + i], a[13 + i]), e ? bh.y : bh.x), add2(pk2u(a[8 + i], a[9 + i]), e ? bi.y : bi.x));
+            const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
+            const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
+            o[e] = ov;
+            dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+          }
+          if (s + 2 < 4) ldstep(s + 2, a);
+          // columns +0..3 of the chunk go to the row's own slot of the hi image, columns +4..7 to the slot of row r ^ 4 of
+          // the lo image (slot index ^ 4: the other half of the bank groups): conflict-free transposed read-back
+          if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
+          else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 2 * CQ + ch)) = make_ulonglong2(o[0], o[1]);
+        }
+      };
+      if (cq == 0) gate_steps(std::integral_constant<int, 0>{});
+      else if (cq == 1) gate_steps(std::integral_constant<int, 1>{});
+      else if (cq == 2) gate_steps(std::integral_constant<int, 2>{});
+      else gate_steps(std::integral_constant<int, 3>{});
+      float dot;
+      {
+        float d0, d1;
+        up2(dot2, d0, d1);
+        dot = d0 + d1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the far-endpoint MMAs of tile it + 2 may start
+      TC3_TRACE(it, 11, tr);
+      // transposed read-back: each store instruction writes 8 rows x 64 B.  Lane (q, cc): float4 cc of row 8 k + q; even cc
+      // from the hi image at the row's slot, odd cc from the lo image at row ^ 4
+      {
+        const int cc = lane & 3, wh = cc & 1, q = lane >> 2;
+        const unsigned char* a0 = (wh ? h_lo : h_hi) + sw128(quad * 32 + (q ^ (wh << 2)), 2 * cq + (cc >> 1));
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(a0 + k * 1024);
+        float* op = out0 + (size_t)q * ldh + 4 * cc;
+        const size_t step = (size_t)ldh * 8;
+        const uint32_t vm = vmask >> q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.u32 p, %0, 0;\n\t"
+              "@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+              ::"r"((vm >> (8 * k)) & 1u), "l"(op), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w)
+              : "memory");
+          op += step;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // h images read back: the producers may write the own rows of tile it + 2
+      TC3_TRACE(it, 12, tr);
+      // head: a row's four column quarters live in the warps (quad, 0..3); fixed summation order (d0 + d1) + (d2 + d3)
+      if (cq == 1) dot_p1[r] = dot;
+      if (cq == 3) dot_p3[r] = dot;
+      named_bar_sync(bar_id, 128);
+      if (cq == 0) dot += dot_p1[r];
+      if (cq == 2) dot_s2[r] = dot + dot_p3[r];
+      named_bar_sync(bar_id, 128);
+      if (cq == 0 && valid) {
+        const float lg = dot + dot_s2[r] + (first_group ? headb : logit[row_cur]);
+        logit[row_cur] = lg;
+        if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
+      }
+      TC3_TRACE(it, 13, tr);
+      T0 = T1; T1 = T2; srcv = srcv1;
+    }
+#else
     // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
     const int team = warp >> 3, w8 = warp & 7;
     const int quad = w8 & 3, half = w8 >> 2;  // quad == warp % 4: the TMEM lane quadrant this warp may read
@@ -258,17 +431,24 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
     const int bar_id = 1 + team * 4 + quad;
+    const uint32_t bar_dfull = sm_u + OFF_DOT + 512 + 8 * (team * 4 + quad);  // + 64: the reverse direction (partials read)
+    const uint32_t bar_tok = sm_u + OFF_DOT + 512;  // experiment (TC3_GATE_TOKEN; not together with TC3_HEAD_MBAR)
     auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
     const int first = blockIdx.x + team * stride, step2 = 2 * stride;
     int4 T0 = ldtab(first), T1 = ldtab(first + step2);
     int srcv = ld_src(T0);
+#ifdef TC3_KS_PIPE
+    int ks = __ldg(det_of_row + T0.x + max(srcv, 0));
+#endif
     uint32_t n = 0;  // tiles this team has done
     for (int tile = first; tile < total; tile += step2, ++n) {
       const uint32_t phase = n & 1u;
       const int it = 2 * (int)n + team;
       const size_t row_cur = (size_t)T0.x + T0.y + r;
       const bool valid = T0.z - r > 0 && srcv >= 0;
+#ifndef TC3_KS_PIPE
       const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
+#endif
       const int4 T2 = ldtab(tile + 2 * step2);
       const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the team's next tile
 #ifdef TC3_PREFETCH_P
@@ -280,9 +460,23 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 2 * H));
       }
 #endif
+#ifdef TC3_PRELOAD_P
+      // the first step's P' terms are fetched before the wait (cold lines: an L2 round trip that would otherwise sit
+      // in front of the first gate of the tile); the later steps hit the same three lines in L1
+      const float* __restrict__ pp_pre = det_p + (size_t)max(ks, 0) * 192 + c0;
+      const ulonglong2 br0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre));
+      const ulonglong2 bz0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre + H));
+      const ulonglong2 bi0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre + 2 * H));
+#endif
       TC3_TRACE(it, 8, tr);
       mbar_wait(bar_done + 8 * stage, phase, status);
       tc_fence_after();
+#ifdef TC3_GATE_TOKEN
+      // strict alternation of the two teams' gate phases: a team starts its MUFU-heavy gates only when the other team's
+      // previous gates are through (experiment: does sharing the MUFU pipe cost more than waiting for it?)
+      if (team == 1) mbar_wait(bar_tok, phase, status);
+      else if (n > 0) mbar_wait(bar_tok + 8, phase ^ 1u, status);
+#endif
       TC3_TRACE(it, 9, tr);
 #ifdef ABL_PP0
       const float* __restrict__ pp = det_p + (size_t)(ks == -12345 ? 7 : 0) * 192 + c0;
@@ -327,9 +521,15 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
           __syncwarp();
         }
         tmem_ld_wait();
+#ifdef TC3_PRELOAD_P
+        const ulonglong2 br = s == 0 ? br0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
+        const ulonglong2 bz = s == 0 ? bz0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
+        const ulonglong2 bi = s == 0 ? bi0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+#else
         const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
         const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
         const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+#endif
         const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
         const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
         const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
@@ -443,7 +643,15 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start
+#ifdef TC3_GATE_TOKEN
+      if (lane == 0) mbar_arrive(bar_tok + 8 * team);
+#endif
       TC3_TRACE(it, 11, tr);
+#ifdef TC3_KS_PIPE
+      // the next tile's P' row index: its source row landed during the gates, this lookup lands during the stores, so
+      // the dependent chain source -> detection rank -> P' never sits in front of a tile's first gate
+      const int ks1 = __ldg(det_of_row + T1.x + max(srcv1, 0));
+#endif
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines).  Lane (rr, cc): float4 cc of
       // row rr; even cc from the hi image at the row's slot, odd cc from the lo image at row rr ^ 4
 #ifndef TC3_NO_PRED_STG
@@ -498,6 +706,25 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // h images read back: the producers may write the next own rows
       TC3_TRACE(it, 12, tr);
       // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
+#ifdef TC3_HEAD_MBAR
+      // hand-over through a pair of mbarriers instead of two named barriers: the upper half publishes its partial sums
+      // and goes on to its next tile at once; it only ever waits for the lower half to have read the PREVIOUS tile's
+      if (half == 1) {
+        mbar_wait(bar_dfull + 64, phase ^ 1u, status);
+        dot_part[r] = dot;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfull);
+      } else {
+        mbar_wait(bar_dfull, phase, status);
+        if (valid) {
+          const float lg = dot + dot_part[r] + (first_group ? headb : logit[row_cur]);
+          logit[row_cur] = lg;
+          if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfull + 64);
+      }
+#else
       if (half == 1) dot_part[r] = dot;
       named_bar_sync(bar_id, 64);
       if (half == 0 && valid) {
@@ -506,9 +733,14 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
       }
       named_bar_sync(bar_id, 64);
+#endif
       TC3_TRACE(it, 13, tr);
       T0 = T1; T1 = T2; srcv = srcv1;
+#ifdef TC3_KS_PIPE
+      ks = ks1;
+#endif
     }
+#endif
   }
 
   tc_fence_before();

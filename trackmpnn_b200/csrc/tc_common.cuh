@@ -78,6 +78,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
     }
   }
 }
+// one elected lane of a converged warp (the compiler knows a region guarded by elect.sync has a single active thread, so
+// descriptors computed inside it go to uniform registers without a per-lane broadcast loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
