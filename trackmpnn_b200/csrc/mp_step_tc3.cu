@@ -51,6 +51,7 @@ namespace {
 constexpr int EPI3 = 16, PROD3 = 8;
 constexpr int ISSUER3 = EPI3 + PROD3;              // warp 24
 constexpr int TC3_THREADS = 32 * (EPI3 + PROD3 + 1);  // 800 -> 80 registers per thread
+constexpr int H_BUF = 2 * A_PART;                      // one own-row buffer: [h_hi | h_lo]
 // barriers (8 bytes each, two stages): full, done, gfree, xfree; then the TMEM pointer
 // head partial sums: team 0 in the r | z bias slots of the image (unused here: folded into P'), team 1 at OFF_DOT
 
@@ -77,8 +78,11 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_hfull = sm_u + OFF_BAR, bar_xfull = bar_hfull + 16, bar_done = bar_hfull + 32, bar_gfree = bar_hfull + 48,
-                 bar_xfree = bar_hfull + 64, bar_hfree = bar_hfull + 80;
+  // shared-memory images behind the weights: ONE pair of far-endpoint images and THREE pairs of own-row images
+  const uint32_t x_u = sm_u + OFF_A;
+  unsigned char* const h_img = sm + OFF_A + 2 * A_PART;  // + hb * H_BUF: [h_hi | h_lo] of buffer hb
+  const uint32_t bar_hfull = sm_u + OFF_BAR, bar_hfree = bar_hfull + 24, bar_xfull = bar_hfull + 48, bar_xfree = bar_hfull + 56,
+                 bar_done = bar_hfull + 64, bar_gfree = bar_hfull + 80;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 96);
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
@@ -88,24 +92,16 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     for (int i = threadIdx.x; i < IMAGE_BYTES / 16; i += TC3_THREADS) sdst[i] = __ldg(gsrc + i);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_hfull + 8 * s, PROD3);       // one arrive per producer warp: own rows written
-      mbar_init(bar_xfull + 8 * s, 32 * PROD3);  // one arrive per producer THREAD: its far-endpoint copies landed
-      mbar_init(bar_done + 8 * s, 1);            // tcgen05.commit behind the own-row MMAs: accumulators complete
-      mbar_init(bar_xfree + 8 * s, 1);           // tcgen05.commit behind the far-endpoint MMAs: x images reusable
-#ifdef TC3_ONE_TEAM
-      mbar_init(bar_gfree + 8 * s, EPI3);        // one arrive per epilogue warp: accumulators drained
-      mbar_init(bar_hfree + 8 * s, EPI3);        // ... : h images (previous state + transpose buffer) read back
-#else
-      mbar_init(bar_gfree + 8 * s, 8);           // one arrive per warp of the stage's team: accumulators drained
-      mbar_init(bar_hfree + 8 * s, 8);           // ... : h images (previous state + transpose buffer) read back
-#endif
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(bar_hfull + 8 * b, PROD3);  // one arrive per producer warp: own rows written
+      mbar_init(bar_hfree + 8 * b, 8);      // one arrive per warp of the tile's team: previous state + transpose buffer read back
     }
-#ifdef TC3_GATE_TOKEN
-    for (int q = 0; q < 2; ++q) mbar_init(sm_u + OFF_DOT + 512 + 8 * q, 8);
-#else
-    for (int q = 0; q < 16; ++q) mbar_init(sm_u + OFF_DOT + 512 + 8 * q, 1);  // head hand-over, per team and quadrant
-#endif
+    mbar_init(bar_xfull, 32 * PROD3);       // one arrive per producer THREAD: its far-endpoint copies landed
+    mbar_init(bar_xfree, 1);                // tcgen05.commit behind the far-endpoint MMAs: x images reusable
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_done + 8 * s, 1);       // tcgen05.commit behind the own-row MMAs: accumulators complete
+      mbar_init(bar_gfree + 8 * s, 8);      // one arrive per warp of the stage's team: accumulators drained
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -123,34 +119,30 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 
   if (warp == ISSUER3) {
     // ================= MMA issuer =================
-#ifdef TC3_ELECT
     if (elect_one()) {
-#else
-    if (lane == 0) {
-#endif
-      int it = 0;
+      int it = 0, hb = 0;
+      uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
         const int stage = it & 1;
         const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
         TC3_TRACE(it, 5, true);
-        mbar_wait(bar_xfull + 8 * stage, phase, status);       // far-endpoint images landed (issued two tiles ago)
+        mbar_wait(bar_xfull, (uint32_t)it & 1u, status);       // far-endpoint images landed (issued a tile ago)
         TC3_TRACE(it, 6, true);
         fence_proxy_async();  // the copies were generic-proxy writes of other threads, observed through the barrier
         tc_fence_after();
-#ifndef ABL_NOXMMA
-        issue_tile_mma_x_first(sm_u, tmem_base, stage, xflags);
-#endif
-        umma_commit(bar_xfree + 8 * stage);  // x images reusable once these retire: the copies of tile it + 2 start here
-        // the own-row images come last: they are the previous tile's transpose buffer until its stores are out
-        mbar_wait(bar_hfull + 8 * stage, phase, status);
+        issue_tile_mma_x_first(sm_u, d0, x_u, xflags);
+        umma_commit(bar_xfree);  // x images reusable once these retire: the copies of tile it + 1 start here
+        // own rows: written up to two tiles ahead into the third buffer, so this wait is normally over already and
+        // a team's hand-over from one tile to its next is the 36 MMAs only
+        mbar_wait(bar_hfull + 8 * hb, hphase, status);
         TC3_TRACE(it, 10, true);
         tc_fence_after();
-#ifndef ABL_NOHMMA
-        issue_tile_mma_h_second(sm_u, tmem_base, stage);
-#endif
+        issue_tile_mma_h_second(sm_u, d0, x_u + 2 * A_PART + (uint32_t)hb * H_BUF);
         umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
         TC3_TRACE(it, 7, true);
+        if (++hb == 3) { hb = 0; hphase ^= 1u; }
       }
     }
   } else if (warp >= EPI3) {
@@ -173,29 +165,24 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     // rows past the end of the slab repeat its last row; everything they produce is masked by the epilogue
     auto ld_idx = [&](const int4 T) { return __ldg(dst + T.x + T.y + min(idx_row, T.z - 1)); };
     auto ld_phys = [&](const int4 T) { return dfr ? __ldg(phys + T.x + T.y + min(idx_row, T.z - 1)) : 0; };
-    auto issue_x = [&](int st, uint32_t b, int iv) {
-      const uint32_t s0 = x_dst0 + (uint32_t)st * A_STAGE;
+    auto issue_x = [&](uint32_t b, int iv) {
+      const uint32_t s0 = x_dst0;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int d = __shfl_sync(FULL, iv, gl0 + p);  // -1 for detection rows inside the tile: any valid row will do
         const unsigned char* sp = imgb + (size_t)(b + (uint32_t)max(d, 0)) * row_bytes;
-#ifndef ABL_NOXCOPY
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2048u * p), "l"(sp) : "memory");
-#else
-        if (sp == nullptr) atomicOr(status, 1);
-#endif
       }
       // completion is signalled by the copy engine itself (one arrival per thread once its copies have landed)
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_xfull + 8 * st) : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_xfull) : "memory");
     };
     int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride), T2 = ldtab(blockIdx.x + 2 * stride);
-    int pw1 = ld_phys(T1);
+    int pw1 = ld_phys(T1), i1 = ld_idx(T1);
     uint2 hh[8], hl[8];
     {
-      // far-endpoint images of the first two tiles; own rows of the first
-      const int i0 = ld_idx(T0), i1 = ld_idx(T1), pw0 = ld_phys(T0);
-      issue_x(0, (uint32_t)T0.x, i0);
-      issue_x(1, (uint32_t)T1.x, i1);
+      // far-endpoint images and own rows of the first tile
+      const int i0 = ld_idx(T0), pw0 = ld_phys(T0);
+      issue_x((uint32_t)T0.x, i0);
       float amax = 0.f;
       float4 own[8];
 #pragma unroll
@@ -208,27 +195,26 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       for (int p = 0; p < 8; ++p) split4(own[p], hh[p], hl[p], amax);
       if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
     }
-    int it = 0;
+    int it = 0, hb = 0;
+    uint32_t hphase = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
-      const int stage = it & 1;
-      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-      unsigned char* a_stage = sm + OFF_A + stage * A_STAGE;
+      unsigned char* hbuf = h_img + hb * H_BUF;
       const int4 T3 = ldtab(tile + 3 * stride);      // in flight for a whole tile
-      const int i2 = ld_idx(T2), pw2 = ld_phys(T2);  // T2 landed a tile ago; i2 is consumed at the bottom of this iteration
+      const int i2 = ld_idx(T2), pw2 = ld_phys(T2);  // T2 landed a tile ago; consumed a tile from now
       TC3_TRACE(it, 2, tr);
-      // h images: previous state and transpose buffer of the tile two back until its stores were out.  The rows were
-      // split while waiting, so the hand-over to the tensor core is sixteen shared-memory stores
-      mbar_wait(bar_hfree + 8 * stage, phase ^ 1u, status);
+      // own-row images, buffer it % 3: previous state and transpose buffer of the tile three back -- free long ago, so
+      // the rows (split while waiting) go in one or two tiles before their MMAs can start
+      mbar_wait(bar_hfree + 8 * hb, hphase ^ 1u, status);
       TC3_TRACE(it, 3, tr);
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const uint32_t off = h_off0 + 2048u * p;
-        *reinterpret_cast<uint2*>(a_stage + 2 * A_PART + off) = hh[p];
-        *reinterpret_cast<uint2*>(a_stage + 3 * A_PART + off) = hl[p];
+        *reinterpret_cast<uint2*>(hbuf + off) = hh[p];
+        *reinterpret_cast<uint2*>(hbuf + A_PART + off) = hl[p];
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_hfull + 8 * stage);
+      if (lane == 0) mbar_arrive(bar_hfull + 8 * hb);
       TC3_TRACE(it, 4, tr);
       // own rows of the next tile: HBM latency overlaps the copy issue below (unconditional, clamped addresses)
       float4 own[8];
@@ -236,184 +222,22 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       for (int p = 0; p < 8; ++p) {
         const int sp = __shfl_sync(FULL, pw1, gl0 + p);
         const uint32_t orow = dfr ? (uint32_t)sp : (uint32_t)(T1.x + T1.y + min(g + 16 * p, T1.z - 1));
-#ifndef ABL_NOOWN
         own[p] = __ldg(h4p + orow * ldh4 + cl4);
-#else
-        own[p] = make_float4((float)orow, 0.f, 1.f, (float)p);
-#endif
       }
-      // far-endpoint images of tile it + 2 into this stage's x images, free as soon as this tile's MMAs on them retire
+      // far-endpoint images of the next tile: the single pair of x images is free as soon as this tile's MMAs on it retire
       TC3_TRACE(it, 0, tr);
-      mbar_wait(bar_xfree + 8 * stage, phase, status);
+      mbar_wait(bar_xfree, (uint32_t)it & 1u, status);
       TC3_TRACE(it, 1, tr);
-      issue_x(stage, (uint32_t)T2.x, i2);
+      issue_x((uint32_t)T1.x, i1);
       float amax = 0.f;
 #pragma unroll
       for (int p = 0; p < 8; ++p) split4(own[p], hh[p], hl[p], amax);
       if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);  // fp16 split would overflow: use the FMA path
-      T0 = T1; T1 = T2; T2 = T3; pw1 = pw2;
+      T0 = T1; T1 = T2; T2 = T3; pw1 = pw2; i1 = i2;
+      if (++hb == 3) { hb = 0; hphase ^= 1u; }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");  // copies issued for tiles past the end
   } else {
-#ifdef TC3_ONE_TEAM
-    // ================= epilogue: all 16 warps on every tile, stages alternate =================
-    // Two concurrently draining teams leave no stage to prepare ahead: each team's next tile can only be loaded and
-    // multiplied after its own stores.  With every warp on every tile the other stage is filled while this one drains
-    // (true double buffering); warps run free between the barriers, so one warp's stores overlap another's gate math.
-    const int quad = warp & 3, cq = warp >> 2;  // quad == warp % 4: the TMEM lane quadrant this warp may read
-    const int r = quad * 32 + lane;             // row of the tile == TMEM lane
-    const int c0 = 16 * cq;                     // this warp's columns of every gate: [c0, c0 + 16)
-    const bool tr = threadIdx.x == 0;
-    const float headb = c_tc3_expo[0];
-    float* dot_p1 = reinterpret_cast<float*>(sm + OFF_BIAS);        // bias slots of the image: folded into P' / constants
-    float* dot_p3 = dot_p1 + 128;
-    float* dot_s2 = reinterpret_cast<float*>(sm + OFF_DOT);
-    const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
-    const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
-    const uint32_t t00 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-    const int bar_id = 1 + quad;
-    auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
-    int4 T0 = ldtab(blockIdx.x), T1 = ldtab(blockIdx.x + stride);
-    int srcv = ld_src(T0);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
-      const int stage = it & 1;
-      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-      unsigned char* h_hi = sm + OFF_A + stage * A_STAGE + 2 * A_PART;
-      unsigned char* h_lo = h_hi + A_PART;
-      const uint32_t t0 = t00 + (uint32_t)(stage * 256);
-      const size_t row_cur = (size_t)T0.x + T0.y + r;
-      const bool valid = T0.z - r > 0 && srcv >= 0;
-      const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the previous tile
-      const int4 T2 = ldtab(tile + 2 * stride);
-      const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the next tile
-      TC3_TRACE(it, 8, tr);
-      mbar_wait(bar_done + 8 * stage, phase, status);
-      tc_fence_after();
-      TC3_TRACE(it, 9, tr);
-      const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
-      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
-      f32x2 dot2 = 0ull;
-      auto gate_steps = [&](auto cq_c) {
-        constexpr int CQ = decltype(cq_c)::value;
-        // software-pipelined accumulator drain: two sets of 4 columns x 4 gates
-        uint32_t A[2][16];
-        auto ldstep = [&](int s, uint32_t* a) {
-          const uint32_t cb = t0 + (uint32_t)(4 * s);
-          tmem_ld4u(cb, a);
-          tmem_ld4u(cb + 64, a + 4);
-          tmem_ld4u(cb + 128, a + 8);
-          tmem_ld4u(cb + 192, a + 12);
-        };
-        ldstep(0, A[0]);
-        ldstep(1, A[1]);
-        f32x2 hp[4];
-        uint32_t off = 0;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const int ch = s >> 1, v = s & 1;
-          uint32_t* a = A[s & 1];
-          if (v == 0) {
-            // previous state of these 8 columns = hi + lo of the stage's h images; the slots read here (this warp's own)
-            // are dead afterwards and take the new state: the h images are the transpose buffer, in place
-            off = sw128(r, 2 * CQ + ch);
-            const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
-            const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
-            const __half2* ph = reinterpret_cast<const __half2*>(&vh);
-            const __half2* pl = reinterpret_cast<const __half2*>(&vl);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
-              hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
-            }
-            __syncwarp();  // every lane has read its slots of this chunk before a neighbour's new state lands in them
-          }
-          tmem_ld_wait();
-          // additive terms of the three input gates: the source's P' row, which already holds
-          // -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
-          const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + 4 * s));
-          const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + 4 * s));
-          const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + 4 * s));
-          const int jc = 16 * CQ + 4 * s;  // compile-time after unrolling
-          const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
-          const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
-          f32x2 o[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = 2 * e;
-            // r, z = 1 / (1 + 2^(-log2e (acc + P + b)))   (2^x -> inf gives exactly 0, no clamp needed)
-            const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(a[i], a[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
-            const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(a[4 + i], a[5 + i]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
-            // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + P_n + b_in + r (h_n + b_hn), in the accumulators' scale
-            const f32x2 u = fma2(rg, add2(pk2u(a[12 + i], a[13 + i]), e ? bh.y : bh.x), add2(pk2u(a[8 + i], a[9 + i]), e ? bi.y : bi.x));
-            const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
-            const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
-            o[e] = ov;
-            dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
-          }
-          if (s + 2 < 4) ldstep(s + 2, a);
-          // columns +0..3 of the chunk go to the row's own slot of the hi image, columns +4..7 to the slot of row r ^ 4 of
-          // the lo image (slot index ^ 4: the other half of the bank groups): conflict-free transposed read-back
-          if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
-          else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 2 * CQ + ch)) = make_ulonglong2(o[0], o[1]);
-        }
-      };
-      if (cq == 0) gate_steps(std::integral_constant<int, 0>{});
-      else if (cq == 1) gate_steps(std::integral_constant<int, 1>{});
-      else if (cq == 2) gate_steps(std::integral_constant<int, 2>{});
-      else gate_steps(std::integral_constant<int, 3>{});
-      float dot;
-      {
-        float d0, d1;
-        up2(dot2, d0, d1);
-        dot = d0 + d1;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the far-endpoint MMAs of tile it + 2 may start
-      TC3_TRACE(it, 11, tr);
-      // transposed read-back: each store instruction writes 8 rows x 64 B.  Lane (q, cc): float4 cc of row 8 k + q; even cc
-      // from the hi image at the row's slot, odd cc from the lo image at row ^ 4
-      {
-        const int cc = lane & 3, wh = cc & 1, q = lane >> 2;
-        const unsigned char* a0 = (wh ? h_lo : h_hi) + sw128(quad * 32 + (q ^ (wh << 2)), 2 * cq + (cc >> 1));
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(a0 + k * 1024);
-        float* op = out0 + (size_t)q * ldh + 4 * cc;
-        const size_t step = (size_t)ldh * 8;
-        const uint32_t vm = vmask >> q;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t"
-              "setp.ne.u32 p, %0, 0;\n\t"
-              "@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
-              ::"r"((vm >> (8 * k)) & 1u), "l"(op), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w)
-              : "memory");
-          op += step;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // h images read back: the producers may write the own rows of tile it + 2
-      TC3_TRACE(it, 12, tr);
-      // head: a row's four column quarters live in the warps (quad, 0..3); fixed summation order (d0 + d1) + (d2 + d3)
-      if (cq == 1) dot_p1[r] = dot;
-      if (cq == 3) dot_p3[r] = dot;
-      named_bar_sync(bar_id, 128);
-      if (cq == 0) dot += dot_p1[r];
-      if (cq == 2) dot_s2[r] = dot + dot_p3[r];
-      named_bar_sync(bar_id, 128);
-      if (cq == 0 && valid) {
-        const float lg = dot + dot_s2[r] + (first_group ? headb : logit[row_cur]);
-        logit[row_cur] = lg;
-        if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
-      }
-      TC3_TRACE(it, 13, tr);
-      T0 = T1; T1 = T2; srcv = srcv1;
-    }
-#else
     // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
     const int team = warp >> 3, w8 = warp & 7;
     const int quad = w8 & 3, half = w8 >> 2;  // quad == warp % 4: the TMEM lane quadrant this warp may read
@@ -421,74 +245,44 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const int c0 = 32 * half;                 // this warp's columns of every gate: [c0, c0 + 32)
     const int stage = team;
     const bool tr = threadIdx.x == 0 || threadIdx.x == 256;
-    unsigned char* h_hi = sm + OFF_A + stage * A_STAGE + 2 * A_PART;
-    unsigned char* h_lo = h_hi + A_PART;
-    const float* bias = reinterpret_cast<const float*>(sm + OFF_BIAS);
-    const float* headw = reinterpret_cast<const float*>(sm + OFF_HEADW);
-    const float headb = *reinterpret_cast<const float*>(sm + OFF_HEADB);
+    const float headb = c_tc3_expo[0];
     float* dot_part = reinterpret_cast<float*>(sm + (team ? OFF_DOT : OFF_BIAS));
     const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
     const int bar_id = 1 + team * 4 + quad;
-    const uint32_t bar_dfull = sm_u + OFF_DOT + 512 + 8 * (team * 4 + quad);  // + 64: the reverse direction (partials read)
-    const uint32_t bar_tok = sm_u + OFF_DOT + 512;  // experiment (TC3_GATE_TOKEN; not together with TC3_HEAD_MBAR)
     auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
     const int first = blockIdx.x + team * stride, step2 = 2 * stride;
     int4 T0 = ldtab(first), T1 = ldtab(first + step2);
     int srcv = ld_src(T0);
-#ifdef TC3_KS_PIPE
-    int ks = __ldg(det_of_row + T0.x + max(srcv, 0));
-#endif
     uint32_t n = 0;  // tiles this team has done
+    int hb = team;   // own-row buffer of tile it = 2 n + team: it % 3
     for (int tile = first; tile < total; tile += step2, ++n) {
       const uint32_t phase = n & 1u;
+      unsigned char* const h_hi = h_img + hb * H_BUF;
+      unsigned char* const h_lo = h_hi + A_PART;
       const int it = 2 * (int)n + team;
       const size_t row_cur = (size_t)T0.x + T0.y + r;
       const bool valid = T0.z - r > 0 && srcv >= 0;
-#ifndef TC3_KS_PIPE
       const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
-#endif
       const int4 T2 = ldtab(tile + 2 * step2);
       const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the team's next tile
-#ifdef TC3_PREFETCH_P
-      {
-        // the three 128-byte lines of the source's P' row this warp will read (r, z, n halves)
-        const float* q = det_p + (size_t)max(ks, 0) * 192 + c0;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + H));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 2 * H));
-      }
-#endif
-#ifdef TC3_PRELOAD_P
       // the first step's P' terms are fetched before the wait (cold lines: an L2 round trip that would otherwise sit
       // in front of the first gate of the tile); the later steps hit the same three lines in L1
       const float* __restrict__ pp_pre = det_p + (size_t)max(ks, 0) * 192 + c0;
       const ulonglong2 br0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre));
       const ulonglong2 bz0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre + H));
       const ulonglong2 bi0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre + 2 * H));
-#endif
       TC3_TRACE(it, 8, tr);
       mbar_wait(bar_done + 8 * stage, phase, status);
       tc_fence_after();
-#ifdef TC3_GATE_TOKEN
-      // strict alternation of the two teams' gate phases: a team starts its MUFU-heavy gates only when the other team's
-      // previous gates are through (experiment: does sharing the MUFU pipe cost more than waiting for it?)
-      if (team == 1) mbar_wait(bar_tok, phase, status);
-      else if (n > 0) mbar_wait(bar_tok + 8, phase ^ 1u, status);
-#endif
       TC3_TRACE(it, 9, tr);
-#ifdef ABL_PP0
-      const float* __restrict__ pp = det_p + (size_t)(ks == -12345 ? 7 : 0) * 192 + c0;
-#else
       const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
-#endif
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       float* out0 = h_out + (row_cur - lane) * ldh + col + c0;  // first row of this warp's quadrant
       f32x2 dot2 = 0ull;
       auto gate_chunks = [&](auto half_c) {
       constexpr int HALF = decltype(half_c)::value;
-#ifndef TC3_NO_LDTM_PIPE
       // software-pipelined accumulator drain: two sets of 4 columns x 4 gates; the TMEM loads of step s + 2 are issued
       // as soon as step s has consumed its set, so they land during step s + 1 (same 32 accumulator registers)
       uint32_t A[2][16];
@@ -521,15 +315,9 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
           __syncwarp();
         }
         tmem_ld_wait();
-#ifdef TC3_PRELOAD_P
         const ulonglong2 br = s == 0 ? br0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
         const ulonglong2 bz = s == 0 ? bz0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
         const ulonglong2 bi = s == 0 ? bi0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
-#else
-        const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
-        const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
-        const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
-#endif
         const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
         const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
         const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
@@ -549,88 +337,6 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
         else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
       }
-#else
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t ar[8], az[8], an[8], ahn[8];
-#ifndef ABL_NOLDTM
-        tmem_ld8u(t0 + ch * 8, ar);
-        tmem_ld8u(t0 + 64 + ch * 8, az);
-        tmem_ld8u(t0 + 128 + ch * 8, an);
-        tmem_ld8u(t0 + 192 + ch * 8, ahn);
-#else
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { ar[q] = srcv + q; az[q] = srcv ^ q; an[q] = ks + q; ahn[q] = ks ^ q; }
-#endif
-        const int j0 = c0 + ch * 8;
-        // previous state of these 8 columns = hi + lo of the stage's h images.  The two 16-byte slots read here
-        // (this warp's own: nobody else touches the 32 rows x 64 B x 2 images of its quadrant and column half) are
-        // dead afterwards and take the new state: the h images are the transpose buffer, in place
-        const uint32_t off = sw128(r, 4 * half + ch);
-        f32x2 hp[4];
-        {
-#ifndef ABL_NOPREV
-          const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
-          const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
-#else
-          const uint4 vh = make_uint4(srcv, ks, srcv, ks), vl = make_uint4(ks, srcv, ks, srcv);
-#endif
-          const __half2* ph = reinterpret_cast<const __half2*>(&vh);
-          const __half2* pl = reinterpret_cast<const __half2*>(&vl);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
-            hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
-          }
-        }
-        __syncwarp();  // every lane has read its slots of this chunk before a neighbour's new state lands in them
-        tmem_ld_wait();
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          // additive terms of the three input gates: the source's P' row, which already holds
-          // -log2e (P_r + b_ir + b_hr) | -log2e (P_z + b_iz + b_hz) | P_n + b_in
-#ifndef ABL_NOPP
-          const ulonglong2 br = __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
-          const ulonglong2 bz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
-          const ulonglong2 bi = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
-#else
-          const ulonglong2 br = make_ulonglong2(ONE2, NTWO2), bz = make_ulonglong2(NTWO2, ONE2), bi = make_ulonglong2(ONE2, ONE2);
-#endif
-#if defined(TC3_BIAS_SMEM)
-          const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
-          const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
-#elif !defined(ABL_NOBIAS)
-          const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
-          const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
-          const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
-#else
-          const ulonglong2 bh = make_ulonglong2(ONE2, NTWO2), hw = make_ulonglong2(NTWO2, ONE2);
-#endif
-          f32x2 o[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = 4 * v + 2 * e;  // columns j0 + i, j0 + i + 1
-            // r, z = 1 / (1 + 2^(-log2e (acc + P + b)))   (2^x -> inf gives exactly 0, no clamp needed)
-            const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(ar[i], ar[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
-            const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(az[i], az[i + 1]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
-            // n = tanh(u) = 1 - 2 / (1 + 2^(2 log2e u)),  u = i_n + P_n + b_in + r (h_n + b_hn)
-            // u is kept in the accumulators' scale (x 2^k: b_in, b_hn and P_n arrive pre-multiplied), TWOLOG2E2 undoes it
-            const f32x2 u = fma2(rg, add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), add2(pk2u(an[i], an[i + 1]), e ? bi.y : bi.x));
-            const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
-            const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
-            o[e] = ov;
-            dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
-          }
-          // columns j0 .. j0 + 3 go to the row's own slot of the hi image, columns j0 + 4 .. j0 + 7 to the slot of row
-          // r ^ 4 of the lo image (slot index ^ 4: the other half of the bank groups), so that the transposed read-back
-          // below -- eight lanes per row, hi and lo slots alternating -- touches every bank group exactly once per row
-#ifndef ABL_NOTRANS
-          if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
-          else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
-#endif
-        }
-      }
-#endif
       };
       if (half == 0) gate_chunks(std::integral_constant<int, 0>{});
       else gate_chunks(std::integral_constant<int, 1>{});
@@ -643,18 +349,9 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start
-#ifdef TC3_GATE_TOKEN
-      if (lane == 0) mbar_arrive(bar_tok + 8 * team);
-#endif
       TC3_TRACE(it, 11, tr);
-#ifdef TC3_KS_PIPE
-      // the next tile's P' row index: its source row landed during the gates, this lookup lands during the stores, so
-      // the dependent chain source -> detection rank -> P' never sits in front of a tile's first gate
-      const int ks1 = __ldg(det_of_row + T1.x + max(srcv1, 0));
-#endif
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines).  Lane (rr, cc): float4 cc of
       // row rr; even cc from the hi image at the row's slot, odd cc from the lo image at row rr ^ 4
-#ifndef TC3_NO_PRED_STG
       {
         // all eight shared-memory reads first, then eight predicated stores off one running pointer (no branches, no
         // 64-bit multiply per row)
@@ -680,51 +377,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
           op += step;
         }
       }
-#else
-      {
-        const int cc = lane & 7, wh = cc & 1;
-        const unsigned char* img = wh ? h_lo : h_hi;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int rr = 4 * k + (lane >> 3);
-          const int rs = quad * 32 + (wh ? (rr ^ 4) : rr);
-#ifndef ABL_NOTRANS
-          const float4 v = *reinterpret_cast<const float4*>(img + sw128(rs, 4 * half + (cc >> 1)));
-#else
-          const float4 v = make_float4(dot, dot, (float)rs, dot);
-          if (img == nullptr) atomicOr(status, 1);
-#endif
-#ifndef ABL_NOSTG
-          if ((vmask >> rr) & 1u) *reinterpret_cast<float4*>(out0 + (size_t)rr * ldh + 4 * cc) = v;
-#else
-          if (v.x == 123.456f) atomicOr(status, 1);
-#endif
-        }
-      }
-#endif
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_hfree + 8 * stage);  // h images read back: the producers may write the next own rows
+      if (lane == 0) mbar_arrive(bar_hfree + 8 * hb);  // h images read back: the producers may write the next own rows
       TC3_TRACE(it, 12, tr);
       // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
-#ifdef TC3_HEAD_MBAR
-      // hand-over through a pair of mbarriers instead of two named barriers: the upper half publishes its partial sums
-      // and goes on to its next tile at once; it only ever waits for the lower half to have read the PREVIOUS tile's
-      if (half == 1) {
-        mbar_wait(bar_dfull + 64, phase ^ 1u, status);
-        dot_part[r] = dot;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dfull);
-      } else {
-        mbar_wait(bar_dfull, phase, status);
-        if (valid) {
-          const float lg = dot + dot_part[r] + (first_group ? headb : logit[row_cur]);
-          logit[row_cur] = lg;
-          if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dfull + 64);
-      }
-#else
       if (half == 1) dot_part[r] = dot;
       named_bar_sync(bar_id, 64);
       if (half == 0 && valid) {
@@ -733,14 +389,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
       }
       named_bar_sync(bar_id, 64);
-#endif
       TC3_TRACE(it, 13, tr);
       T0 = T1; T1 = T2; srcv = srcv1;
-#ifdef TC3_KS_PIPE
-      ks = ks1;
-#endif
+      hb = hb == 0 ? 2 : hb - 1;  // (hb + 2) % 3
     }
-#endif
   }
 
   tc_fence_before();

@@ -195,20 +195,12 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
-#ifdef ABL_NOMUFU
-  return pk2(a * a, b * b);
-#else
   return pk2(ex2_approx(a), ex2_approx(b));
-#endif
 }
 __device__ __forceinline__ f32x2 rcp_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
-#ifdef ABL_NOMUFU
-  return pk2(a * 0.5f, b * 0.5f);
-#else
   return pk2(rcp_approx(a), rcp_approx(b));
-#endif
 }
 __device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -259,14 +251,13 @@ __device__ __forceinline__ void issue_tile_mma_x_second(uint32_t sm_u, uint32_t 
     for (int j = 0; j < 4; ++j)
       umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, 1);
 }
-// ---- the two halves of the MMA issue, far-endpoint part FIRST (mp_step_tc3.cu, in-place transpose) --------
-// The x images are complete long before the stage's h images may be rewritten (those double as the epilogue's
-// transpose buffer), so the far-endpoint MMAs initialise r | z | i_n as soon as the accumulators are drained and
-// run while the previous tile's stores are still going out; only the own-row half waits for the h images.
-__device__ __forceinline__ void issue_tile_mma_x_first(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags) {
-  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
-  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
+// ---- the two halves of the MMA issue, far-endpoint part FIRST (mp_step_tc3.cu) ---------------------------
+// The x images are complete long before the tile's h images may be written (those double as the epilogue's
+// transpose buffer), so the far-endpoint MMAs initialise r | z | i_n as soon as the accumulators are drained;
+// only the own-row half waits for the h images.  x_u / h_u: shared-memory addresses of [x_hi | x_lo] and
+// [h_hi | h_lo]; d0: first TMEM column of the accumulator stage.
+__device__ __forceinline__ void issue_tile_mma_x_first(uint32_t sm_u, uint32_t d0, uint32_t x_u, uint32_t xflags) {
+  const uint32_t ax[3] = {x_u, x_u + A_PART, x_u};
   const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
   uint32_t acc = 0;
 #pragma unroll
@@ -277,10 +268,8 @@ __device__ __forceinline__ void issue_tile_mma_x_first(uint32_t sm_u, uint32_t t
       acc = 1;
     }
 }
-__device__ __forceinline__ void issue_tile_mma_h_second(uint32_t sm_u, uint32_t tmem_base, int stage) {
-  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
-  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
+__device__ __forceinline__ void issue_tile_mma_h_second(uint32_t sm_u, uint32_t d0, uint32_t h_u) {
+  const uint32_t ah[3] = {h_u, h_u + A_PART, h_u};
   const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
   uint32_t acc_n = 0;
 #pragma unroll
