@@ -101,7 +101,8 @@ __global__ void k_pack_gru_tc(const float* __restrict__ w_ih, const float* __res
     const float w = wscale * (m == 0 ? w_ih[n * ldw + xcol0 + k] : w_hh[n * 64 + k]);
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    const uint32_t off = sw128(n, k >> 3) + (k & 7) * 2;
+    const int nr = m == 0 ? n : (n + 64) % 192;  // W_hh rows in the order n | r | z
+    const uint32_t off = sw128(nr, k >> 3) + (k & 7) * 2;
     *reinterpret_cast<__half*>(img + (m == 0 ? OFF_BX_HI : OFF_BH_HI) + off) = hi;
     *reinterpret_cast<__half*>(img + (m == 0 ? OFF_BX_LO : OFF_BH_LO) + off) = lo;
   }
@@ -287,9 +288,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
       fence_proxy_async();
       __syncwarp();
       TC_TRACE(it, 4, threadIdx.x == 32 * EPI_WARPS);
-      if (lane == 0) {
-        mbar_arrive(bar_full + 8 * stage);
-        if (warp - EPI_WARPS == (it & (PROD_WARPS - 1))) {  // this tile's MMA issuer
+      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+      __syncwarp();
+      if (warp - EPI_WARPS == (it & (PROD_WARPS - 1))) {  // this tile's MMA issuer (warp-uniform test, then one elected lane:
+        if (elect_one()) {                                //  descriptors stay in uniform registers, the MMAs issue back to back)
           mbar_wait(bar_tfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained
           TC_TRACE(it, 5, true);
           mbar_wait(bar_full + 8 * stage, phase, status);        // every producer warp has landed its rows

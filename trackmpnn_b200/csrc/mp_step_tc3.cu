@@ -114,6 +114,12 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int stride = gridDim.x;
+  // the own-row MMAs only ever accumulate: the h_n columns of both accumulator stages start at zero (each epilogue
+  // warp owns the 32 lanes x 32 columns it will later drain and re-zero)
+  if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 32 * ((warp & 7) >> 2)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   // tiles past the end repeat the last one (their loads are simply unused)
   auto ldtab = [&](int tile) { return __ldg(tab + min(tile, total - 1)); };
 
@@ -288,10 +294,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       uint32_t A[2][16];
       auto ldstep = [&](int s, uint32_t* a) {
         const uint32_t cb = t0 + (uint32_t)((s >> 1) * 8 + (s & 1) * 4);
-        tmem_ld4u(cb, a);
-        tmem_ld4u(cb + 64, a + 4);
-        tmem_ld4u(cb + 128, a + 8);
-        tmem_ld4u(cb + 192, a + 12);
+        tmem_ld4u(cb + 64, a);        // r
+        tmem_ld4u(cb + 128, a + 4);   // z
+        tmem_ld4u(cb + 192, a + 8);   // i_n
+        tmem_ld4u(cb, a + 12);        // h_n
       };
       ldstep(0, A[0]);
       ldstep(1, A[1]);
@@ -346,6 +352,8 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         up2(dot2, d0, d1);
         dot = d0 + d1;
       }
+      // accumulator stage drained: re-zero this warp's h_n columns for the accumulate-only own-row MMAs
+      tmem_zero32(t0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start

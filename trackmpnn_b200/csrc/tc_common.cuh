@@ -12,6 +12,7 @@ constexpr int H = TMPNN_HIDDEN;
 constexpr int TCM = 128;            // rows per tile == UMMA M
 constexpr int B_BYTES = 192 * 128;  // one [192 x 64] fp16 weight image
 constexpr int OFF_BX_HI = 0, OFF_BX_LO = B_BYTES, OFF_BH_HI = 2 * B_BYTES, OFF_BH_LO = 3 * B_BYTES;
+// row order of the images: W_ih r | z | n, W_hh n | r | z (so that one N = 192 instruction covers h_n | r | z, see mp_step_tc3.cu)
 constexpr int OFF_BIAS = 4 * B_BYTES;            // 4 x 64 floats: -log2e (b_ir+b_hr), -log2e (b_iz+b_hz), b_in, b_hn
 constexpr int OFF_HEADW = OFF_BIAS + 1024;       // 64 floats
 constexpr int OFF_HEADB = OFF_HEADW + 256;       // 1 float (+ pad)
@@ -221,36 +222,6 @@ __device__ __forceinline__ void seek_seq(const int32_t* __restrict__ tile_ptr, i
   while (seq + 1 < num_seqs && __ldg(tile_ptr + seq + 1) <= tile) ++seq;
 }
 
-// ---- the two halves of the MMA issue, h part FIRST (mp_step_tc3.cu) -----------------------------------
-// own-row part: columns [0,128) = r | z and [192,256) = h_n are (re)initialised here
-__device__ __forceinline__ void issue_tile_mma_h_first(uint32_t sm_u, uint32_t tmem_base, int stage) {
-  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
-  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-  const uint32_t ah[3] = {a_u + 2 * A_PART, a_u + 3 * A_PART, a_u + 2 * A_PART};
-  const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
-  uint32_t acc = 0;
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), acc);
-      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc);
-      acc = 1;
-    }
-}
-// far-endpoint part: accumulates into r | z | i_n; the i_n columns [128,192) were zeroed by the epilogue
-// (tcgen05.st) when it drained the stage, so this is 12 instructions on the critical path instead of 24
-__device__ __forceinline__ void issue_tile_mma_x_second(uint32_t sm_u, uint32_t tmem_base, int stage, uint32_t xflags) {
-  const uint32_t a_u = sm_u + OFF_A + stage * A_STAGE;
-  const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
-  const uint32_t ax[3] = {a_u, a_u + A_PART, a_u};
-  const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, 1);
-}
 // ---- the two halves of the MMA issue, far-endpoint part FIRST (mp_step_tc3.cu) ---------------------------
 // The x images are complete long before the tile's h images may be written (those double as the epilogue's
 // transpose buffer), so the far-endpoint MMAs initialise r | z | i_n as soon as the accumulators are drained;
@@ -264,22 +235,21 @@ __device__ __forceinline__ void issue_tile_mma_x_first(uint32_t sm_u, uint32_t d
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, acc);
+      umma_f16(d0 + 64, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, acc);
       acc = 1;
     }
 }
+// own-row part as ONE N = 192 instruction per K step: the W_hh image holds its rows in the order n | r | z (k_pack_gru_tc),
+// the accumulator stage is laid out h_n | r | z | i_n, so [0,192) takes the own-row product and [64,256) the far-endpoint
+// product.  Always accumulates: r | z continue the far-endpoint sums, the h_n columns were zeroed by the epilogue when it
+// drained the stage.  12 instructions and 120 KB of operand reads per tile instead of 24 and 168 KB.
 __device__ __forceinline__ void issue_tile_mma_h_second(uint32_t sm_u, uint32_t d0, uint32_t h_u) {
   const uint32_t ah[3] = {h_u, h_u + A_PART, h_u};
   const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
-  uint32_t acc_n = 0;
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
-      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
-      acc_n = 1;
-    }
+    for (int j = 0; j < 4; ++j) umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(192), 1);
 }
 // 32 zero columns for this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
@@ -315,8 +285,8 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t sm_u, uint32_t tmem_base
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(128), 1);
-      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 128 * 128 + 32 * j), umma_idesc(64), acc_n);
+      umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 64 * 128 + 32 * j), umma_idesc(128), 1);  // rows r | z
+      umma_f16(d0 + 192, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(64), acc_n);        // rows n
       acc_n = 1;
     }
 }

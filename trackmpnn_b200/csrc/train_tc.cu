@@ -134,7 +134,7 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
 
   if (warp == BW_EPI + BW_PROD) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: descriptors stay in uniform registers, the MMAs issue back to back
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += stride, ++it) {
         const int stage = it & 1;
