@@ -547,7 +547,8 @@ def rooflines(a, eng, r, ms):
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     tk = {'auto': 'pre'}.get(eng.tensor_kernel, eng.tensor_kernel)
     kname = ({'pre': 'k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied by cp.async, '
-                     'tcgen05.mma kind::f16 with a 3-term fp16 split, TMEM accumulators, dedicated MMA issuer warp, two epilogue teams)',
+                     '24 tcgen05.mma kind::f16 per tile (3-term fp16 split, N = 192), TMEM accumulators, elect.sync MMA issuer warp, two '
+                     'epilogue teams, own-row images triple-buffered and reused in place as the transpose buffer)',
               'gather': 'k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'}[tk]
              if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
     tr_e, src_e = measured_traffic('k_mp_edge_tc3') if eng.tensor else (None, None)
