@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--win', type=int, default=5)
     ap.add_argument('--no-cuda-graph', action='store_true')
     ap.add_argument('--no-deferred', action='store_true', help='move the hidden states in every window slide (A/B switch)')
+    ap.add_argument('--list-aggregation', action='store_true', help='aggregate through the incidence lists (A/B switch)')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU-baseline sample (0 = auto)')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
@@ -410,7 +411,8 @@ def run_c4_leg(a, dev):
     torch.manual_seed(5)
     model = TrackMPNN('2d', synth.num_categories(b.dataset), 64, 0, 'diff').to(dev).eval()
     seqs = make_sequences(b, 7000, b.seqs_per_gpu)
-    eng = TrackEngine(model, seqs, cur_win_size=b.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph)
+    eng = TrackEngine(model, seqs, cur_win_size=b.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
+                      block_aggregation=not a.list_aggregation)
     for _ in range(2):
         eng.run()
     eng.results()
@@ -552,7 +554,13 @@ def rooflines(a, eng, r, ms):
               'gather': 'k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'}[tk]
              if eng.tensor else 'k_mp_edge<64> (fused gather-diff + GRU + head, fp32 FMA path)')
     tr_e, src_e = measured_traffic('k_mp_edge_tc3') if eng.tensor else (None, None)
-    tr_a, src_a = measured_traffic('k_aggregate_dets')
+    blocks = getattr(eng, '_agg_blocks', None) is not None
+    if blocks:   # the block pass and the per-detection combine are timed (and counted) together
+        tr_a, src_a = measured_traffic('k_aggregate_blocks')
+        tr_c, _ = measured_traffic('k_aggregate_blocks_combine')
+        tr_a = tr_a + tr_c if tr_a is not None and tr_c is not None else None
+    else:
+        tr_a, src_a = measured_traffic('k_aggregate_dets')
     traffic = tr_e * k_edges / n_l if tr_e else None
     roof = {'kernel': kname, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
             'frac_algorithmic': achieved / hbm_peak,
@@ -569,7 +577,9 @@ def rooflines(a, eng, r, ms):
     a_ms = sum(p[3].elapsed_time(p[4]) for p in prof)
     agg_bytes = 256.0 * (k_edges - fresh) + 256.0 * r['dets']
     tr_agg = tr_a * k_edges / n_l if tr_a else None
-    agg = {'kernel': 'k_aggregate_dets (CSR segmented signed sum of incident association rows, CTA per detection)',
+    agg = {'kernel': ('k_aggregate_blocks + k_aggregate_blocks_combine (one pass over every dense edge block: row sums of 32-source '
+                      'stripes + per-stripe column partials, every association row read once; blocks appended this frame skipped)'
+                      if blocks else 'k_aggregate_dets (CSR segmented signed sum of incident association rows, CTA per detection)'),
            'bound': 'hbm', 'achieved': agg_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0, 'peak': hbm_peak, 'unit': 'GB/s',
            'frac': agg_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak if a_ms > 0 else 0.0,
            'frac_dram': (tr_agg / (a_ms / n_l * 1e-3) / 1e9 / hbm_peak) if tr_agg and a_ms > 0 else None,
@@ -680,7 +690,7 @@ def main():
     # ---- weak-scaling leg (the headline line): --seqs-per-gpu sequences on EVERY rank ------------------------------------
     seqs = make_sequences(a, 5 + rank * a.seqs_per_gpu, a.seqs_per_gpu)
     eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
-                      deferred_compaction=not a.no_deferred)
+                      deferred_compaction=not a.no_deferred, block_aggregation=not a.list_aggregation)
     for _ in range(max(a.warmup, 1)):
         eng.run()
     eng.results()

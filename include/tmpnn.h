@@ -170,6 +170,19 @@ int tmpnn_index_build_structured(const tmpnn_graph *g, const tmpnn_index *ix, co
 int tmpnn_aggregate_dets(const tmpnn_graph *g, const tmpnn_index *ix, const float *h, int ldh, int col,
                          float *agg, void *stream);
 
+/* tmpnn_aggregate_dets for a graph indexed by tmpnn_index_build_structured (index_scratch2 = that call's scratch2, which
+ * holds the slab's segment tables and run offsets): the window graph is a chain of dense [sources x detections] edge
+ * blocks, so one pass over each block yields the row sums (every source's future run) and per-stripe column partials
+ * (every detection's past edges), and every association row is read exactly once -- the incidence-list form requests each
+ * row twice.  Blocks appended this frame (deferred compaction: rows aliasing the slab's zero row) are skipped.  Same sums up
+ * to fp32 re-association, bit-reproducible.  Per slab the scratch holds cap_runs run sums (>= detections x blocks a
+ * detection can be a source of, i.e. window size) and cap_cpart column partials (>= cap_rows / 32 + detections) of 64
+ * floats; exceeding either sets TMPNN_FLAG_INC_CAPACITY.  Replaces the sparse product edge_adj_norm . h of
+ * models/layers.py:103 like tmpnn_aggregate_dets. */
+size_t tmpnn_aggregate_blocks_scratch_bytes(int num_seqs, int cap_runs, int cap_cpart);
+int tmpnn_aggregate_dets_blocks(const tmpnn_graph *g, const tmpnn_index *ix, const void *index_scratch2, const float *h,
+                                int ldh, int col, float *agg, void *scratch, int cap_runs, int cap_cpart, void *stream);
+
 /* node_support for every edge row (layers.py:91-95): diff -> h[src]-h[dst] (64 wide),
  * concat -> [h[src] | h[dst]] (128 wide); rows of support that belong to detections are zero.
  * Stand-alone form of what tmpnn_mp_step_fwd fuses; kept for the roofline study. */

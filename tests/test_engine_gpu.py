@@ -147,6 +147,48 @@ def test_structured_index_equals_general_index(ret):
         assert sa[-1] == 2 * int(a.n_edges.item())
 
 
+@pytest.mark.parametrize('deferred', [False, True])
+@pytest.mark.parametrize('cfg', [dict(win=5, ret=1, seqs=[(30, 12, 6), (49, 14, 9), (34, 10, 5), (52, 11, 7), (54, 16, 4)], gap=(49, 52)),
+                                 dict(win=20, ret=2, stock=True, seqs=[(803, 30, 6), (804, 27, 5), (805, 24, 7)], gap=()),
+                                 dict(win=8, ret=0, stock=True, seqs=[(811, 14, 40), (812, 12, 75)], gap=())])
+def test_block_aggregation_equals_incidence_list_aggregation(cfg, deferred):
+    """tmpnn_aggregate_dets_blocks (one pass over every dense edge block: row sums + per-stripe column partials, freshly
+    appended blocks skipped) against tmpnn_aggregate_dets (incidence lists) on every step of a run: same sums up to fp32
+    re-association (models/layers.py:103).  Blocks wider than one 64-column chunk and longer than one 32-source stripe
+    are covered by the 40 / 75 detections-per-frame streams."""
+    from trackmpnn_b200.engine import TrackEngine
+    dev = torch.device('cuda:0')
+    stock = cfg.get('stock', False)
+    model = _model(dev, scale=1.0 if stock else 20.0, edge_bias=None if stock else 0.0)
+    seqs = []
+    for sd, T, D in cfg['seqs']:
+        ts = (list(range(0, 4)) + list(range(4 + cfg['win'] + 1, 4 + cfg['win'] + 1 + T))) if sd in cfg['gap'] else None
+        X, y = synth.make_sequence(sd, T, D, 'kitti', timestamps=ts)
+        seqs.append((X[0], y[0]))
+    eng = TrackEngine(model, seqs, cur_win_size=cfg['win'], ret_win_size=cfg['ret'], use_cuda_graph=False,
+                      deferred_compaction=deferred)
+    assert eng._agg_blocks is not None
+    eng.check_aggregation = []
+    eng.run()
+    eng.results()
+    assert len(eng.check_aggregation) > 8
+    assert max(nd for nd, _, _ in eng.check_aggregation) > 20
+    assert max(ref for _, _, ref in eng.check_aggregation) > 1e-3
+    for nd, diff, ref in eng.check_aggregation:
+        assert diff <= 2e-6 * max(1.0, ref), (nd, diff, ref)
+    eng.check_aggregation = None
+    # and the engine's tracks do not depend on the form of the aggregation (decisions margin-guarded by the seeds)
+    ref_eng = TrackEngine(model, seqs, cur_win_size=cfg['win'], ret_win_size=cfg['ret'], use_cuda_graph=False,
+                          deferred_compaction=deferred, block_aggregation=False)
+    assert ref_eng._agg_blocks is None
+    a, sa = eng.run().results()
+    b, sb = ref_eng.run().results()
+    assert sa == sb
+    if stock:
+        for x, y_ in zip(a, b):
+            np.testing.assert_array_equal(x, y_)
+
+
 @pytest.mark.parametrize('kernel', ['fma', 'gather', 'pre'])
 def test_engine_state_at_workload_size(kernel):
     """BDD-shaped sequences at the bench workload's size (~80 detections / frame, ~60 k association rows per

@@ -86,6 +86,8 @@ _PROTOS = {
     'tmpnn_index_structured_scratch_bytes': ([_I, _I], C.c_size_t),
     'tmpnn_index_build_structured': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _VP], _I),
     'tmpnn_aggregate_dets': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP], _I),
+    'tmpnn_aggregate_blocks_scratch_bytes': ([_I, _I, _I], C.c_size_t),
+    'tmpnn_aggregate_dets_blocks': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _VP, _VP, _I, _I, _VP], _I),
     'tmpnn_gat_aggregate_dets': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_gat_aggregate_dets_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _I, _I, _VP, _VP, _I, _I, _VP, C.c_float] + [_VP] * 6, _I),
     'tmpnn_gat_bwd': ([C.POINTER(Graph), C.POINTER(Index), _I, _VP, _I, _I, _VP, _VP, _I, _VP, C.c_float] + [_VP] * 13, _I),
@@ -198,7 +200,7 @@ _LAUNCHES = [0]
 # kernels launched per C-ABI call (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
-    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 12, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
+    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 11, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_dets_blocks': 3, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1, 'tmpnn_mp_edge_fwd_on_flag': 1, 'tmpnn_graph_force_det_scores': 1,
@@ -262,3 +264,35 @@ def call(name, *args):
             torch.cuda.nvtx.range_pop()
         return
     check(getattr(lib(), name)(*args))
+
+
+class ZeroArena:
+    """One pre-allocated float32 buffer that the batched trainer zeroes ONCE per optimizer step and the step's small
+    zero-initialised scratch tensors (loss accumulators, per-segment sums, the CE gradient) are carved from, instead of one
+    fill kernel each (~40 per step).  ``zeros()`` falls back to ``torch.zeros`` when no arena is active or it is full."""
+    active = None
+
+    def __init__(self, device, nfloats=1 << 22):
+        self.buf = torch.zeros(nfloats, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def begin(self):
+        self.buf.zero_()
+        self.off = 0
+        ZeroArena.active = self
+
+    @staticmethod
+    def end():
+        ZeroArena.active = None
+
+
+def zeros(n, device):
+    """n zero floats on ``device``: a 16-byte aligned slice of the active ZeroArena, else a fresh tensor."""
+    a = ZeroArena.active
+    n = int(n)
+    if a is not None and a.buf.device == torch.device(device) and a.off + n <= a.buf.numel():
+        out = a.buf[a.off:a.off + n]
+        a.off += (n + 3) // 4 * 4
+        return out
+    return torch.zeros(n, dtype=torch.float32, device=device)
+

@@ -28,6 +28,17 @@ int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
     if (!(cond)) return tmpnn_set_error(TMPNN_E_BADARG, "%s: %s", __func__, msg); \
   } while (0)
 
+// Segment table of one slab, written by tmpnn_index_build_structured at the start of its scratch2 (graph_index.cu) and
+// read by the block-structured aggregation (mp_step.cu): the window graph as a chain [dets][edges][dets]...
+constexpr int MAXSEG = 128;  // segments per slab (2 per frame in the window)
+constexpr int MAXE = 64;     // edge segments per slab
+struct SlabSegs {            // per slab, in global scratch
+  int32_t nedge;             // number of edge segments (<= MAXE)
+  int32_t nseg;              // number of segments
+  int32_t start[MAXSEG + 1]; // slab-local first row of segment q; start[nseg] = n_rows
+  int32_t eord[MAXSEG];      // ordinal among the edge segments, -1 for detection segments
+};
+
 static inline int tmpnn_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float tmpnn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }

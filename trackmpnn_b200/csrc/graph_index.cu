@@ -216,15 +216,8 @@ __global__ void __launch_bounds__(128) k_sort_segments(const int32_t* __restrict
 // d0 + j are e0 + a Nt + j (a ascending), the future edges of a source are its runs in ascending
 // segment order.  The builder finds the segment boundaries from ts, derives the counts, scans them and
 // writes inc with coalesced stores; it verifies the structure as it goes (TMPNN_FLAG_UNSTRUCTURED).
-constexpr int MAXSEG = 128;  // segments per slab (2 per frame in the window)
-constexpr int MAXE = 64;     // edge segments per slab
-
-struct SlabSegs {            // per slab, in global scratch
-  int32_t nedge;             // number of edge segments (<= MAXE)
-  int32_t nseg;              // number of segments
-  int32_t start[MAXSEG + 1]; // slab-local first row of segment q; start[nseg] = n_rows
-  int32_t eord[MAXSEG];      // ordinal among the edge segments, -1 for detection segments
-};
+// MAXSEG, MAXE and SlabSegs (the per-slab segment table this builder leaves in scratch2) live in common.cuh: the
+// block-structured aggregation (mp_step.cu) reads the same table
 
 // Segment boundaries: a boundary sits in front of row i when i is the first row or the timestamp changes (edge rows all
 // carry -1).  Found by a grid over the rows (a window of W = 20 frames x 200 detections has millions of rows per
@@ -245,7 +238,8 @@ __global__ void __launch_bounds__(256) k_segment_bounds(const int32_t* __restric
 }
 __global__ void __launch_bounds__(32) k_block_segments(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
                                                        const int32_t* __restrict__ ts, int cap_rows, int32_t* __restrict__ bnd_all,
-                                                       SlabSegs* __restrict__ segs, int32_t* __restrict__ status) {
+                                                       SlabSegs* __restrict__ segs, int32_t* __restrict__ slab_nd,
+                                                       int32_t* __restrict__ status) {
   const int s = blockIdx.x;
   if (threadIdx.x != 0) return;
   const int n = (active && !active[s]) ? 0 : n_rows[s];
@@ -272,6 +266,79 @@ __global__ void __launch_bounds__(32) k_block_segments(const int32_t* __restrict
   o.nedge = ne;
   o.nseg = m;
   o.start[m] = n;
+  // detection rows of the slab = total length of its detection segments (the structured builder derives the detection
+  // list from the segments instead of scanning every row's timestamp twice)
+  int nd = 0;
+  for (int q = 0; q < m; ++q)
+    if (o.eord[q] < 0) nd += o.start[q + 1] - o.start[q];
+  slab_nd[s] = nd;
+}
+
+// single CTA: per-slab detection ranges, tile tables, totals (the structured counterpart of k_scan_det_blocks)
+__global__ void __launch_bounds__(1024) k_scan_slabs(const int32_t* __restrict__ n_rows, const int32_t* __restrict__ active,
+                                                     int num_seqs, const int32_t* __restrict__ slab_nd,
+                                                     int32_t* __restrict__ seq_det_ptr, int32_t* __restrict__ tile_ptr,
+                                                     int32_t* __restrict__ tile128_ptr, int32_t* __restrict__ n_dets,
+                                                     int32_t* __restrict__ n_edges, int cap_dets, int cap_inc,
+                                                     int32_t* __restrict__ status) {
+  __shared__ int sm[33];
+  int dcarry = 0, tcarry = 0, rcarry = 0, t128carry = 0;
+  for (int s0 = 0; s0 < num_seqs; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    const int n = (s < num_seqs && !(active && !active[s])) ? n_rows[s] : 0;
+    int total;
+    int ex = block_exclusive_scan(s < num_seqs ? slab_nd[s] : 0, sm, &total);
+    if (s < num_seqs) seq_det_ptr[s] = dcarry + ex;
+    dcarry += total;
+    ex = block_exclusive_scan((n + TMPNN_TILE_ROWS - 1) / TMPNN_TILE_ROWS, sm, &total);
+    if (s < num_seqs) tile_ptr[s] = tcarry + ex;
+    tcarry += total;
+    if (tile128_ptr) {
+      ex = block_exclusive_scan((n + 127) / 128, sm, &total);
+      if (s < num_seqs) tile128_ptr[s] = t128carry + ex;
+      t128carry += total;
+    }
+    block_exclusive_scan(n, sm, &total);
+    rcarry += total;
+  }
+  if (threadIdx.x == 0) {
+    const int nd = dcarry;
+    seq_det_ptr[num_seqs] = nd;
+    tile_ptr[num_seqs] = tcarry;
+    if (tile128_ptr) tile128_ptr[num_seqs] = t128carry;
+    const int ne = rcarry - nd;
+    int flags = 0;
+    if (nd > cap_dets) flags |= TMPNN_FLAG_DET_CAPACITY;
+    if (2 * ne > cap_inc) flags |= TMPNN_FLAG_INC_CAPACITY;
+    if (flags) atomicOr(status, flags);
+    *n_dets = flags ? 0 : nd;   // on overflow the consumers see an empty index instead of writing out of bounds
+    *n_edges = ne;
+  }
+}
+
+// detection list from the detection segments: only the detection rows are touched (det_of_row of association rows is
+// never read: every consumer indexes it with an endpoint row)
+__global__ void __launch_bounds__(256) k_write_dets_segs(const SlabSegs* __restrict__ segs, int cap_rows,
+                                                         const int32_t* __restrict__ seq_det_ptr,
+                                                         const int32_t* __restrict__ n_dets, int32_t* __restrict__ det_rows,
+                                                         int32_t* __restrict__ det_of_row, int32_t* __restrict__ cnt) {
+  if (*n_dets == 0) return;  // capacity exceeded (or no detections at all)
+  const int s = blockIdx.y;
+  const SlabSegs& sg = segs[s];
+  const size_t base = (size_t)s * cap_rows;
+  int k0 = seq_det_ptr[s];
+  for (int q = 0; q < sg.nseg; ++q) {
+    if (sg.eord[q] >= 0) continue;
+    const int r0 = sg.start[q], len = sg.start[q + 1] - r0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+      const int k = k0 + i;
+      det_rows[k] = (int32_t)(base + r0 + i);
+      det_of_row[base + r0 + i] = k;
+      cnt[2 * k] = 0;
+      cnt[2 * k + 1] = 0;
+    }
+    k0 += len;
+  }
 }
 
 // counts: cnt[2k] = past edges, futlen[k][eord] = run length of detection k in edge segment eord
@@ -410,19 +477,18 @@ extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_in
   int32_t* bnd = futlen + (size_t)ix->cap_dets * MAXE;  // per-slab boundary lists; the counts start at zero and are
                                                         // re-zeroed by k_block_segments (SlabIndex allocates zeros)
 
-  dim3 grid_rows(nblk, S);
-  k_count_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk);
-  TMPNN_LAUNCH_CHECK();
-  k_scan_det_blocks<<<1, 1024, 0, st>>>(g->n_rows, active, S, nblk, blk, ix->seq_det_ptr, ix->tile_ptr, ix->tile128_ptr, ix->n_dets,
-                                        ix->n_edges, ix->cap_dets, ix->cap_inc, g->status);
-  TMPNN_LAUNCH_CHECK();
-  k_write_dets<<<grid_rows, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, nblk, blk, ix->n_dets, ix->det_rows,
-                                          ix->det_of_row, cnt);
-  TMPNN_LAUNCH_CHECK();
+  // segments first; the detection list, the per-slab ranges and the tile tables follow from them (the general builder scans
+  // every row's timestamp twice for the same list: ~100 us per frame on the 16 M rows of configs[2])
   dim3 grid_b(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 16), 256)), S);
   k_segment_bounds<<<grid_b, 256, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, bnd);
   TMPNN_LAUNCH_CHECK();
-  k_block_segments<<<S, 32, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, bnd, segs, g->status);
+  k_block_segments<<<S, 32, 0, st>>>(g->n_rows, active, g->ts, g->cap_rows, bnd, segs, blk, g->status);
+  TMPNN_LAUNCH_CHECK();
+  k_scan_slabs<<<1, 1024, 0, st>>>(g->n_rows, active, S, blk, ix->seq_det_ptr, ix->tile_ptr, ix->tile128_ptr, ix->n_dets,
+                                   ix->n_edges, ix->cap_dets, ix->cap_inc, g->status);
+  TMPNN_LAUNCH_CHECK();
+  k_write_dets_segs<<<dim3(max(1, min(tmpnn_div_up(ix->cap_dets, 256 * max(S, 1)), 16)), S), 256, 0, st>>>(
+      segs, g->cap_rows, ix->seq_det_ptr, ix->n_dets, ix->det_rows, ix->det_of_row, cnt);
   TMPNN_LAUNCH_CHECK();
   TMPNN_CUDA_TRY(cudaMemsetAsync(futlen, 0, (size_t)ix->cap_dets * MAXE * sizeof(int32_t), st));
   dim3 grid_d(4, S);

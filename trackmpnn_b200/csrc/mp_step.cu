@@ -282,6 +282,226 @@ extern "C" int tmpnn_aggregate_dets(const tmpnn_graph* g, const tmpnn_index* ix,
   return TMPNN_OK;
 }
 
+// ---- block-structured K1-det: every association row read ONCE ------------------------------------------------
+// The engine's window graphs are chains of dense edge blocks (graph_index.cu, tmpnn_index_build_structured): block b of a
+// slab holds rows e0 + a nt + j joining source a to detection j of the following detection segment.  k_aggregate_dets
+// walks the incidence lists, so every association row is requested twice (once by each endpoint; the second request only
+// hits L2 while the detections in flight stay within a few sequences) plus 8 B of incidence entries per row.  Here a CTA
+// takes a stripe of AB_SA sources x all nt columns of one block and forms, in one pass, the stripe's complete row sums
+// (the future-run sum of each source) and its column partials (the past sum of each detection over the stripe's
+// sources); k_aggregate_blocks_combine then adds, per detection and in a fixed order, its column partials (-) and its run
+// sums (+).  A block appended this frame is all zero (its rows alias the slab's zero row) and is skipped outright.
+// Same sums as k_aggregate_dets up to fp32 re-association; bit-reproducible (no atomics, fixed orders, the partition into
+// stripes depends on the slab's own structure only).
+constexpr int AB_SA = 32;  // sources per stripe
+struct AggBlock { int32_t e0, nt, A, rbase, cbase, tile0, fresh, nst; };
+struct AggSlab {
+  int32_t nblk, ntiles, pad[6];
+  AggBlock b[MAXE];  // by edge-segment ordinal
+};
+
+__global__ void __launch_bounds__(128) k_agg_block_table(const SlabSegs* __restrict__ segs, int num_seqs, int cap_rows,
+                                                         const int32_t* __restrict__ phys, int cap_runs, int cap_cpart,
+                                                         AggSlab* __restrict__ tab, int32_t* __restrict__ status) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num_seqs) return;
+  const SlabSegs& sg = segs[s];
+  AggSlab& o = tab[s];
+  const size_t base = (size_t)s * cap_rows;
+  const int32_t zrow = (int32_t)(base + cap_rows - 1);
+  int runs = 0, cp = 0, tiles = 0;
+  for (int q = 0; q < sg.nseg; ++q) {
+    const int b = sg.eord[q];
+    if (b < 0) continue;
+    const int e0 = sg.start[q], d0 = sg.start[q + 1], d1 = q + 2 <= sg.nseg ? sg.start[q + 2] : d0;
+    const int nt = d1 - d0;
+    const bool ok = nt > 0 && q + 1 < sg.nseg && sg.eord[q + 1] < 0 && (d0 - e0) % nt == 0;  // else TMPNN_FLAG_UNSTRUCTURED is set
+    int A = ok ? (d0 - e0) / nt : 0;
+    const int fresh = (phys && A > 0 && phys[base + e0] == zrow) ? 1 : 0;
+    int nst = fresh ? 0 : (A + AB_SA - 1) / AB_SA;
+    if (!fresh && ((long long)runs + A > cap_runs || (long long)cp + (long long)nst * nt > cap_cpart)) {
+      atomicOr(status, TMPNN_FLAG_INC_CAPACITY);
+      A = 0; nst = 0;
+    }
+    AggBlock B;
+    B.e0 = e0; B.nt = max(nt, 1); B.A = A; B.rbase = runs; B.cbase = cp; B.tile0 = tiles; B.fresh = fresh; B.nst = nst;
+    o.b[b] = B;
+    if (!fresh) { runs += A; cp += nst * nt; }
+    tiles += nst;
+  }
+  o.nblk = sg.nedge;
+  o.ntiles = tiles;
+}
+
+__global__ void __launch_bounds__(128) k_aggregate_blocks(const AggSlab* __restrict__ tab, const float* __restrict__ h, int ldh,
+                                                          int col, int cap_rows, const int32_t* __restrict__ phys,
+                                                          float* __restrict__ rsum, int cap_runs, float* __restrict__ cpart,
+                                                          int cap_cpart) {
+  __shared__ float4 rowpart[AB_SA][4][16];  // [source of the stripe][warp][float4 of the row]: 32 KB
+  __shared__ int32_t idx[AB_SA][64];        // physical rows of the stripe x column chunk: 8 KB
+  const int s = blockIdx.y;
+  const AggSlab& sl = tab[s];
+  const int ntiles = sl.ntiles;
+  if ((int)blockIdx.x >= ntiles) return;
+  const size_t base = (size_t)s * cap_rows;
+  const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* __restrict__ rs = rsum + (size_t)s * cap_runs * H;
+  float* __restrict__ cpb = cpart + (size_t)s * cap_cpart * H;
+  const float* __restrict__ hc = h + col + 4 * l16;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int b = 0;
+    while (b + 1 < sl.nblk && t >= sl.b[b].tile0 + sl.b[b].nst) ++b;
+    const AggBlock B = sl.b[b];
+    const int i = t - B.tile0, a0 = i * AB_SA, na = min(AB_SA, B.A - a0), nt = B.nt;
+    // column chunks of equal width (<= 64, a multiple of 8): half-warp hw owns columns c0 + hw + 8 u, u < cw / 8, so
+    // consecutive half-warps read consecutive rows and every chunk keeps all half-warps equally busy
+    const int nch = (nt + 63) >> 6;
+    const int cw = 8 * ((nt + 8 * nch - 1) / (8 * nch));
+    for (int c0 = 0; c0 < nt; c0 += cw) {
+      // the chunk's physical rows first (coalesced; deferred compaction scatters them), so that the state loads below
+      // are independent of each other
+      __syncthreads();
+      for (int o = threadIdx.x; o < na * cw; o += 128) {
+        const int al = o / cw, jj = o - al * cw, j = c0 + jj;
+        const size_t r = base + B.e0 + (size_t)(a0 + al) * nt + j;
+        idx[al][jj] = j < nt ? (phys ? __ldg(phys + r) : (int32_t)r) : -1;
+      }
+      __syncthreads();
+      float4 ca[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ca[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int nu = cw >> 3;
+      for (int al = 0; al < na; al += 2) {
+        // two sources per pass: up to 16 independent 16-byte loads in flight per thread
+        float4 v[2][8];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int pr = (u < nu && al + w < na) ? idx[al + w][hw + 8 * u] : -1;
+            v[w][u] = pr >= 0 ? ldg4(hc + (size_t)pr * ldh) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          float4 rp = v[w][0];
+          ca[0].x += v[w][0].x; ca[0].y += v[w][0].y; ca[0].z += v[w][0].z; ca[0].w += v[w][0].w;
+#pragma unroll
+          for (int u = 1; u < 8; ++u) {
+            rp.x += v[w][u].x; rp.y += v[w][u].y; rp.z += v[w][u].z; rp.w += v[w][u].w;
+            ca[u].x += v[w][u].x; ca[u].y += v[w][u].y; ca[u].z += v[w][u].z; ca[u].w += v[w][u].w;
+          }
+          // the warp's two half-warps hold different columns of the same source row
+          rp.x += __shfl_xor_sync(0xffffffffu, rp.x, 16);
+          rp.y += __shfl_xor_sync(0xffffffffu, rp.y, 16);
+          rp.z += __shfl_xor_sync(0xffffffffu, rp.z, 16);
+          rp.w += __shfl_xor_sync(0xffffffffu, rp.w, 16);
+          if (lane < 16 && al + w < na) {
+            float4* p = &rowpart[al + w][warp][l16];
+            if (c0 != 0) {
+              const float4 o = *p;
+              rp.x += o.x; rp.y += o.y; rp.z += o.z; rp.w += o.w;
+            }
+            *p = rp;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = c0 + hw + 8 * u;
+        if (u < nu && j < nt) *reinterpret_cast<float4*>(cpb + ((size_t)B.cbase + (size_t)i * nt + j) * H + 4 * l16) = ca[u];
+      }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < na * 16; o += 128) {
+      const int al = o >> 4, l = o & 15;
+      float4 t4 = rowpart[al][0][l];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        const float4 u4 = rowpart[al][w][l];
+        t4.x += u4.x; t4.y += u4.y; t4.z += u4.z; t4.w += u4.w;
+      }
+      *reinterpret_cast<float4*>(rs + ((size_t)B.rbase + a0 + al) * H + 4 * l) = t4;
+    }
+  }
+}
+
+// half-warp per detection: - column partials of the block in front of its segment, + run sums of its future runs
+__global__ void __launch_bounds__(256) k_aggregate_blocks_combine(const SlabSegs* __restrict__ segs, const AggSlab* __restrict__ tab,
+                                                                  const int32_t* __restrict__ n_dets,
+                                                                  const int32_t* __restrict__ det_rows,
+                                                                  const int32_t* __restrict__ seg_ptr,
+                                                                  const int32_t* __restrict__ inc,
+                                                                  const int32_t* __restrict__ futoff, int cap_rows,
+                                                                  const float* __restrict__ rsum, int cap_runs,
+                                                                  const float* __restrict__ cpart, int cap_cpart,
+                                                                  float* __restrict__ agg) {
+  const int k = (blockIdx.x * 256 + threadIdx.x) >> 4, l16 = threadIdx.x & 15;
+  if (k >= *n_dets) return;
+  const int row = det_rows[k];
+  const int s = row / cap_rows, dl = row - s * cap_rows;
+  const SlabSegs& sg = segs[s];
+  const AggSlab& sl = tab[s];
+  int qd = 0;
+  while (qd + 1 < sg.nseg && sg.start[qd + 1] <= dl) ++qd;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (qd >= 1 && sg.eord[qd - 1] >= 0) {
+    const AggBlock B = sl.b[sg.eord[qd - 1]];
+    if (B.A > 0 && !B.fresh) {
+      const float* p = cpart + ((size_t)s * cap_cpart + B.cbase + (dl - sg.start[qd])) * H + 4 * l16;
+      for (int i = 0; i < B.nst; ++i) {
+        const float4 v = ldg4(p + (size_t)i * B.nt * H);
+        acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;
+      }
+    }
+  }
+  const int f0 = seg_ptr[2 * k + 1], flen = seg_ptr[2 * k + 2] - f0;
+  if (flen > 0) {
+    const int32_t* f = futoff + (size_t)k * MAXE;
+    for (int b = 0; b < sl.nblk; ++b) {
+      const int o0 = f[b], o1 = b + 1 < sl.nblk ? f[b + 1] : flen;
+      if (o1 <= o0) continue;
+      const AggBlock B = sl.b[b];
+      if (B.fresh || B.A == 0) continue;
+      const int e = inc[f0 + o0] - s * cap_rows;  // first row of the run
+      const int a = (e - B.e0) / B.nt;
+      const float4 v = ldg4(rsum + ((size_t)s * cap_runs + B.rbase + a) * H + 4 * l16);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  *reinterpret_cast<float4*>(agg + (size_t)k * H + 4 * l16) = acc;
+}
+
+extern "C" size_t tmpnn_aggregate_blocks_scratch_bytes(int num_seqs, int cap_runs, int cap_cpart) {
+  return (size_t)num_seqs * sizeof(AggSlab) + (size_t)num_seqs * ((size_t)cap_runs + (size_t)cap_cpart) * H * sizeof(float) + 256;
+}
+
+extern "C" int tmpnn_aggregate_dets_blocks(const tmpnn_graph* g, const tmpnn_index* ix, const void* index_scratch2,
+                                           const float* h, int ldh, int col, float* agg, void* scratch, int cap_runs,
+                                           int cap_cpart, void* stream) {
+  TMPNN_REQUIRE(g && ix && index_scratch2 && h && agg && scratch, "null argument");
+  TMPNN_REQUIRE(ldh % 4 == 0 && col % 4 == 0, "h rows must be 16-byte aligned");
+  TMPNN_REQUIRE(cap_runs > 0 && cap_cpart > 0 && ((uintptr_t)scratch & 15) == 0, "bad scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = g->num_seqs;
+  const SlabSegs* segs = (const SlabSegs*)index_scratch2;
+  // the run offsets of k_block_futoff sit behind the segment tables (tmpnn_index_build_structured's layout)
+  const int32_t* futoff = (const int32_t*)((const unsigned char*)index_scratch2 + (size_t)S * sizeof(SlabSegs));
+  AggSlab* tab = (AggSlab*)scratch;
+  float* rsum = (float*)((unsigned char*)scratch + (((size_t)S * sizeof(AggSlab) + 255) & ~(size_t)255));
+  float* cpart = rsum + (size_t)S * cap_runs * H;
+  k_agg_block_table<<<tmpnn_div_up(S, 128), 128, 0, st>>>(segs, S, g->cap_rows, g->phys, cap_runs, cap_cpart, tab, g->status);
+  TMPNN_LAUNCH_CHECK();
+  // CTAs per slab: enough for the largest windows (a stripe is AB_SA x nt rows), and at least ~6 per SM in total
+  const int gx = max(1, min(tmpnn_div_up(g->cap_rows, 64 * AB_SA), max(64, tmpnn_div_up(TMPNN_SM_COUNT * 6, S))));
+  k_aggregate_blocks<<<dim3(gx, S), 128, 0, st>>>(tab, h, ldh, col, g->cap_rows, g->phys, rsum, cap_runs, cpart, cap_cpart);
+  TMPNN_LAUNCH_CHECK();
+  k_aggregate_blocks_combine<<<tmpnn_div_up(ix->cap_dets, 16), 256, 0, st>>>(segs, tab, ix->n_dets, ix->det_rows, ix->seg_ptr, ix->inc,
+                                                                            futoff, g->cap_rows, rsum, cap_runs, cpart, cap_cpart, agg);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
 // Stand-alone node_support: half-warp per edge row.
 __global__ void __launch_bounds__(256) k_aggregate_edges(const float* __restrict__ h, int ldh, int col, int concat,
                                                          const int32_t* __restrict__ n_rows,

@@ -373,12 +373,31 @@ input_bwd_body(const float* __restrict__ x, int ldx, int col0, int f_in, const i
   if (rl == 0) grad_add<ATOMIC>(&gb2[j], red[0][0][j] + red[0][1][j] + red[0][2][j] + red[0][3][j]);
   const float m1 = training ? m_s[0][j] / ntot : 0.f, m2 = training ? m_s[1][j] / ntot : 0.f;
   __syncthreads();
-  // d W2[o][j] += sum_i dh[i][o] act[i][j]
-  for (int q = threadIdx.x; q < H * H; q += 256) {
-    const int o = q / H, jj = q % H;
-    float s = 0.f;
-    for (int i = 0; i < n; ++i) s = fmaf(dh[(size_t)out_rows[i] * ldh + col + o], act[(size_t)i * H + jj], s);
-    grad_add<ATOMIC>(&gw2[q], s);
+  // d W2[o][j] += sum_i dh[i][o] act[i][j]: thread (rl, j) owns o = rl + 4 m; the rows are staged 32 at a time in shared
+  // memory (the global-memory form spent most of the kernel in this loop: 2 dependent-address loads per FMA); same
+  // ascending order over i as before
+  {
+    __shared__ float sdh[32][H], sact[32][H];
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int nb = min(32, n - i0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < nb * H; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        sdh[r][c] = dh[(size_t)out_rows[i0 + r] * ldh + col + c];
+        sact[r][c] = act[(size_t)(i0 + r) * H + c];
+      }
+      __syncthreads();
+      for (int i = 0; i < nb; ++i) {
+        const float av = sact[i][j];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) acc[m] = fmaf(sdh[i][rl + 4 * m], av, acc[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) grad_add<ATOMIC>(&gw2[(rl + 4 * m) * H + j], acc[m]);
   }
   // pass 2: through the BatchNorm
   float sda = 0.f;
@@ -731,12 +750,20 @@ __global__ void k_bn_running_groups(const InputGroupBatch groups, int n_groups, 
                                     float* __restrict__ rvar) {
   const int j = threadIdx.x;
   float m = rmean[j], v = rvar[j];
-  for (int k = 0; k < n_groups; ++k) {
-    const tmpnn_input_group& g = groups.g[k];
-    if (g.n <= 0) continue;
-    const double ntot = (double)g.n + (double)g.n_edge_rows;
-    m = 0.9f * m + 0.1f * g.mean[j];
-    v = 0.9f * v + 0.1f * (float)((double)g.var[j] * ntot / (ntot - 1.0));
+  // the groups' statistics are fetched up front (independent loads), the recurrence itself stays in group order
+  float gm[GROUPS_PER_LAUNCH], gv[GROUPS_PER_LAUNCH];
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) {
+    const bool on = k < n_groups && groups.g[k].n > 0;
+    gm[k] = on ? groups.g[k].mean[j] : 0.f;
+    gv[k] = on ? groups.g[k].var[j] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) {
+    if (k >= n_groups || groups.g[k].n <= 0) continue;
+    const double ntot = (double)groups.g[k].n + (double)groups.g[k].n_edge_rows;
+    m = 0.9f * m + 0.1f * gm[k];
+    v = 0.9f * v + 0.1f * (float)((double)gv[k] * ntot / (ntot - 1.0));
   }
   rmean[j] = m;
   rvar[j] = v;
@@ -746,15 +773,12 @@ __global__ void __launch_bounds__(128)
 k_input_bn_relu_linear2_groups(const InputGroupBatch groups, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h, int ldh,
                                int col) {
-  __shared__ float w2t[H * H];  // [k][j]
+  __shared__ float w2t[H * (H + 1)];  // [j][k], rows padded to 65 floats: coalesced global reads, conflict-free reads below
   __shared__ float act[4][H];
   const tmpnn_input_group& g = groups.g[blockIdx.x];
   const int n = g.n;
   if (n <= 0) return;
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
-    int k = i / H, j = i % H;
-    w2t[i] = w2[j * H + k];
-  }
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) w2t[(i >> 6) * (H + 1) + (i & 63)] = w2[i];
   __syncthreads();
   const float* a = g.a;
   const float* mean = g.mean;
@@ -771,8 +795,8 @@ k_input_bn_relu_linear2_groups(const InputGroupBatch groups, const float* __rest
 #pragma unroll 8
     for (int k = 0; k < H; ++k) {
       float av = act[w][k];
-      o0 = fmaf(av, w2t[k * H + lane], o0);
-      o1 = fmaf(av, w2t[k * H + lane + 32], o1);
+      o0 = fmaf(av, w2t[lane * (H + 1) + k], o0);
+      o1 = fmaf(av, w2t[(lane + 32) * (H + 1) + k], o1);
     }
     __syncwarp();
     float* hr = h + (size_t)g.out_rows[r] * ldh + col;

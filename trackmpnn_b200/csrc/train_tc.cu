@@ -310,24 +310,34 @@ k_rows_gemm_tc(const int32_t* __restrict__ r_dev, int r_host, const int32_t* __r
   }
 }
 
-// G[m][0:64] += sum over the CTA partials, CTA 0 first: a fixed order, so the weight gradients are reproducible bit for bit
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ partials, int n_sm, const int32_t* __restrict__ r_dev,
-                                                         int r_host, float* __restrict__ G, int ldg) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BGK * 64) return;
+// G[m][0:64] += sum over the CTA partials in a fixed order, so the weight gradients are reproducible bit for bit.  64 outputs
+// per CTA x 16 groups of partials (group p takes CTAs p, p + 16, ...: <= 10 independent loads per thread, all in flight at
+// once; one thread per output walking all 148 partials was latency bound at ~11 us per call, 32 calls per training step)
+__global__ void __launch_bounds__(1024) k_reduce_partials(const float* __restrict__ partials, int n_sm, const int32_t* __restrict__ r_dev,
+                                                          int r_host, float* __restrict__ G, int ldg) {
+  __shared__ float part[16][64];
+  const int il = threadIdx.x & 63, pg = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + il;
   // only the CTAs that had a tile hold a partial (the others did not even write zeros)
   const int R = r_dev ? *r_dev : r_host;
   const int n_part = min(n_sm, (R + TCM - 1) / TCM);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains of loads in flight; the combination order is fixed
-  int c = 0;
-  for (; c + 3 < n_part; c += 4) {
-    s0 += partials[(size_t)c * BGK * 64 + i];
-    s1 += partials[(size_t)(c + 1) * BGK * 64 + i];
-    s2 += partials[(size_t)(c + 2) * BGK * 64 + i];
-    s3 += partials[(size_t)(c + 3) * BGK * 64 + i];
+  float v[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const int c = pg + 16 * q;
+    v[q] = c < n_part ? partials[(size_t)c * BGK * 64 + i] : 0.f;
   }
-  for (; c < n_part; ++c) s0 += partials[(size_t)c * BGK * 64 + i];
-  G[(size_t)(i / 64) * ldg + (i % 64)] += (s0 + s1) + (s2 + s3);
+  float s = v[0];
+#pragma unroll
+  for (int q = 1; q < 10; ++q) s += v[q];
+  part[pg][il] = s;
+  __syncthreads();
+  if (pg == 0) {
+    float t = part[0][il];
+#pragma unroll
+    for (int p = 1; p < 16; ++p) t += part[p][il];
+    G[(size_t)(i / 64) * ldg + (i % 64)] += t;
+  }
 }
 
 bool g_bw_init = false;
@@ -367,7 +377,8 @@ extern "C" int tmpnn_rows_gemm_tc(const int32_t* r_dev, int r_host, const int32_
                                                              (const unsigned char*)w_image, C, ldc, accumulate, X, ldx, partials,
                                                              status);
   TMPNN_LAUNCH_CHECK();
-  k_reduce_partials<<<tmpnn_div_up(BGK * 64, 256), 256, 0, st>>>(partials, TMPNN_SM_COUNT, r_dev, r_host, G, ldg);
+  static_assert(TMPNN_SM_COUNT <= 160, "k_reduce_partials: 16 groups x 10 partials");
+  k_reduce_partials<<<BGK, 1024, 0, st>>>(partials, TMPNN_SM_COUNT, r_dev, r_host, G, ldg);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }

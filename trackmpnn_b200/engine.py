@@ -36,12 +36,15 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True):
+                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True, block_aggregation=True):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
         through the position maps the compaction emits (tmpnn_graph.phys / psrc / pdst) and writes its output
-        densely, so the state only ever crosses HBM once per step in each direction."""
+        densely, so the state only ever crosses HBM once per step in each direction.
+
+        block_aggregation: with the structured index the detections' aggregation reads each dense edge block once
+        (tmpnn_aggregate_dets_blocks) instead of walking the incidence lists."""
         self.model = model
         self.tp_classifier = bool(tp_classifier)   # False: infer.py's --no-tp-classifier
         self.dev = device if device is not None else next(model.parameters()).device
@@ -121,11 +124,23 @@ class TrackEngine:
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self._tc_scratch = {}
         self._gat_scratch = {}
+        # block-structured aggregation (needs the structured index): per slab one run sum per (source, edge block) and one
+        # column partial per (stripe of 32 sources, detection)
+        self._agg_blocks = None
+        if self.structured_index and block_aggregation:
+            cap_runs = max_dets * min(self.W + self.R, 64)
+            cap_cpart = self.cap_rows // 32 + max_dets + 64
+            nbytes = int(L.lib().tmpnn_aggregate_blocks_scratch_bytes(self.S, cap_runs, cap_cpart))
+            self._agg_blocks = dict(cap_runs=cap_runs, cap_cpart=cap_cpart,
+                                    scratch=torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=dev))
         self.profile = None  # when a list: (edge start, edge end, n_edges tensor, aggregation start, aggregation end, new edge rows) per step
         self.profile_compact = None  # when a list: (start, end, rows before, rows after) per window slide
         # when a list: four events per tick bracketing the reference's three phases -- update_graph (append) |
         # forward (input transform, index, aggregation, both row types) | decode_tracks (associate, walk, window slide)
         self.profile_phases = None
+        # when a list (eager ticks only): every step also aggregates through the incidence lists (tmpnn_aggregate_dets) and
+        # appends (detections, max |difference| to the block-structured result, max |reference|)
+        self.check_aggregation = None
         self._graph = None
         self._graph_key = None
         self.ticks = 0
@@ -156,7 +171,14 @@ class TrackEngine:
             if self.profile is not None:
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
-            F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, self.agg, self._gat_scratch)
+            F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, self.agg, self._gat_scratch,
+                                  blocks=self._agg_blocks)
+            if self.check_aggregation is not None and self._agg_blocks is not None and model.factor_grus[grp].gat is None:
+                ref = torch.empty_like(self.agg)
+                L.call('tmpnn_aggregate_dets', g.c, self.index.c, L.ptr(h_in), self.ldh, grp * H, L.ptr(ref), st)
+                nd = int(self.index.n_dets.item())
+                self.check_aggregation.append((nd, float((ref[:nd] - self.agg[:nd]).abs().max()) if nd else 0.0,
+                                               float(ref[:nd].abs().max()) if nd else 0.0))
             if self.profile is not None:
                 a1.record()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

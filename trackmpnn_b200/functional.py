@@ -102,13 +102,18 @@ class SparseAttention:
         return A
 
 
-def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, keep_attention=False):
+def aggregate_for_dets(gru, graph, index, h_in, ldh, col, agg, scratch=None, keep_attention=False, blocks=None):
     """Input of the node GRU for the detection rows: the plain signed sum, or -- with attention heads --
     the attention-weighted one (reference ``models/layers.py:101-112``).  Returns a list of per-head
     ``alpha`` tensors when ``keep_attention`` (else None)."""
     st = L.stream()
     if gru.gat is None:
-        L.call('tmpnn_aggregate_dets', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(agg), st)
+        if blocks is not None:
+            # structured index (TrackEngine): one pass over the dense edge blocks, every association row read once
+            L.call('tmpnn_aggregate_dets_blocks', graph.c, index.c, L.ptr(index._scratch2), L.ptr(h_in), ldh, col, L.ptr(agg),
+                   L.ptr(blocks['scratch']), blocks['cap_runs'], blocks['cap_cpart'], st)
+        else:
+            L.call('tmpnn_aggregate_dets', graph.c, index.c, L.ptr(h_in), ldh, col, L.ptr(agg), st)
         return None
     if gru.training:
         # train mode: dropout on the attention (same kernels as the autograd path; the saved tensors are dropped)

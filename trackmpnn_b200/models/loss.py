@@ -48,10 +48,10 @@ class _CEFn(torch.autograd.Function):
         lg = logits.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         tg = targets.detach().to(device=dev, dtype=torch.int32).contiguous().view(-1)
         nseg = 2 * ix.cap_dets + 2
-        seg_lse = torch.zeros(nseg, dtype=torch.float32, device=dev)
+        seg_lse = L.zeros(nseg, dev)
         seg_pos = torch.full((nseg,), -1, dtype=torch.int32, device=dev)
-        seg_loss = torch.zeros(nseg, dtype=torch.float32, device=dev)
-        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        seg_loss = L.zeros(nseg, dev)
+        loss = L.zeros(1, dev)
         L.call('tmpnn_loss_ce_fwd', ix.c, n, L.ptr(tg), L.ptr(lg), L.ptr(seg_lse), L.ptr(seg_pos), L.ptr(seg_loss),
                L.ptr(loss), L.stream())
         ctx.wg, ctx.ix, ctx.lg, ctx.seg_lse, ctx.seg_pos = wg, ix, lg, seg_lse, seg_pos
@@ -62,7 +62,7 @@ class _CEFn(torch.autograd.Function):
     def backward(ctx, gout):
         wg = ctx.wg
         g = gout.detach().to(device=wg.device, dtype=torch.float32).contiguous().view(1)
-        d = torch.zeros(max(1, wg.n), dtype=torch.float32, device=wg.device)
+        d = L.zeros(max(1, wg.n), wg.device)
         L.call('tmpnn_loss_ce_bwd', wg.g.c, ctx.ix.c, wg.n, L.ptr(ctx.seg_lse), L.ptr(ctx.seg_pos), L.ptr(ctx.lg), L.ptr(g),
                L.ptr(d), L.stream())
         return d[:wg.n].view(ctx.shape).to(ctx.dev), None, None

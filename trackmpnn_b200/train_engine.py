@@ -243,7 +243,7 @@ class _WeightedBCE(torch.autograd.Function):
         n = int(p.numel())
         pc = p.detach().to(torch.float32).contiguous().view(-1)
         per = torch.empty(n, dtype=torch.float32, device=p.device)
-        loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+        loss = L.zeros(1, p.device)
         L.call('tmpnn_loss_wbce_fwd', n, L.ptr(pc), L.ptr(targets), L.ptr(w), L.ptr(per), L.ptr(loss), L.stream())
         ctx.pc, ctx.t, ctx.w, ctx.n, ctx.shape = pc, targets, w, n, p.shape
         return loss[0]
@@ -302,11 +302,16 @@ class GraphedTrainStep:
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, capturable=True)  # train.py:329
         self.loss = torch.zeros((), dtype=torch.float32, device=batch.device)
         self._g_fb = self._g_opt = None
+        self.arena = L.ZeroArena(batch.device)
 
     def _forward_backward(self):
         self.flat.zero()
-        loss = batch_loss(self.model, self.batch, self.tp)
-        loss.backward()
+        self.arena.begin()      # one fill for the step's small zero-initialised scratch tensors
+        try:
+            loss = batch_loss(self.model, self.batch, self.tp)
+            loss.backward()
+        finally:
+            L.ZeroArena.end()
         self.loss.copy_(loss.detach())
 
     def eager(self):
