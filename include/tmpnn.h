@@ -362,10 +362,15 @@ typedef struct tmpnn_input_group {
 int tmpnn_input_bn_groups_fwd(const tmpnn_input_group *groups, int n_groups, const float *b1, const float *gamma,
                               const float *beta, const float *w2, const float *b2, float *running_mean,
                               float *running_var, float *h, int ldh, int col, void *stream);
+/* partials: NULL = the groups add into the gradient buffers atomically; else tmpnn_input_bwd_partial_floats(n_groups)
+ * floats of scratch: every group stores its own partial gradients and a second kernel adds them in group order (no
+ * contention on the 4 k shared addresses, and the weight gradients of the input transform come out reproducible bit for
+ * bit). */
+size_t tmpnn_input_bwd_partial_floats(int n_groups);
 int tmpnn_input_bwd_groups(const float *x, int ldx, int col0, int f_in, const tmpnn_input_group *groups, int n_groups,
                            const float *gamma, const float *beta, const float *b1, const float *w2, const float *dh,
                            int ldh, int col, int training, float *gw1, float *gb1, float *ggamma, float *gbeta,
-                           float *gw2, float *gb2, void *stream);
+                           float *gw2, float *gb2, float *partials, void *stream);
 
 /* create_targets (models/loss.py:8-44) on a single-slab graph with labels: targets[N] int32. */
 int tmpnn_loss_targets(const tmpnn_graph *g, const tmpnn_index *ix, int n_rows, int32_t *targets, void *stream);

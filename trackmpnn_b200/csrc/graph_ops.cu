@@ -137,14 +137,25 @@ __global__ void __launch_bounds__(256) k_associate(const int32_t* __restrict__ n
     } else if (score[row] >= 0.5f) {
       int b_ts = INT_MAX, b_e = INT_MAX;
       float b_p = -1.f;
-      for (int i = f0 + lane; i < f1; i += 32) {
-        const int e = inc[i];
-        const float pe = score[e];
-        if (!(pe >= 0.5f)) continue;
-        const int d = base + dst[e];
-        if (!(score[d] >= 0.5f)) continue;
-        const int t = ts[d];
-        if (t < b_ts || (t == b_ts && (pe > b_p || (pe == b_p && e < b_e)))) { b_ts = t; b_p = pe; b_e = e; }
+      // four strides of the list in flight (the walk is a chain of dependent loads inc -> score; one stride at a time left
+      // the kernel latency bound); the best candidate is a minimum of a total order, so the visiting order is free
+      for (int i0 = f0 + lane; i0 < f1; i0 += 128) {
+        int ev[4];
+        float pv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ev[q] = i0 + 32 * q < f1 ? inc[i0 + 32 * q] : -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pv[q] = ev[q] >= 0 ? score[ev[q]] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = ev[q];
+          const float pe = pv[q];
+          if (!(pe >= 0.5f)) continue;
+          const int d = base + dst[e];
+          if (!(score[d] >= 0.5f)) continue;
+          const int t = ts[d];
+          if (t < b_ts || (t == b_ts && (pe > b_p || (pe == b_p && e < b_e)))) { b_ts = t; b_p = pe; b_e = e; }
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -784,7 +795,7 @@ extern "C" int tmpnn_graph_associate(const tmpnn_graph* g, const tmpnn_index* ix
   cudaStream_t st = (cudaStream_t)stream;
   k_reset_ass<<<stride_grid(g), 256, 0, st>>>(g->n_rows, active, g->cap_rows, g->ass);
   TMPNN_LAUNCH_CHECK();
-  k_associate<<<TMPNN_SM_COUNT * 4, 256, 0, st>>>(ix->n_dets, ix->det_rows, ix->seg_ptr, ix->inc, g->ts, g->det, g->dst,
+  k_associate<<<TMPNN_SM_COUNT * 8, 256, 0, st>>>(ix->n_dets, ix->det_rows, ix->seg_ptr, ix->inc, g->ts, g->det, g->dst,
                                                  g->label, g->score, g->cap_rows, mode, g->ass, g->status);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;

@@ -323,13 +323,15 @@ k_scatter_bwd_dets(const int32_t* __restrict__ n_dets, const int32_t* __restrict
 // ------------------------------------------------------------------------------------------
 constexpr int GROUPS_PER_LAUNCH = 32;  // descriptors travel by value in the kernel parameters (32 x 56 B)
 struct InputGroupBatch { tmpnn_input_group g[GROUPS_PER_LAUNCH]; };
-// ATOMIC: several CTAs (one per group of rows = one BatchNorm batch) add into the same gradient buffers
-template <bool ATOMIC>
+// ATOMIC 0: one CTA owns the gradient buffers (+=); 1: several CTAs (one per group of rows = one BatchNorm batch) add into
+// the same buffers atomically; 2: every CTA stores into its own partial buffer (k_input_bwd_reduce adds them in group order)
+template <int ATOMIC>
 __device__ __forceinline__ void grad_add(float* p, float v) {
-  if (ATOMIC) atomicAdd(p, v);
+  if (ATOMIC == 1) atomicAdd(p, v);
+  else if (ATOMIC == 2) *p = v;
   else *p += v;
 }
-template <bool ATOMIC>
+template <int ATOMIC>
 __device__ __forceinline__ void
 input_bwd_body(const float* __restrict__ x, int ldx, int col0, int f_in, const int32_t* __restrict__ x_idx,
                const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ var,
@@ -436,7 +438,7 @@ k_input_bwd(const float* __restrict__ x, int ldx, int col0, int f_in, const int3
             const int32_t* __restrict__ out_rows, int n, int n_edge, int training, float* __restrict__ scratch,
             float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ ggamma, float* __restrict__ gbeta,
             float* __restrict__ gw2, float* __restrict__ gb2) {
-  input_bwd_body<false>(x, ldx, col0, f_in, x_idx, a, mean, var, gamma, beta, b1, w2, dh, ldh, col, out_rows, n, n_edge,
+  input_bwd_body<0>(x, ldx, col0, f_in, x_idx, a, mean, var, gamma, beta, b1, w2, dh, ldh, col, out_rows, n, n_edge,
                         training, scratch, gw1, gb1, ggamma, gbeta, gw2, gb2);
 }
 // one CTA per group (tmpnn_input_group): the batched trainer's chunks, each its own BatchNorm batch
@@ -448,8 +450,45 @@ k_input_bwd_groups(const float* __restrict__ x, int ldx, int col0, int f_in, con
                    float* __restrict__ gw2, float* __restrict__ gb2) {
   const tmpnn_input_group& g = groups.g[blockIdx.x];
   if (g.n <= 0) return;
-  input_bwd_body<true>(x, ldx, col0, f_in, g.x_idx, g.a, g.mean, g.var, gamma, beta, b1, w2, dh, ldh, col, g.out_rows, g.n,
-                       g.n_edge_rows, training, g.scratch, gw1, gb1, ggamma, gbeta, gw2, gb2);
+  input_bwd_body<1>(x, ldx, col0, f_in, g.x_idx, g.a, g.mean, g.var, gamma, beta, b1, w2, dh, ldh, col, g.out_rows, g.n,
+                    g.n_edge_rows, training, g.scratch, gw1, gb1, ggamma, gbeta, gw2, gb2);
+}
+// The same with per-group partial gradients instead of atomics: 32 CTAs adding 4 k values each into the same addresses
+// spent most of the kernel in the L2 atomic units, and the sums came out in arbitrary order.  Partial of group k (floats):
+// [0, 4096) d W2 | [4096, 8192) d W1 (64 x f_in) | then 64 each of d b1, d gamma, d beta, d b2.
+constexpr int IBW_PART = 2 * H * H + 4 * H;
+__global__ void __launch_bounds__(256)
+k_input_bwd_groups_part(const float* __restrict__ x, int ldx, int col0, int f_in, const InputGroupBatch groups,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ b1,
+                        const float* __restrict__ w2, const float* __restrict__ dh, int ldh, int col, int training,
+                        float* __restrict__ partials) {
+  const tmpnn_input_group& g = groups.g[blockIdx.x];
+  if (g.n <= 0) return;
+  float* p = partials + (size_t)blockIdx.x * IBW_PART;
+  input_bwd_body<2>(x, ldx, col0, f_in, g.x_idx, g.a, g.mean, g.var, gamma, beta, b1, w2, dh, ldh, col, g.out_rows, g.n,
+                    g.n_edge_rows, training, g.scratch, p + H * H, p + 2 * H * H, p + 2 * H * H + H, p + 2 * H * H + 2 * H, p,
+                    p + 2 * H * H + 3 * H);
+}
+__global__ void __launch_bounds__(256)
+k_input_bwd_reduce(const InputGroupBatch groups, int n_groups, int f_in, const float* __restrict__ partials,
+                   float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                   float* __restrict__ gw2, float* __restrict__ gb2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= IBW_PART) return;
+  float* dst;
+  if (i < H * H) dst = gw2 + i;
+  else if (i < 2 * H * H) { if (i - H * H >= H * f_in) return; dst = gw1 + (i - H * H); }
+  else {
+    const int q = (i - 2 * H * H) / H, j = (i - 2 * H * H) % H;
+    dst = (q == 0 ? gb1 : q == 1 ? ggamma : q == 2 ? gbeta : gb2) + j;
+  }
+  float v[GROUPS_PER_LAUNCH];
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) v[k] = (k < n_groups && groups.g[k].n > 0) ? partials[(size_t)k * IBW_PART + i] : 0.f;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) t += v[k];   // group order: reproducible bit for bit
+  *dst += t;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -758,50 +797,69 @@ __global__ void k_bn_running_groups(const InputGroupBatch groups, int n_groups, 
     gm[k] = on ? groups.g[k].mean[j] : 0.f;
     gv[k] = on ? groups.g[k].var[j] : 0.f;
   }
+  // unbiased variance: var n / (n - 1) in double like before, but all the (slow) fp64 divisions issue before the recurrence
+  float gu[GROUPS_PER_LAUNCH];
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) {
+    const double ntot = k < n_groups ? (double)groups.g[k].n + (double)groups.g[k].n_edge_rows : 2.0;
+    gu[k] = (float)((double)gv[k] * ntot / (ntot - 1.0));
+  }
 #pragma unroll
   for (int k = 0; k < GROUPS_PER_LAUNCH; ++k) {
     if (k >= n_groups || groups.g[k].n <= 0) continue;
-    const double ntot = (double)groups.g[k].n + (double)groups.g[k].n_edge_rows;
     m = 0.9f * m + 0.1f * gm[k];
-    v = 0.9f * v + 0.1f * (float)((double)gv[k] * ntot / (ntot - 1.0));
+    v = 0.9f * v + 0.1f * gu[k];
   }
   rmean[j] = m;
   rvar[j] = v;
 }
-// BatchNorm -> ReLU -> Linear2 of every group with its own statistics, one CTA per group
-__global__ void __launch_bounds__(128)
+// BatchNorm -> ReLU -> Linear2 of every group with its own statistics, one CTA per group (8 warps, two rows per warp pass;
+// the per-channel constants are fetched once)
+__global__ void __launch_bounds__(256)
 k_input_bn_relu_linear2_groups(const InputGroupBatch groups, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ h, int ldh,
                                int col) {
   __shared__ float w2t[H * (H + 1)];  // [j][k], rows padded to 65 floats: coalesced global reads, conflict-free reads below
-  __shared__ float act[4][H];
+  __shared__ float act[8][2][H];
   const tmpnn_input_group& g = groups.g[blockIdx.x];
   const int n = g.n;
   if (n <= 0) return;
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) w2t[(i >> 6) * (H + 1) + (i & 63)] = w2[i];
-  __syncthreads();
   const float* a = g.a;
-  const float* mean = g.mean;
-  const float* var = g.var;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int r = w; r < n; r += 4) {
-    // (a - mean) / sqrt(var + eps) * gamma + beta, written like torch's batch_norm
-    float v0 = (a[(size_t)r * H + lane] - mean[lane]) * (1.0f / sqrtf(var[lane] + 1e-5f)) * gamma[lane] + beta[lane];
-    float v1 = (a[(size_t)r * H + lane + 32] - mean[lane + 32]) * (1.0f / sqrtf(var[lane + 32] + 1e-5f)) * gamma[lane + 32] + beta[lane + 32];
-    act[w][lane] = fmaxf(v0, 0.f);
-    act[w][lane + 32] = fmaxf(v1, 0.f);
+  // (a - mean) / sqrt(var + eps) * gamma + beta, written like torch's batch_norm
+  const float mu0 = g.mean[lane], mu1 = g.mean[lane + 32];
+  const float is0 = 1.0f / sqrtf(g.var[lane] + 1e-5f), is1 = 1.0f / sqrtf(g.var[lane + 32] + 1e-5f);
+  const float ga0 = gamma[lane], ga1 = gamma[lane + 32], be0 = beta[lane], be1 = beta[lane + 32];
+  const float bo0 = b2[lane], bo1 = b2[lane + 32];
+  __syncthreads();
+  for (int r = 2 * w; r < n; r += 16) {
+    const bool two = r + 1 < n;
+    const float x00 = a[(size_t)r * H + lane], x01 = a[(size_t)r * H + lane + 32];
+    const float x10 = two ? a[(size_t)(r + 1) * H + lane] : 0.f, x11 = two ? a[(size_t)(r + 1) * H + lane + 32] : 0.f;
+    const int orow0 = g.out_rows[r], orow1 = two ? g.out_rows[r + 1] : 0;
+    act[w][0][lane] = fmaxf((x00 - mu0) * is0 * ga0 + be0, 0.f);
+    act[w][0][lane + 32] = fmaxf((x01 - mu1) * is1 * ga1 + be1, 0.f);
+    act[w][1][lane] = fmaxf((x10 - mu0) * is0 * ga0 + be0, 0.f);
+    act[w][1][lane + 32] = fmaxf((x11 - mu1) * is1 * ga1 + be1, 0.f);
     __syncwarp();
-    float o0 = b2[lane], o1 = b2[lane + 32];
+    float o00 = bo0, o01 = bo1, o10 = bo0, o11 = bo1;
 #pragma unroll 8
     for (int k = 0; k < H; ++k) {
-      float av = act[w][k];
-      o0 = fmaf(av, w2t[lane * (H + 1) + k], o0);
-      o1 = fmaf(av, w2t[(lane + 32) * (H + 1) + k], o1);
+      const float w0 = w2t[lane * (H + 1) + k], w1 = w2t[(lane + 32) * (H + 1) + k];
+      const float a0 = act[w][0][k], a1 = act[w][1][k];
+      o00 = fmaf(a0, w0, o00); o01 = fmaf(a0, w1, o01);
+      o10 = fmaf(a1, w0, o10); o11 = fmaf(a1, w1, o11);
     }
     __syncwarp();
-    float* hr = h + (size_t)g.out_rows[r] * ldh + col;
-    hr[lane] = o0;
-    hr[lane + 32] = o1;
+    float* hr = h + (size_t)orow0 * ldh + col;
+    hr[lane] = o00;
+    hr[lane + 32] = o01;
+    if (two) {
+      hr = h + (size_t)orow1 * ldh + col;
+      hr[lane] = o10;
+      hr[lane + 32] = o11;
+    }
   }
 }
 
@@ -824,7 +882,7 @@ extern "C" int tmpnn_input_bn_groups_fwd(const tmpnn_input_group* groups, int n_
       k_bn_running_groups<<<1, H, 0, st>>>(batch, nb, running_mean, running_var);
       TMPNN_LAUNCH_CHECK();
     }
-    k_input_bn_relu_linear2_groups<<<nb, 128, 0, st>>>(batch, gamma, beta, w2, b2, h, ldh, col);
+    k_input_bn_relu_linear2_groups<<<nb, 256, 0, st>>>(batch, gamma, beta, w2, b2, h, ldh, col);
     TMPNN_LAUNCH_CHECK();
   }
   return TMPNN_OK;
@@ -833,19 +891,29 @@ extern "C" int tmpnn_input_bn_groups_fwd(const tmpnn_input_group* groups, int n_
 extern "C" int tmpnn_input_bwd_groups(const float* x, int ldx, int col0, int f_in, const tmpnn_input_group* groups,
                                       int n_groups, const float* gamma, const float* beta, const float* b1,
                                       const float* w2, const float* dh, int ldh, int col, int training, float* gw1,
-                                      float* gb1, float* ggamma, float* gbeta, float* gw2, float* gb2, void* stream) {
+                                      float* gb1, float* ggamma, float* gbeta, float* gw2, float* gb2, float* partials,
+                                      void* stream) {
   TMPNN_REQUIRE(x && groups && gamma && beta && b1 && w2 && dh, "null argument");
   TMPNN_REQUIRE(gw1 && gb1 && ggamma && gbeta && gw2 && gb2, "null gradient buffer");
+  TMPNN_REQUIRE(!partials || f_in <= H, "partial buffers hold at most 64 input features per group");
+  cudaStream_t st = (cudaStream_t)stream;
   for (int g0 = 0; g0 < n_groups; g0 += GROUPS_PER_LAUNCH) {
     InputGroupBatch batch;
     const int nb = min(GROUPS_PER_LAUNCH, n_groups - g0);
     for (int k = 0; k < nb; ++k) batch.g[k] = groups[g0 + k];
-    k_input_bwd_groups<<<nb, 256, 0, (cudaStream_t)stream>>>(x, ldx, col0, f_in, batch, gamma, beta, b1, w2, dh, ldh, col,
-                                                             training, gw1, gb1, ggamma, gbeta, gw2, gb2);
+    if (partials) {
+      k_input_bwd_groups_part<<<nb, 256, 0, st>>>(x, ldx, col0, f_in, batch, gamma, beta, b1, w2, dh, ldh, col, training, partials);
+      TMPNN_LAUNCH_CHECK();
+      k_input_bwd_reduce<<<tmpnn_div_up(IBW_PART, 256), 256, 0, st>>>(batch, nb, f_in, partials, gw1, gb1, ggamma, gbeta, gw2, gb2);
+    } else {
+      k_input_bwd_groups<<<nb, 256, 0, st>>>(x, ldx, col0, f_in, batch, gamma, beta, b1, w2, dh, ldh, col, training, gw1, gb1,
+                                             ggamma, gbeta, gw2, gb2);
+    }
     TMPNN_LAUNCH_CHECK();
   }
   return TMPNN_OK;
 }
+extern "C" size_t tmpnn_input_bwd_partial_floats(int n_groups) { return (size_t)min(max(n_groups, 1), GROUPS_PER_LAUNCH) * IBW_PART; }
 
 extern "C" int tmpnn_loss_targets(const tmpnn_graph* g, const tmpnn_index* ix, int n_rows, int32_t* targets, void* stream) {
   TMPNN_REQUIRE(g && ix && targets && g->label && g->num_seqs == 1, "bad argument (single-slab graph with labels)");

@@ -670,6 +670,8 @@ class _MPStepFn(torch.autograd.Function):
                 cols = model.feature_idx[g]
                 tot = sum(t[3] for t in groups_in)
                 scratch = torch.empty((2 * tot, H), **f32)
+                # per-group partial gradients, added in group order by a second kernel (no atomics on the shared buffers)
+                part = torch.empty(int(L.lib().tmpnn_input_bwd_partial_floats(len(groups_in))), **f32) if len(cols) <= H else None
                 desc = (L.InputGroup * len(groups_in))()
                 off = 0
                 for k, (_, x_idx, out_rows, nd, n_edge_new, per_group) in enumerate(groups_in):
@@ -680,7 +682,7 @@ class _MPStepFn(torch.autograd.Function):
                 L.call('tmpnn_input_bwd_groups', L.ptr(xd), int(xd.shape[1]), int(cols[0]), len(cols), desc,
                        len(groups_in), L.ptr(P[b + 2]), L.ptr(P[b + 3]), L.ptr(P[b + 1]), L.ptr(P[b + 4]), L.ptr(dh_cur), ldh,
                        col, int(groups_in[0][5][g][3]), L.ptr(grads[b + 0]), L.ptr(grads[b + 1]), L.ptr(grads[b + 2]),
-                       L.ptr(grads[b + 3]), L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), st)
+                       L.ptr(grads[b + 3]), L.ptr(grads[b + 4]), L.ptr(grads[b + 5]), L.ptr(part), st)
                 groups_in = []
             for xd, new_det, out_rows, nd, n_edge_new, per_group in groups_in:
                 a, mean, var, training = per_group[g]
