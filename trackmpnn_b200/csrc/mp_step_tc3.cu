@@ -46,6 +46,22 @@ __constant__ float c_tc3_expo[4];
 // operands: no shared-memory broadcast loads (sixteen LDS.128 per warp and tile), no registers held across the math
 __constant__ float c_tc3_tail[128];
 
+// Two measured experiments, kept behind flags (profiles/r02_ab_tc3_split.txt, r02_tc_trace_split.txt; parity green for both):
+// TC3_SPLIT: the accumulator stage is released to the MMA issuer in two halves (hidden units 0-15 | 32-47 after the first
+// four gate steps, the rest after the last; weight images group-major, every MMA N = 96), so that the next tile's MMAs on
+// the stage overlap the second half of the gate phase.  14 % SLOWER (2.71 -> 3.10 ms): the single pair of far-endpoint
+// images is now held from the first group's MMAs until the second group's retire, the copies of the next tile start that
+// much later, and the issuer waits for them (xfull 0.5 k -> 1.3 k cycles, producers' xfree wait 1.6 k -> 2.3 k); a second
+// pair of x images does not fit beside three own-row buffers.
+// TC3_HEAD_EARLY: the upper column half of a row publishes its head partial sum right after the gate phase (before its
+// stores) through an mbarrier pair, so the lower half never waits for its partner when it writes the logit: 2 % slower.
+#ifndef TC3_SPLIT
+#define TC3_SPLIT 0
+#endif
+#ifndef TC3_HEAD_EARLY
+#define TC3_HEAD_EARLY 0
+#endif
+
 namespace {
 
 constexpr int EPI3 = 16, PROD3 = 8;
@@ -82,14 +98,35 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   const uint32_t x_u = sm_u + OFF_A;
   unsigned char* const h_img = sm + OFF_A + 2 * A_PART;  // + hb * H_BUF: [h_hi | h_lo] of buffer hb
   const uint32_t bar_hfull = sm_u + OFF_BAR, bar_hfree = bar_hfull + 24, bar_xfull = bar_hfull + 48, bar_xfree = bar_hfull + 56,
-                 bar_done = bar_hfull + 64, bar_gfree = bar_hfull + 80;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 96);
+                 bar_done = bar_hfull + 64, bar_gfree = bar_hfull + 80, bar_doneB = bar_hfull + 96, bar_gfreeB = bar_hfull + 112;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 128);
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
   {
     const uint4* gsrc = reinterpret_cast<const uint4*>(image);
     uint4* sdst = reinterpret_cast<uint4*>(sm);
-    for (int i = threadIdx.x; i < IMAGE_BYTES / 16; i += TC3_THREADS) sdst[i] = __ldg(gsrc + i);
+#if TC3_HEAD_EARLY
+    constexpr int IMG_CHUNKS = 4 * B_BYTES / 16;  // the bias / head slots are not read from shared memory (constant bank): they
+                                                  // hold the head partial sums and their barriers
+#else
+    constexpr int IMG_CHUNKS = IMAGE_BYTES / 16;
+#endif
+#if TC3_SPLIT
+    // weight images group-major: packed row 64 t + 32 h + 16 g + q (gate t, hidden unit 32 h + 16 g + q) goes to row
+    // 96 g + 32 t + 16 h + q.  Both rows have the same (row & 7), i.e. the same 128B-swizzle phase: a plain row move
+    for (int i = threadIdx.x; i < IMG_CHUNKS; i += TC3_THREADS) {
+      int o = i;
+      if (i < 4 * B_BYTES / 16) {
+        const int img = i / (B_BYTES / 16), rem = i - img * (B_BYTES / 16);
+        const int row = rem >> 3, c = rem & 7;
+        const int t = row >> 6, h = (row >> 5) & 1, g = (row >> 4) & 1, q = row & 15;
+        o = img * (B_BYTES / 16) + ((96 * g + 32 * t + 16 * h + q) << 3) + c;
+      }
+      sdst[o] = __ldg(gsrc + i);
+    }
+#else
+    for (int i = threadIdx.x; i < IMG_CHUNKS; i += TC3_THREADS) sdst[i] = __ldg(gsrc + i);
+#endif
   }
   if (threadIdx.x == 0) {
     for (int b = 0; b < 3; ++b) {
@@ -101,7 +138,12 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_done + 8 * s, 1);       // tcgen05.commit behind the own-row MMAs: accumulators complete
       mbar_init(bar_gfree + 8 * s, 8);      // one arrive per warp of the stage's team: accumulators drained
+      mbar_init(bar_doneB + 8 * s, 1);      // TC3_SPLIT: the same pair for the second hidden group of the stage
+      mbar_init(bar_gfreeB + 8 * s, 8);
     }
+#if TC3_HEAD_EARLY
+    for (int q = 0; q < 16; ++q) mbar_init(sm_u + OFF_HEADW + 8 * q, 1);  // head partials published / consumed, per (team, quadrant)
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -116,7 +158,15 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   const int stride = gridDim.x;
   // the own-row MMAs only ever accumulate: the h_n columns of both accumulator stages start at zero (each epilogue
   // warp owns the 32 lanes x 32 columns it will later drain and re-zero)
+#if TC3_SPLIT
+  if (warp < EPI3) {
+    const uint32_t tz = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 16 * ((warp & 7) >> 2));
+    tmem_zero16(tz);
+    tmem_zero16(tz + 128);
+  }
+#else
   if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 32 * ((warp & 7) >> 2)));
+#endif
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,6 +182,29 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         const int stage = it & 1;
         const uint32_t phase = (uint32_t)(it >> 1) & 1u;
         const uint32_t d0 = tmem_base + (uint32_t)(stage * 256);
+#if TC3_SPLIT
+        // first hidden group: its columns were drained by the team half way through the gate phase of the tile two back
+        mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);
+        TC3_TRACE(it, 5, true);
+        mbar_wait(bar_xfull, (uint32_t)it & 1u, status);       // far-endpoint images landed (issued a tile ago)
+        TC3_TRACE(it, 6, true);
+        fence_proxy_async();  // the copies were generic-proxy writes of other threads, observed through the barrier
+        tc_fence_after();
+        issue_group_mma_x(sm_u, d0, x_u, xflags, 0);
+        mbar_wait(bar_hfull + 8 * hb, hphase, status);         // own rows: written up to two tiles ahead
+        TC3_TRACE(it, 10, true);
+        tc_fence_after();
+        issue_group_mma_h(sm_u, d0, x_u + 2 * A_PART + (uint32_t)hb * H_BUF, 0);
+        umma_commit(bar_done + 8 * stage);  // first group ready (implies tcgen05.fence::before_thread_sync)
+        // second hidden group: drained at the end of that gate phase
+        mbar_wait(bar_gfreeB + 8 * stage, phase ^ 1u, status);
+        tc_fence_after();
+        issue_group_mma_x(sm_u, d0 + 128, x_u, xflags, 1);
+        umma_commit(bar_xfree);  // x images reusable once these retire: the copies of tile it + 1 start here
+        issue_group_mma_h(sm_u, d0 + 128, x_u + 2 * A_PART + (uint32_t)hb * H_BUF, 1);
+        umma_commit(bar_doneB + 8 * stage);
+        TC3_TRACE(it, 7, true);
+#else
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
         TC3_TRACE(it, 5, true);
         mbar_wait(bar_xfull, (uint32_t)it & 1u, status);       // far-endpoint images landed (issued a tile ago)
@@ -148,6 +221,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         issue_tile_mma_h_second(sm_u, d0, x_u + 2 * A_PART + (uint32_t)hb * H_BUF);
         umma_commit(bar_done + 8 * stage);  // accumulators ready (implies tcgen05.fence::before_thread_sync)
         TC3_TRACE(it, 7, true);
+#endif
         if (++hb == 3) { hb = 0; hphase ^= 1u; }
       }
     }
@@ -252,10 +326,20 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const int stage = team;
     const bool tr = threadIdx.x == 0 || threadIdx.x == 256;
     const float headb = c_tc3_expo[0];
+#if TC3_HEAD_EARLY
+    float* dot_part = reinterpret_cast<float*>(sm + OFF_BIAS + 512 * team);
+    const uint32_t bar_dfull = sm_u + OFF_HEADW + 8 * (team * 4 + quad), bar_dfree = bar_dfull + 64;
+#else
     float* dot_part = reinterpret_cast<float*>(sm + (team ? OFF_DOT : OFF_BIAS));
+#endif
     const f32x2 NLOG2E2 = pk2(c_tc3_expo[1], c_tc3_expo[1]), TWOLOG2E2 = pk2(c_tc3_expo[3], c_tc3_expo[3]), ONE2 = pk2(1.0f, 1.0f);
     const f32x2 NTWO2 = pk2(-2.0f, -2.0f), NONE2 = pk2(-1.0f, -1.0f);
+#if TC3_SPLIT
+    // this warp's 16 columns inside each gate block of either hidden group: group g at + 128 g, gates at + 0 / 32 / 64 / 96
+    const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + 16 * half);
+#else
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
+#endif
     const int bar_id = 1 + team * 4 + quad;
     auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
     const int first = blockIdx.x + team * stride, step2 = 2 * stride;
@@ -281,6 +365,11 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       const ulonglong2 bi0 = __ldg(reinterpret_cast<const ulonglong2*>(pp_pre + 2 * H));
       TC3_TRACE(it, 8, tr);
       mbar_wait(bar_done + 8 * stage, phase, status);
+#if TC3_SPLIT
+      // both hidden groups: the gate loop overwrites the own-row images (its transpose buffer) from its first step on, so
+      // the second group's own-row MMAs must have retired too (issued a whole store / head phase ago: no wait in practice)
+      mbar_wait(bar_doneB + 8 * stage, phase, status);
+#endif
       tc_fence_after();
       TC3_TRACE(it, 9, tr);
       const float* __restrict__ pp = det_p + (size_t)max(ks, 0) * 192 + c0;  // this row's source contribution
@@ -293,11 +382,19 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       // as soon as step s has consumed its set, so they land during step s + 1 (same 32 accumulator registers)
       uint32_t A[2][16];
       auto ldstep = [&](int s, uint32_t* a) {
+#if TC3_SPLIT
+        const uint32_t cb = t0 + (uint32_t)((s >> 2) * 128 + (s & 3) * 4);   // steps 0-3: first hidden group, 4-7: second
+        tmem_ld4u(cb + 32, a);        // r
+        tmem_ld4u(cb + 64, a + 4);    // z
+        tmem_ld4u(cb + 96, a + 8);    // i_n
+        tmem_ld4u(cb, a + 12);        // h_n
+#else
         const uint32_t cb = t0 + (uint32_t)((s >> 1) * 8 + (s & 1) * 4);
         tmem_ld4u(cb + 64, a);        // r
         tmem_ld4u(cb + 128, a + 4);   // z
         tmem_ld4u(cb + 192, a + 8);   // i_n
         tmem_ld4u(cb, a + 12);        // h_n
+#endif
       };
       ldstep(0, A[0]);
       ldstep(1, A[1]);
@@ -342,6 +439,16 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         if (s + 2 < 8) ldstep(s + 2, a);
         if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
         else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
+#if TC3_SPLIT
+        if (s == 3) {
+          // first hidden group drained (the loads of steps 4 and 5 in flight read the other group): re-zero this warp's
+          // h_n columns and hand the group to the issuer -- its MMAs for the team's next tile run under steps 4-7
+          tmem_zero16(t0);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);
+        }
+#endif
       }
       };
       if (half == 0) gate_chunks(std::integral_constant<int, 0>{});
@@ -353,11 +460,26 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         dot = d0 + d1;
       }
       // accumulator stage drained: re-zero this warp's h_n columns for the accumulate-only own-row MMAs
+#if TC3_SPLIT
+      tmem_zero16(t0 + 128);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfreeB + 8 * stage);  // second hidden group drained
+#else
       tmem_zero32(t0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start
+#endif
       TC3_TRACE(it, 11, tr);
+#if TC3_HEAD_EARLY
+      if (half == 1) {
+        mbar_wait(bar_dfree, phase ^ 1u, status);  // the previous tile's partials have been read (normally long ago)
+        dot_part[r] = dot;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfull);
+      }
+#endif
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines).  Lane (rr, cc): float4 cc of
       // row rr; even cc from the hi image at the row's slot, odd cc from the lo image at row rr ^ 4
       {
@@ -389,6 +511,18 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       if (lane == 0) mbar_arrive(bar_hfree + 8 * hb);  // h images read back: the producers may write the next own rows
       TC3_TRACE(it, 12, tr);
       // head: the two column halves of a row live in warps (quad, 0) and (quad, 1) of the team
+#if TC3_HEAD_EARLY
+      if (half == 0) {
+        mbar_wait(bar_dfull, phase, status);
+        if (valid) {
+          const float lg = dot + dot_part[r] + (first_group ? headb : logit[row_cur]);
+          logit[row_cur] = lg;
+          if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dfree);
+      }
+#else
       if (half == 1) dot_part[r] = dot;
       named_bar_sync(bar_id, 64);
       if (half == 0 && valid) {
@@ -397,6 +531,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         if (last_group) score[row_cur] = tmpnn_sigmoid(lg);
       }
       named_bar_sync(bar_id, 64);
+#endif
       TC3_TRACE(it, 13, tr);
       T0 = T1; T1 = T2; srcv = srcv1;
       hb = hb == 0 ? 2 : hb - 1;  // (hb + 2) % 3

@@ -21,8 +21,8 @@ constexpr int IMAGE_BYTES = OFF_HEADB + 16;      // the part of the packed image
 constexpr int OFF_WT = IMAGE_BYTES;
 constexpr int OFF_BS = OFF_WT + 64 * 192 * 4;
 constexpr int IMAGE_TOTAL_BYTES = OFF_BS + 192 * 4;
-constexpr int OFF_BAR = IMAGE_BYTES;             // 12 mbarriers + tmem pointer, inside the alignment gap
-constexpr int OFF_DOT = OFF_BAR + 112;           // 128 floats: head partial sums of the upper column half
+constexpr int OFF_BAR = IMAGE_BYTES;             // up to 16 mbarriers + tmem pointer, inside the alignment gap
+constexpr int OFF_DOT = OFF_BAR + 144;           // 128 floats: head partial sums of the upper column half
 constexpr int OFF_A = 98 * 1024;                 // first A stage (1024-aligned)
 constexpr int A_PART = TCM * 128;                // [128 rows x 64 fp16] = 16 KB
 constexpr int A_STAGE = 4 * A_PART;              // x_hi, x_lo, h_hi, h_lo
@@ -250,6 +250,38 @@ __device__ __forceinline__ void issue_tile_mma_h_second(uint32_t sm_u, uint32_t 
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(192), 1);
+}
+// the same two halves for ONE hidden group (mp_step_tc3.cu, TC3_SPLIT): the kernel keeps its weight images group-major --
+// rows [96 g, 96 g + 96) = the three gates of hidden group g -- and the accumulator stage as two 128-column groups
+// h_n | r | z | i_n of 32 hidden units each, so every instruction has N = 96: the far-endpoint product lands in columns
+// [32, 128) of the group, the own-row product in [0, 96).  dg: first TMEM column of the group.
+__device__ __forceinline__ void issue_group_mma_x(uint32_t sm_u, uint32_t dg, uint32_t x_u, uint32_t xflags, int g) {
+  const uint32_t ax[3] = {x_u, x_u + A_PART, x_u};
+  const uint32_t bx[3] = {sm_u + OFF_BX_HI + 96 * 128 * g, sm_u + OFF_BX_HI + 96 * 128 * g, sm_u + OFF_BX_LO + 96 * 128 * g};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(dg + 32, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(96) | xflags, acc);
+      acc = 1;
+    }
+}
+__device__ __forceinline__ void issue_group_mma_h(uint32_t sm_u, uint32_t dg, uint32_t h_u, int g) {
+  const uint32_t ah[3] = {h_u, h_u + A_PART, h_u};
+  const uint32_t bh[3] = {sm_u + OFF_BH_HI + 96 * 128 * g, sm_u + OFF_BH_HI + 96 * 128 * g, sm_u + OFF_BH_LO + 96 * 128 * g};
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) umma_f16(dg, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(96), 1);
+}
+// 16 zero columns for this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(0u)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 // 32 zero columns for this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
