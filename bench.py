@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--no-cuda-graph', action='store_true')
     ap.add_argument('--no-deferred', action='store_true', help='move the hidden states in every window slide (A/B switch)')
     ap.add_argument('--list-aggregation', action='store_true', help='aggregate through the incidence lists (A/B switch)')
+    ap.add_argument('--fma-dets', action='store_true', help='detection rows on the fp32 FMA kernel (A/B switch)')
     ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the CPU-baseline sample (0 = auto)')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
@@ -690,7 +691,7 @@ def main():
     # ---- weak-scaling leg (the headline line): --seqs-per-gpu sequences on EVERY rank ------------------------------------
     seqs = make_sequences(a, 5 + rank * a.seqs_per_gpu, a.seqs_per_gpu)
     eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
-                      deferred_compaction=not a.no_deferred, block_aggregation=not a.list_aggregation)
+                      deferred_compaction=not a.no_deferred, block_aggregation=not a.list_aggregation, det_tensor=not a.fma_dets)
     for _ in range(max(a.warmup, 1)):
         eng.run()
     eng.results()

@@ -237,6 +237,21 @@ int tmpnn_mp_edge_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *
 int tmpnn_mp_det_fwd(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
                      int group, int num_groups, const float *node_pack, const float *agg, void *stream);
 
+/* The detection rows' half on the tensor cores, through the edge-step kernel of tmpnn_mp_edge_fwd_tc_pre in "detection mode":
+ * tiles over the detection segments of every slab (index_scratch2 = the scratch2 of tmpnn_index_build_structured), x = agg
+ * (from tmpnn_aggregate_dets[_blocks]) enters as fp16 hi / lo images written into det_img at the detections' rows, the
+ * weights are the NODE cell's image (tmpnn_pack_gru_tc of the node GRU + detection head, concat = 0).  Call it after the
+ * edge step of the same group: det_img / det_p (the edge step's scratch) are dead by then and reused.  det_tile_table:
+ * tmpnn_tc_det_tile_table_bytes() of scratch.  Sets TMPNN_FLAG_TC_RANGE like the edge step; tmpnn_mp_det_fwd_on_flag is the
+ * fp32 FMA re-run (tmpnn_mp_det_fwd that only runs when the status word holds one of flag_mask). */
+size_t tmpnn_tc_det_tile_table_bytes(int num_seqs, int cap_dets);
+int tmpnn_mp_det_fwd_tc(const tmpnn_graph *g, const tmpnn_index *ix, const void *index_scratch2, const float *h_in,
+                        float *h_out, int ldh, int group, int num_groups, const void *node_image, const float *agg,
+                        float *det_img, float *det_p, void *det_tile_table, void *stream);
+int tmpnn_mp_det_fwd_on_flag(const tmpnn_graph *g, const tmpnn_index *ix, const float *h_in, float *h_out, int ldh,
+                             int group, int num_groups, const float *node_pack, const float *agg, int flag_mask,
+                             void *stream);
+
 /* tmpnn_mp_edge_fwd that only runs when the sticky status word holds one of flag_mask at launch time (the test is made on
  * the device, so the call can sit in a CUDA graph): the engine enqueues it behind the tensor-core step with
  * flag_mask = TMPNN_FLAG_TC_RANGE, which re-runs a step whose activations left the fp16 split's range on the fp32 FMA

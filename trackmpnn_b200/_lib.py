@@ -98,6 +98,9 @@ _PROTOS = {
     'tmpnn_graph_force_det_scores': ([C.POINTER(Graph), C.POINTER(Index), _VP], _I),
     'tmpnn_status_ack': ([C.POINTER(Graph), _I, _I, _VP], _I),
     'tmpnn_mp_det_fwd': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _VP], _I),
+    'tmpnn_tc_det_tile_table_bytes': ([_I, _I], C.c_size_t),
+    'tmpnn_mp_det_fwd_tc': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP], _I),
+    'tmpnn_mp_det_fwd_on_flag': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _I, _VP], _I),
     'tmpnn_gru_tc_pack_bytes': ([], C.c_size_t),
     'tmpnn_pack_gru_tc': ([_VP] * 6 + [_I, _VP, _VP], _I),
     'tmpnn_tc_tile_table_bytes': ([_I, _I], C.c_size_t),
@@ -201,7 +204,7 @@ _LAUNCHES = [0]
 # kernels launched per C-ABI call (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     'tmpnn_pack_gru': 1, 'tmpnn_input_linear1': 1, 'tmpnn_input_bn_stats': 1, 'tmpnn_input_bn_relu_linear2': 1,
-    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 11, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_dets_blocks': 3, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
+    'tmpnn_index_build': 9, 'tmpnn_gat_aggregate_dets': 3, 'tmpnn_index_build_structured': 11, 'tmpnn_aggregate_dets': 1, 'tmpnn_aggregate_dets_blocks': 3, 'tmpnn_aggregate_edges': 1, 'tmpnn_mp_step_fwd': 3, 'tmpnn_mp_edge_fwd': 1, 'tmpnn_mp_det_fwd': 1, 'tmpnn_mp_det_fwd_tc': 3, 'tmpnn_mp_det_fwd_on_flag': 1, 'tmpnn_mp_edge_fwd_tc': 1, 'tmpnn_mp_edge_fwd_tc_pre': 3, 'tmpnn_pack_gru_tc': 1,
     'tmpnn_ypred_unpack': 1, 'tmpnn_ypred_pack': 1, 'tmpnn_coo_from_edges': 5, 'tmpnn_edges_from_coo': 1,
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1, 'tmpnn_mp_edge_fwd_on_flag': 1, 'tmpnn_graph_force_det_scores': 1,

@@ -712,9 +712,11 @@ __global__ void __launch_bounds__(NT, 1)
 k_mp_det(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh, int col,
          const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows, const float* __restrict__ agg,
          const float* __restrict__ pack, float* __restrict__ logit, float* __restrict__ score, int first_group,
-         int last_group, float* __restrict__ gates, const int32_t* __restrict__ phys) {
+         int last_group, float* __restrict__ gates, const int32_t* __restrict__ phys,
+         const int32_t* __restrict__ run_if_status, int run_if_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<H>& s = *reinterpret_cast<StepSmem<H>*>(smem_raw);
+  if (run_if_status && !(*run_if_status & run_if_mask)) return;  // conditional re-run (tmpnn_mp_det_fwd_on_flag)
   const int nd = *n_dets;
   const int total = (nd + TM - 1) / TM;
   if ((int)blockIdx.x >= total) return;
@@ -790,14 +792,15 @@ static int mp_edge_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
 }
 
 static int mp_det_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,
-                         int num_groups, const float* node_pack, const float* agg, float* gates, void* stream) {
+                         int num_groups, const float* node_pack, const float* agg, float* gates, void* stream,
+                         int run_if_mask = 0) {
   TMPNN_REQUIRE(g && ix && h_in && h_out && node_pack && agg, "null argument");
   TMPNN_REQUIRE(h_in != h_out, "h_in and h_out must be distinct buffers (Jacobi update)");
   TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
   if (!g_init_done) { int rc0 = tmpnn_init(); if (rc0) return rc0; }
   k_mp_det<<<TMPNN_SM_COUNT, NT, sizeof(StepSmem<H>), (cudaStream_t)stream>>>(
       h_in, h_out, ldh, group * H, ix->n_dets, ix->det_rows, agg, node_pack, g->logit, g->score, group == 0,
-      group == num_groups - 1, gates, g->phys);
+      group == num_groups - 1, gates, g->phys, run_if_mask ? g->status : nullptr, run_if_mask);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -817,6 +820,13 @@ extern "C" int tmpnn_mp_edge_fwd_on_flag(const tmpnn_graph* g, const tmpnn_index
 extern "C" int tmpnn_mp_det_fwd(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
                                 int group, int num_groups, const float* node_pack, const float* agg, void* stream) {
   return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, nullptr, stream);
+}
+
+extern "C" int tmpnn_mp_det_fwd_on_flag(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,
+                                        int group, int num_groups, const float* node_pack, const float* agg, int flag_mask,
+                                        void* stream) {
+  TMPNN_REQUIRE(flag_mask != 0, "flag_mask must name at least one status bit");
+  return mp_det_launch(g, ix, h_in, h_out, ldh, group, num_groups, node_pack, agg, nullptr, stream, flag_mask);
 }
 
 extern "C" int tmpnn_mp_det_fwd_train(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh,

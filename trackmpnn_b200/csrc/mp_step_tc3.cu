@@ -91,6 +91,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   extern __shared__ unsigned char smem_dyn[];
   const int total = *n_tiles;
   if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
+  // detection mode (tmpnn_mp_det_fwd_tc): the tiles cover the detection segments, the "far endpoint" of a row is the row
+  // itself (det_img then holds the images of the detections' aggregates), P' is one bias row and every row in range counts
+  const bool detm = (xflags & 1u) != 0;
+  xflags &= ~1u;
   unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sm_u = smem_u32(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,7 +247,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const uint32_t x_dst0 = sm_u + OFF_A + (uint32_t)(l >> 3) * A_PART + sw128(g, l & 7);  // + 2048 p: row g + 16 p
     const uint32_t h_off0 = sw128(g, l >> 1) + ((l & 1) << 3);
     // rows past the end of the slab repeat its last row; everything they produce is masked by the epilogue
-    auto ld_idx = [&](const int4 T) { return __ldg(dst + T.x + T.y + min(idx_row, T.z - 1)); };
+    auto ld_idx = [&](const int4 T) {
+      const int rr = T.y + min(idx_row, T.z - 1);
+      return detm ? rr : __ldg(dst + T.x + rr);
+    };
     auto ld_phys = [&](const int4 T) { return dfr ? __ldg(phys + T.x + T.y + min(idx_row, T.z - 1)) : 0; };
     auto issue_x = [&](uint32_t b, int iv) {
       const uint32_t s0 = x_dst0;
@@ -341,7 +348,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(stage * 256 + c0);
 #endif
     const int bar_id = 1 + team * 4 + quad;
-    auto ld_src = [&](const int4 T) { return __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
+    auto ld_src = [&](const int4 T) { return detm ? 0 : __ldg(src + T.x + (T.z - r > 0 ? T.y + r : 0)); };  // clamped to the slab's first row
     const int first = blockIdx.x + team * stride, step2 = 2 * stride;
     int4 T0 = ldtab(first), T1 = ldtab(first + step2);
     int srcv = ld_src(T0);
@@ -354,7 +361,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       const int it = 2 * (int)n + team;
       const size_t row_cur = (size_t)T0.x + T0.y + r;
       const bool valid = T0.z - r > 0 && srcv >= 0;
-      const int ks = __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
+      const int ks = detm ? 0 : __ldg(det_of_row + T0.x + max(srcv, 0));  // srcv landed during the team's previous tile
       const int4 T2 = ldtab(tile + 2 * step2);
       const int srcv1 = ld_src(T1);  // T1 landed a tile ago; consumed by the team's next tile
       // the first step's P' terms are fetched before the wait (cold lines: an L2 round trip that would otherwise sit
@@ -555,6 +562,94 @@ int tmpnn_init_tc3() {
 
 extern "C" size_t tmpnn_tc_tile_table_bytes(int num_seqs, int cap_rows) {
   return (size_t)num_seqs * (size_t)tmpnn_div_up(cap_rows, TCM) * sizeof(int4) + sizeof(int4);
+}
+
+// ---- detection rows on the same kernel (tmpnn_mp_det_fwd_tc) ---------------------------------------------------------------
+// Tiles over the detection segments of every slab (contiguous rows: the kernel writes its output at consecutive logical rows).
+// tab[0].x = number of tiles, tiles from tab[1] on.
+__global__ void __launch_bounds__(1024) k_det_tile_table(const SlabSegs* __restrict__ segs, int num_seqs, int cap_rows, int cap_tiles,
+                                                         int4* __restrict__ tab, int32_t* __restrict__ status) {
+  __shared__ int sm[33];
+  int carry = 0;
+  for (int s0 = 0; s0 < num_seqs; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    int cnt = 0;
+    if (s < num_seqs) {
+      const SlabSegs& sg = segs[s];
+      for (int q = 0; q < sg.nseg; ++q)
+        if (sg.eord[q] < 0) cnt += (sg.start[q + 1] - sg.start[q] + TCM - 1) / TCM;
+    }
+    int total;
+    int o = carry + block_exclusive_scan(cnt, sm, &total);
+    if (s < num_seqs && carry + total <= cap_tiles) {
+      const SlabSegs& sg = segs[s];
+      for (int q = 0; q < sg.nseg; ++q) {
+        if (sg.eord[q] >= 0) continue;
+        const int r0 = sg.start[q], len = sg.start[q + 1] - r0;
+        for (int j = 0; j * TCM < len; ++j) tab[1 + o++] = make_int4(s * cap_rows, r0 + j * TCM, len - j * TCM, 0);
+      }
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    if (carry > cap_tiles) { atomicOr(status, TMPNN_FLAG_DET_CAPACITY); carry = 0; }
+    tab[0] = make_int4(carry, 0, 0, 0);
+  }
+}
+// Half-warp per detection: the fp16 hi / lo image of its aggregate at the detection's logical row of det_img (dead since the
+// edge step finished with the far-endpoint images); thread 0 of the grid writes the bias-only P' row the kernel adds.
+__global__ void __launch_bounds__(256)
+k_agg_image(const float* __restrict__ agg, const int32_t* __restrict__ n_dets, const int32_t* __restrict__ det_rows,
+            const unsigned char* __restrict__ image, float* __restrict__ det_img, int ldh, int col, float* __restrict__ det_p,
+            int32_t* __restrict__ status) {
+  if (blockIdx.x == 0 && threadIdx.x < 192) {
+    const float b = reinterpret_cast<const float*>(image + OFF_BS)[threadIdx.x];
+    const float wscale = *reinterpret_cast<const float*>(image + OFF_HEADB + 8);
+    det_p[threadIdx.x] = threadIdx.x < 2 * H ? -LOG2E * b : wscale * b;   // k_det_prepare's P' of an all-zero source
+  }
+  const int k = (blockIdx.x * 256 + threadIdx.x) >> 4, l = threadIdx.x & 15;
+  if (k >= *n_dets) return;
+  const float4 v = ldg4(agg + (size_t)k * H + 4 * l);
+  uint2 hi, lo;
+  float amax = 0.f;
+  split4(v, hi, lo, amax);
+  unsigned char* ib = reinterpret_cast<unsigned char*>(det_img + (size_t)det_rows[k] * ldh + col);
+  *reinterpret_cast<uint2*>(ib + 8 * l) = hi;
+  *reinterpret_cast<uint2*>(ib + 128 + 8 * l) = lo;
+  if (amax > 60000.f) atomicOr(status, TMPNN_FLAG_TC_RANGE);
+}
+
+extern "C" size_t tmpnn_tc_det_tile_table_bytes(int num_seqs, int cap_dets) {
+  return ((size_t)num_seqs * MAXSEG + (size_t)tmpnn_div_up(cap_dets, TCM) + 2) * sizeof(int4);
+}
+
+extern "C" int tmpnn_mp_det_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix, const void* index_scratch2, const float* h_in,
+                                   float* h_out, int ldh, int group, int num_groups, const void* node_image, const float* agg,
+                                   float* det_img, float* det_p, void* det_tile_table, void* stream) {
+  TMPNN_REQUIRE(g && ix && index_scratch2 && h_in && h_out && node_image && agg && det_img && det_p && det_tile_table, "null argument");
+  TMPNN_REQUIRE(h_in != h_out && det_img != h_in && det_img != h_out, "h_in, h_out and det_img must be distinct buffers");
+  TMPNN_REQUIRE(ldh % 4 == 0 && group >= 0 && group < num_groups && ldh >= num_groups * H, "bad ldh / group");
+  TMPNN_REQUIRE(((uintptr_t)det_tile_table & 15) == 0, "det_tile_table must be 16-byte aligned");
+  int rc = tmpnn_init();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int4* tab = (int4*)det_tile_table;
+  if (group == 0) {
+    const int cap_tiles = (int)(tmpnn_tc_det_tile_table_bytes(g->num_seqs, ix->cap_dets) / sizeof(int4)) - 2;
+    k_det_tile_table<<<1, 1024, 0, st>>>((const SlabSegs*)index_scratch2, g->num_seqs, g->cap_rows, cap_tiles, tab, g->status);
+    TMPNN_LAUNCH_CHECK();
+  }
+  k_agg_image<<<tmpnn_div_up(ix->cap_dets, 16), 256, 0, st>>>(agg, ix->n_dets, ix->det_rows, (const unsigned char*)node_image, det_img,
+                                                            ldh, group * H, det_p, g->status);
+  TMPNN_LAUNCH_CHECK();
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_expo, (const unsigned char*)node_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice, st));
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_tail, (const unsigned char*)node_image + OFF_BIAS + 3 * H * 4, 512, 0, cudaMemcpyDeviceToDevice, st));
+  // x = the aggregate enters with its own sign (no negation), bit 0: detection mode
+  k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
+      h_in, h_out, ldh, group * H, g->src, g->dst, reinterpret_cast<const int32_t*>(tab), tab + 1, (const unsigned char*)node_image,
+      g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys, det_img, det_p, ix->det_of_row, 1u);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
 }
 
 int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const float* h_in, float* h_out, int ldh, int group,

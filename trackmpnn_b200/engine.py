@@ -36,7 +36,7 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True, block_aggregation=True):
+                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True, block_aggregation=True, det_tensor=True):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
@@ -99,6 +99,7 @@ class TrackEngine:
         self.keep = torch.zeros(n_all, dtype=torch.uint8, device=dev)
         self.new_of_old = z(n_all)
         self.agg = torch.empty((self.index.cap_dets, H), dtype=torch.float32, device=dev)
+        self._aggs = None   # per-group aggregates when the detection rows run on the tensor cores (kept for the FMA re-run)
         self.a_scratch = torch.empty((self.cap_new, H), dtype=torch.float32, device=dev)
         # work counters, accumulated on the device
         self.edge_updates = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -124,6 +125,11 @@ class TrackEngine:
             self.S * self.cap_rows >= F_.TENSOR_MIN_ROWS if tensor_cores == 'auto' else bool(tensor_cores))
         self._tc_scratch = {}
         self._gat_scratch = {}
+        # detection rows on the tensor cores too: the edge-step kernel in detection mode (needs the prepared-endpoint kernel's
+        # scratch and the structured index's segment tables)
+        self.det_tensor = bool(det_tensor) and self.tensor and self.structured_index and tensor_kernel in ('auto', 'pre')
+        if self.det_tensor:
+            self._aggs = [self.agg] + [torch.empty_like(self.agg) for _ in range(self.G - 1)]
         # block-structured aggregation (needs the structured index): per slab one run sum per (source, edge block) and one
         # column partial per (stripe of 32 sources, detection)
         self._agg_blocks = None
@@ -166,18 +172,20 @@ class TrackEngine:
         self.index.build(g, self.st['active'], structured=self.structured_index)
         packs = F_.packed_cells(model)
         tc = F_.packed_cells_tc(model) if self.tensor else None
+        tc_node = F_.packed_cells_tc(model, node=True) if self.det_tensor else None
         for grp in range(self.G):
+            agg = self._aggs[grp] if self.det_tensor else self.agg
             concat = int(model.factor_grus[grp].msg_type == 'concat')
             if self.profile is not None:
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
-            F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, self.agg, self._gat_scratch,
+            F_.aggregate_for_dets(model.factor_grus[grp], g, self.index, h_in, self.ldh, grp * H, agg, self._gat_scratch,
                                   blocks=self._agg_blocks)
             if self.check_aggregation is not None and self._agg_blocks is not None and model.factor_grus[grp].gat is None:
-                ref = torch.empty_like(self.agg)
+                ref = torch.empty_like(agg)
                 L.call('tmpnn_aggregate_dets', g.c, self.index.c, L.ptr(h_in), self.ldh, grp * H, L.ptr(ref), st)
                 nd = int(self.index.n_dets.item())
-                self.check_aggregation.append((nd, float((ref[:nd] - self.agg[:nd]).abs().max()) if nd else 0.0,
+                self.check_aggregation.append((nd, float((ref[:nd] - agg[:nd]).abs().max()) if nd else 0.0,
                                                float(ref[:nd].abs().max()) if nd else 0.0))
             if self.profile is not None:
                 a1.record()
@@ -192,10 +200,13 @@ class TrackEngine:
             if self.profile is not None:
                 e1.record()
                 self.profile.append((e0, e1, self.index.n_edges.clone(), a0, a1, self.n_new[1:2].clone()))
-            L.call('tmpnn_mp_det_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
-                   L.ptr(packs[grp][1]), L.ptr(self.agg), st)
+            if self.det_tensor:
+                F_.det_step_tc(g, self.index, h_in, h_out, self.ldh, grp, self.G, tc_node[grp], agg, self._tc_scratch)
+            else:
+                L.call('tmpnn_mp_det_fwd', g.c, self.index.c, L.ptr(h_in), L.ptr(h_out), self.ldh, grp, self.G,
+                       L.ptr(packs[grp][1]), L.ptr(agg), st)
         if self.tensor:
-            F_.rerun_edges_if_out_of_range(model, g, self.index, h_in, h_out, self.ldh, packs)
+            F_.rerun_edges_if_out_of_range(model, g, self.index, h_in, h_out, self.ldh, packs, aggs=self._aggs)
         if not self.tp_classifier:
             # --no-tp-classifier (infer.py:54-57, 77-80): detections count as true positives in association and decoding
             L.call('tmpnn_graph_force_det_scores', g.c, self.index.c, st)

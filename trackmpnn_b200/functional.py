@@ -46,26 +46,29 @@ def packed_cells(model):
     return cache.packs
 
 
-def packed_cells_tc(model):
-    """fp16 hi/lo UMMA weight images of the edge cells (tensor-core path)."""
-    cache = model.__dict__.setdefault('_tmpnn_pack_cache_tc', _PackCache())
+def packed_cells_tc(model, node=False):
+    """fp16 hi/lo UMMA weight images of the edge cells (tensor-core path); node=True: of the node cells with the detection
+    head (tmpnn_mp_det_fwd_tc)."""
+    cache = model.__dict__.setdefault('_tmpnn_pack_cache_tc_node' if node else '_tmpnn_pack_cache_tc', _PackCache())
+    head = model.output_transform_node if node else model.output_transform_edge
     params = []
     for gru in model.factor_grus:
-        cell = gru.edge_gru
+        cell = gru.node_gru if node else gru.edge_gru
         params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
-    params += [model.output_transform_edge.weight, model.output_transform_edge.bias]
+    params += [head.weight, head.bias]
     key = tuple((p.data_ptr(), p._version) for p in params)
     if cache.key != key:
         packs = []
         nbytes = int(L.lib().tmpnn_gru_tc_pack_bytes())
         for g, gru in enumerate(model.factor_grus):
-            cell, head = gru.edge_gru, model.output_transform_edge
+            cell = gru.node_gru if node else gru.edge_gru
             out = torch.empty(nbytes, dtype=torch.uint8, device=cell.weight_ih.device)
             hw = head.weight.detach()[0, g * H:(g + 1) * H]
-            # 'concat': the image holds the far-endpoint half W_ih[:, 64:128] (only tmpnn_mp_edge_fwd_tc_pre takes it)
+            # 'concat': the image holds the far-endpoint half W_ih[:, 64:128] (only tmpnn_mp_edge_fwd_tc_pre takes it);
+            # the node cell's input is always the 64-wide aggregate
             L.call('tmpnn_pack_gru_tc', L.ptr(cell.weight_ih.detach()), L.ptr(cell.weight_hh.detach()),
                    L.ptr(cell.bias_ih.detach()), L.ptr(cell.bias_hh.detach()), L.ptr(hw), L.ptr(head.bias.detach()),
-                   int(gru.msg_type == 'concat'), L.ptr(out), L.stream())
+                   int(gru.msg_type == 'concat' and not node), L.ptr(out), L.stream())
             packs.append(out)
         cache.key, cache.packs = key, packs
     return cache.packs
@@ -214,7 +217,18 @@ def edge_step_tc(model, graph, index, h_in, h_out, ldh, g, G, image, scratch, ke
            L.ptr(img), L.ptr(dp), L.ptr(tab), st)
 
 
-def rerun_edges_if_out_of_range(model, graph, index, h_in, h_out, ldh, packs):
+def det_step_tc(graph, index, h_in, h_out, ldh, g, G, node_image, agg, scratch):
+    """Detection rows of feature group g on the tensor cores (tmpnn_mp_det_fwd_tc): after edge_step_tc(kernel='pre') of the
+    same group, whose det_img / det_p scratch it reuses; needs the structured index (segment tables in index._scratch2)."""
+    nb = int(L.lib().tmpnn_tc_det_tile_table_bytes(graph.num_seqs, index.cap_dets))
+    tab = scratch.get('det_tile_tab')
+    if tab is None or tab.numel() * 4 < nb:
+        tab = scratch['det_tile_tab'] = torch.empty(((nb + 15) // 16, 4), dtype=torch.int32, device=h_in.device)
+    L.call('tmpnn_mp_det_fwd_tc', graph.c, index.c, L.ptr(index._scratch2), L.ptr(h_in), L.ptr(h_out), ldh, g, G,
+           L.ptr(node_image), L.ptr(agg), L.ptr(scratch['det_img']), L.ptr(scratch['det_p']), L.ptr(tab), L.stream())
+
+
+def rerun_edges_if_out_of_range(model, graph, index, h_in, h_out, ldh, packs, aggs=None):
     """Behind the tensor-core edge step: if an activation left the range of the fp16 split (|h| > 6e4, e.g. a trained
     input transform with large outputs; TMPNN_FLAG_TC_RANGE), the association rows of every feature group are re-run by
     the fp32 FMA kernel.  The test happens on the device (the launches exit at once otherwise), so this sits inside the
@@ -225,6 +239,10 @@ def rerun_edges_if_out_of_range(model, graph, index, h_in, h_out, ldh, packs):
         concat = int(model.factor_grus[g].msg_type == 'concat')
         L.call('tmpnn_mp_edge_fwd_on_flag', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, concat, L.ptr(packs[g][0]),
                L.FLAG_TC_RANGE, st)
+    if aggs is not None:   # the detection rows went through the tensor cores too (aggs[g]: group g's aggregates, kept)
+        for g in range(G):
+            L.call('tmpnn_mp_det_fwd_on_flag', graph.c, index.c, L.ptr(h_in), L.ptr(h_out), ldh, g, G, L.ptr(packs[g][1]),
+                   L.ptr(aggs[g]), L.FLAG_TC_RANGE, st)
     L.call('tmpnn_status_ack', graph.c, L.FLAG_TC_RANGE, L.NOTE_TC_RANGE_RERUN, st)
 
 

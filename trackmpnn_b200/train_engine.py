@@ -276,7 +276,7 @@ def batch_loss(model, batch, tp_classifier=True):
 def invalidate_weight_caches(model):
     """Drops the packed weight images cached on ``model`` (functional.packed_cells*, the backward images).  They are keyed by
     the parameters' version counters, which a CUDA-graph replay of an optimizer step does not advance."""
-    for k in ('_tmpnn_pack_cache', '_tmpnn_pack_cache_tc'):
+    for k in ('_tmpnn_pack_cache', '_tmpnn_pack_cache_tc', '_tmpnn_pack_cache_tc_node'):
         model.__dict__.pop(k, None)
     sc = model.__dict__.get('_tmpnn_bwd_tc')
     if sc:
