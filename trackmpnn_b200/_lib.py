@@ -276,7 +276,7 @@ class ZeroArena:
     fill kernel each (~40 per step).  ``zeros()`` falls back to ``torch.zeros`` when no arena is active or it is full."""
     active = None
 
-    def __init__(self, device, nfloats=1 << 22):
+    def __init__(self, device, nfloats=1 << 23):
         self.buf = torch.zeros(nfloats, dtype=torch.float32, device=device)
         self.off = 0
 

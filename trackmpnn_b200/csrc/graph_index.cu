@@ -386,6 +386,11 @@ __global__ void __launch_bounds__(256) k_block_futoff(const int32_t* __restrict_
   cnt[2 * k + 1] = acc;
 }
 
+// Incidence lists by formula, one warp per list piece: a source's run in an edge block (future list: nt consecutive rows,
+// checked against src / dst on the way) or a detection's column of the block in front of it (past list: A rows nt apart, no
+// loads at all).  List offsets are fetched once per piece, every store is coalesced.  Measured per frame on configs[2]
+// (16 M rows): row-parallel form with two integer divisions and eight dependent loads per row 144 us, this form 136 us, a
+// warp walking 32 pieces after fetching their headers at once 201 us (too few warps in flight for the checking loads).
 __global__ void __launch_bounds__(256) k_block_fill(const SlabSegs* __restrict__ segs, const int32_t* __restrict__ src,
                                                     const int32_t* __restrict__ dst, int cap_rows,
                                                     const int32_t* __restrict__ det_of_row, const int32_t* __restrict__ n_dets,
@@ -395,24 +400,37 @@ __global__ void __launch_bounds__(256) k_block_fill(const SlabSegs* __restrict__
   const int s = blockIdx.y;
   const SlabSegs& sg = segs[s];
   const size_t base = (size_t)s * cap_rows;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
   int bad = 0;
+  int item0 = 0;   // pieces of the blocks in front of this one
   for (int q = 0; q + 1 < sg.nseg; ++q) {
     if (sg.eord[q] < 0 || sg.eord[q + 1] >= 0) continue;
     const int e0 = sg.start[q], d0 = sg.start[q + 1], nt = sg.start[q + 2] - d0;
     if (nt <= 0 || (d0 - e0) % nt != 0) continue;
-    const int A = (d0 - e0) / nt, ne = d0 - e0;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ne; p += gridDim.x * blockDim.x) {
-      // past lists, written detection-major (consecutive threads -> consecutive slots)
-      const int j = p / A, a = p % A;
-      inc[seg_ptr[2 * det_of_row[base + d0 + j]] + a] = (int32_t)(base + e0 + (size_t)a * nt + j);
-      // future lists, written in row order (a run is one contiguous stretch of its source's list)
-      const int ar = p / nt, jr = p % nt;
-      const size_t e = base + e0 + p;
-      const int sd = src[base + e0 + (size_t)ar * nt];
-      if (src[e] != sd || dst[e] != d0 + jr) bad = 1;
-      const int ks = det_of_row[base + sd];
-      inc[seg_ptr[2 * ks + 1] + futoff[(size_t)ks * MAXE + sg.eord[q]] + jr] = (int32_t)e;
+    const int A = (d0 - e0) / nt, eo = sg.eord[q];
+    // pieces [item0, item0 + A): runs, [item0 + A, item0 + A + nt): columns; dealt round-robin to the slab's warps
+    int first = warp - item0 % nwarps;
+    if (first < 0) first += nwarps;
+    for (int it = first; it < A + nt; it += nwarps) {
+      if (it < A) {
+        const int a = it;
+        const size_t r0 = base + e0 + (size_t)a * nt;
+        const int sd = src[r0];
+        const int ks = det_of_row[base + sd];
+        int32_t* out = inc + seg_ptr[2 * ks + 1] + futoff[(size_t)ks * MAXE + eo];
+        for (int j = lane; j < nt; j += 32) {
+          if (src[r0 + j] != sd || dst[r0 + j] != d0 + j) bad = 1;
+          out[j] = (int32_t)(r0 + j);
+        }
+      } else {
+        const int j = it - A;
+        int32_t* out = inc + seg_ptr[2 * det_of_row[base + d0 + j]];
+        const int32_t r0 = (int32_t)(base + e0 + j);
+        for (int a = lane; a < A; a += 32) out[a] = r0 + a * nt;
+      }
     }
+    item0 += A + nt;
   }
   if (bad) atomicOr(status, TMPNN_FLAG_UNSTRUCTURED);
 }
@@ -497,7 +515,8 @@ extern "C" int tmpnn_index_build_structured(const tmpnn_graph* g, const tmpnn_in
   k_block_futoff<<<tmpnn_div_up(ix->cap_dets, 256), 256, 0, st>>>(ix->n_dets, futlen, cnt, segs, ix->det_rows, g->cap_rows);
   TMPNN_LAUNCH_CHECK();
   TMPNN_CUDA_TRY(scan_exclusive(cnt, ix->seg_ptr, ix->n_dets, 2, 0, 2 * (long long)ix->cap_dets, sums, st));
-  dim3 grid_e(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 8), 64)), S);
+  // 8 warps per CTA, one list piece per warp at a time: enough CTAs per slab to fill the machine when the slabs are few
+  dim3 grid_e(max(1, min(tmpnn_div_up(g->cap_rows, 256 * 8), max(64, tmpnn_div_up(TMPNN_SM_COUNT * 8, S)))), S);
   k_block_fill<<<grid_e, 256, 0, st>>>(segs, g->src, g->dst, g->cap_rows, ix->det_of_row, ix->n_dets, futlen, ix->seg_ptr, ix->inc,
                                        g->status);
   TMPNN_LAUNCH_CHECK();

@@ -471,7 +471,10 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
 // h: 64 hi halves then 64 lo halves in the row's 256 B), which is what the producers copy for the far endpoint of
 // an association row; (b) P'[k] = the row's source-side contribution to the input gates, fp32 FMA:
 //   P = h W_ih[:, 0:64]^T,  P'[0:128) = -log2e (P + b_ih + b_hh),  P'[128:192) = P + b_ih.
-constexpr int PREP_D = 4;  // detections per warp pass: every weight read from shared memory feeds 4 FMAs
+#ifndef TMPNN_PREP_D
+#define TMPNN_PREP_D 8
+#endif
+constexpr int PREP_D = TMPNN_PREP_D;  // detections per warp pass: every weight read from shared memory feeds PREP_D FMAs
 constexpr int PREP_SMEM = (64 * 192 + 8 * PREP_D * 64 + 192) * 4;
 __global__ void __launch_bounds__(256)
 k_det_prepare(const float* __restrict__ h_in, int ldh, int col, const int32_t* __restrict__ n_dets,
