@@ -413,7 +413,7 @@ def run_c4_leg(a, dev):
     model = TrackMPNN('2d', synth.num_categories(b.dataset), 64, 0, 'diff').to(dev).eval()
     seqs = make_sequences(b, 7000, b.seqs_per_gpu)
     eng = TrackEngine(model, seqs, cur_win_size=b.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
-                      block_aggregation=not a.list_aggregation)
+                      block_aggregation=False if a.list_aggregation else 'auto')
     for _ in range(2):
         eng.run()
     eng.results()
@@ -691,7 +691,7 @@ def main():
     # ---- weak-scaling leg (the headline line): --seqs-per-gpu sequences on EVERY rank ------------------------------------
     seqs = make_sequences(a, 5 + rank * a.seqs_per_gpu, a.seqs_per_gpu)
     eng = TrackEngine(model, seqs, cur_win_size=a.win, ret_win_size=0, use_cuda_graph=not a.no_cuda_graph,
-                      deferred_compaction=not a.no_deferred, block_aggregation=not a.list_aggregation, det_tensor=not a.fma_dets)
+                      deferred_compaction=not a.no_deferred, block_aggregation=False if a.list_aggregation else 'auto', det_tensor=not a.fma_dets)
     for _ in range(max(a.warmup, 1)):
         eng.run()
     eng.results()

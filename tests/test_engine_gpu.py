@@ -166,7 +166,7 @@ def test_block_aggregation_equals_incidence_list_aggregation(cfg, deferred):
         X, y = synth.make_sequence(sd, T, D, 'kitti', timestamps=ts)
         seqs.append((X[0], y[0]))
     eng = TrackEngine(model, seqs, cur_win_size=cfg['win'], ret_win_size=cfg['ret'], use_cuda_graph=False,
-                      deferred_compaction=deferred)
+                      deferred_compaction=deferred, block_aggregation=True)
     assert eng._agg_blocks is not None
     eng.check_aggregation = []
     eng.run()

@@ -36,7 +36,7 @@ def worst_case_rows(frame_counts, window):
 class TrackEngine:
     def __init__(self, model, sequences, cur_win_size=5, ret_win_size=0, device=None, cap_rows=None,
                  use_cuda_graph=True, tensor_cores='auto', use_hungarian=False, structured_index=True,
-                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True, block_aggregation=True, det_tensor=True):
+                 deferred_compaction=True, tensor_kernel='auto', tp_classifier=True, block_aggregation='auto', det_tensor=True):
         """sequences: list of (X [ND, F] float32, y [ND, 2] = [ts, track_id]) host arrays.
 
         deferred_compaction: the slide of the window does not move the hidden states; the next step reads them
@@ -44,7 +44,8 @@ class TrackEngine:
         densely, so the state only ever crosses HBM once per step in each direction.
 
         block_aggregation: with the structured index the detections' aggregation reads each dense edge block once
-        (tmpnn_aggregate_dets_blocks) instead of walking the incidence lists."""
+        (tmpnn_aggregate_dets_blocks) instead of walking the incidence lists; 'auto' = whenever the tensor-core path is on
+        (large batches).  det_tensor: the detection rows run on the tensor cores as well (tmpnn_mp_det_fwd_tc)."""
         self.model = model
         self.tp_classifier = bool(tp_classifier)   # False: infer.py's --no-tp-classifier
         self.dev = device if device is not None else next(model.parameters()).device
@@ -133,6 +134,8 @@ class TrackEngine:
         # block-structured aggregation (needs the structured index): per slab one run sum per (source, edge block) and one
         # column partial per (stripe of 32 sources, detection)
         self._agg_blocks = None
+        if block_aggregation == 'auto':   # three launches instead of one: only pays where the graphs are large
+            block_aggregation = self.tensor
         if self.structured_index and block_aggregation:
             cap_runs = max_dets * min(self.W + self.R, 64)
             cap_cpart = self.cap_rows // 32 + max_dets + 64
