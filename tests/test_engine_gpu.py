@@ -147,6 +147,41 @@ def test_structured_index_equals_general_index(ret):
         assert sa[-1] == 2 * int(a.n_edges.item())
 
 
+@pytest.mark.parametrize('tensor', [False, True])
+@pytest.mark.parametrize('msg_type,seeds', [('diff', [35, 40, 41, 43, 45, 52]), ('concat', [40, 44, 48, 61, 65])])
+def test_engine_two_feature_groups(msg_type, seeds, tensor):
+    """features '2d+temp' (two feature groups, models/track_mpnn.py:17-33): every group has its own input transform, GRU
+    cells and aggregate, the heads read both groups' states.  Decoded tracks bit-exact against the oracle loop on the FMA
+    path and on the tensor-core path (edge step + detection rows in detection mode, one aggregate buffer per group kept
+    for the range-overflow re-run); seeds chosen on the oracle for a decision margin > 5e-4."""
+    from trackmpnn_b200.engine import TrackEngine
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    model = TrackMPNN('2d+temp', 3, 64, 0, msg_type)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.mul_(20.0)
+        model.output_transform_edge.bias.fill_(0.0)
+    model = model.to(dev).eval()
+    params = _params(model)
+    seqs = []
+    for sd in seeds:
+        X, y = synth.make_sequence(sd, 8 + (sd % 7), 4 + (sd % 4), 'kitti')
+        X, y = X[0], y[0]
+        ph = 2 * np.pi * y[:, 0:1] / 10.0
+        seqs.append((np.concatenate((X, np.sin(ph), np.cos(ph)), 1).astype(np.float32), y))
+    eng = TrackEngine(model, seqs, cur_win_size=5, ret_win_size=0, use_cuda_graph=True, tensor_cores=tensor)
+    assert eng.G == 2 and eng.det_tensor == tensor
+    outs, stats = eng.run().results()
+    for (X, y), got in zip(seqs, outs):
+        want, st = run_infer(params, X, y, features='2d+temp', msg_type=msg_type, cur_win_size=5, ret_win_size=0,
+                             record_margin=True)
+        assert st['margin'] > 1e-4
+        np.testing.assert_array_equal(got, want[:, 1])
+
+
 @pytest.mark.parametrize('deferred', [False, True])
 @pytest.mark.parametrize('cfg', [dict(win=5, ret=1, seqs=[(30, 12, 6), (49, 14, 9), (34, 10, 5), (52, 11, 7), (54, 16, 4)], gap=(49, 52)),
                                  dict(win=20, ret=2, stock=True, seqs=[(803, 30, 6), (804, 27, 5), (805, 24, 7)], gap=()),
