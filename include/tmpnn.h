@@ -252,6 +252,12 @@ int tmpnn_mp_det_fwd_on_flag(const tmpnn_graph *g, const tmpnn_index *ix, const 
                              int group, int num_groups, const float *node_pack, const float *agg, int flag_mask,
                              void *stream);
 
+/* The batched engine's device-side work counters and frame clock in one launch (no reference equivalent; bench.py's
+ * edge-updates/s and frames/s are read from them): *edge_updates += *n_edges, *det_updates += *n_dets, *frames_done += sum of
+ * active[0..num_seqs), *t_dev += 1.  Every (destination, source) pair may be NULL. */
+int tmpnn_graph_counters(int64_t *edge_updates, const int32_t *n_edges, int64_t *det_updates, const int32_t *n_dets,
+                         int64_t *frames_done, const int32_t *active, int num_seqs, int32_t *t_dev, void *stream);
+
 /* tmpnn_mp_edge_fwd that only runs when the sticky status word holds one of flag_mask at launch time (the test is made on
  * the device, so the call can sit in a CUDA graph): the engine enqueues it behind the tensor-core step with
  * flag_mask = TMPNN_FLAG_TC_RANGE, which re-runs a step whose activations left the fp16 split's range on the fp32 FMA

@@ -788,6 +788,34 @@ extern "C" int tmpnn_edges_from_coo(const int64_t* idx, const float* val, int64_
   return TMPNN_OK;
 }
 
+// The engine's work counters and clock in one launch (they were five tiny PyTorch kernels per frame): every pair is optional.
+__global__ void __launch_bounds__(256) k_counters(int64_t* __restrict__ edge_updates, const int32_t* __restrict__ n_edges,
+                                                  int64_t* __restrict__ det_updates, const int32_t* __restrict__ n_dets,
+                                                  int64_t* __restrict__ frames_done, const int32_t* __restrict__ active,
+                                                  int num_seqs, int32_t* __restrict__ t_dev) {
+  __shared__ int sm[8];
+  int c = 0;
+  if (frames_done && active)
+    for (int s = threadIdx.x; s < num_seqs; s += blockDim.x) c += active[s] != 0 ? active[s] : 0;
+  c = warp_sum_i(c);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += sm[w];
+    if (frames_done && active) *frames_done += tot;
+    if (edge_updates && n_edges) *edge_updates += *n_edges;
+    if (det_updates && n_dets) *det_updates += *n_dets;
+    if (t_dev) *t_dev += 1;
+  }
+}
+extern "C" int tmpnn_graph_counters(int64_t* edge_updates, const int32_t* n_edges, int64_t* det_updates, const int32_t* n_dets,
+                                    int64_t* frames_done, const int32_t* active, int num_seqs, int32_t* t_dev, void* stream) {
+  k_counters<<<1, 256, 0, (cudaStream_t)stream>>>(edge_updates, n_edges, det_updates, n_dets, frames_done, active, num_seqs, t_dev);
+  TMPNN_LAUNCH_CHECK();
+  return TMPNN_OK;
+}
+
 extern "C" int tmpnn_graph_associate(const tmpnn_graph* g, const tmpnn_index* ix, int mode, const int32_t* active,
                                      void* stream) {
   TMPNN_REQUIRE(g && ix, "null argument");

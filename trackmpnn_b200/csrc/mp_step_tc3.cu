@@ -37,14 +37,15 @@ extern "C" int tmpnn_debug_set_tc3_trace(long long* buf, int cap) {
 #define TC3_TRACE(it_, slot_, cond_) do { } while (0)
 #endif
 
-// -log2e 2^-k and 2 log2e 2^-k of the launch's weight image (k_pack_gru_tc's power-of-two pre-scale), refreshed by a
-// device-to-symbol copy in front of every launch: constant-bank operands cost the epilogue no registers (it sits at the
-// 72-register ceiling; the same constants read from shared memory added 28 bytes of spills)
-__constant__ float c_tc3_expo[4];
-// b_hn (x 2^k) | head weights of the launch's image, refreshed the same way.  The epilogue's chunk loop is instantiated
-// per column half, so every offset into this table is a compile-time constant and the values arrive as constant-bank
-// operands: no shared-memory broadcast loads (sixteen LDS.128 per warp and tile), no registers held across the math
-__constant__ float c_tc3_tail[128];
+// Per-launch constants of the weight image, refreshed by ONE device-to-symbol copy in front of every launch (the three pieces
+// are adjacent in the packed image): [0, 64) b_hn (x 2^k) | [64, 128) head weights | [128, 132) head bias, -log2e 2^-k, 2^k,
+// 2 log2e 2^-k (k_pack_gru_tc's power-of-two pre-scale).  Constant-bank operands cost the epilogue no registers (it sits at
+// the 72-register ceiling; the same constants read from shared memory added 28 bytes of spills), and because the epilogue's
+// chunk loop is instantiated per column half every offset into the table is a compile-time constant: no shared-memory
+// broadcast loads (sixteen LDS.128 per warp and tile), no registers held across the math
+__constant__ float c_tc3_const[132];
+#define c_tc3_tail c_tc3_const
+#define c_tc3_expo (c_tc3_const + 128)
 
 // Two measured experiments, kept behind flags (profiles/r02_ab_tc3_split.txt, r02_tc_trace_split.txt; parity green for both):
 // TC3_SPLIT: the accumulator stage is released to the MMA issuer in two halves (hidden units 0-15 | 32-47 after the first
@@ -642,8 +643,7 @@ extern "C" int tmpnn_mp_det_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix, 
   k_agg_image<<<tmpnn_div_up(ix->cap_dets, 16), 256, 0, st>>>(agg, ix->n_dets, ix->det_rows, (const unsigned char*)node_image, det_img,
                                                             ldh, group * H, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
-  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_expo, (const unsigned char*)node_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice, st));
-  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_tail, (const unsigned char*)node_image + OFF_BIAS + 3 * H * 4, 512, 0, cudaMemcpyDeviceToDevice, st));
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_const, (const unsigned char*)node_image + OFF_BIAS + 3 * H * 4, 528, 0, cudaMemcpyDeviceToDevice, st));
   // x = the aggregate enters with its own sign (no negation), bit 0: detection mode
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, reinterpret_cast<const int32_t*>(tab), tab + 1, (const unsigned char*)node_image,
@@ -660,8 +660,7 @@ int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
     k_tile_table<<<grid, 256, 0, st>>>(g->n_rows, ix->tile128_ptr, g->cap_rows, (int4*)tile_table);
     TMPNN_LAUNCH_CHECK();
   }
-  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_expo, (const unsigned char*)edge_image + OFF_HEADB, 16, 0, cudaMemcpyDeviceToDevice, st));
-  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_tail, (const unsigned char*)edge_image + OFF_BIAS + 3 * H * 4, 512, 0, cudaMemcpyDeviceToDevice, st));
+  TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_const, (const unsigned char*)edge_image + OFF_BIAS + 3 * H * 4, 528, 0, cudaMemcpyDeviceToDevice, st));
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, ix->tile128_ptr + g->num_seqs, (const int4*)tile_table,

@@ -29,6 +29,7 @@ constexpr int A_STAGE = 4 * A_PART;              // x_hi, x_lo, h_hi, h_lo
 constexpr int SMEM_BYTES = OFF_A + 2 * A_STAGE + 1024;  // + slack to 1024-align the base
 static_assert(OFF_DOT + 512 <= OFF_A, "barriers and head partials must fit in the gap");
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+static_assert(OFF_HEADW == OFF_BIAS + 1024 && OFF_HEADB == OFF_HEADW + 256, "b_hn | head weights | head constants must be adjacent (one constant copy)");
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- PTX helpers -----------------------------------------------------------------------------

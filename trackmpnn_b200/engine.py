@@ -213,8 +213,8 @@ class TrackEngine:
         if not self.tp_classifier:
             # --no-tp-classifier (infer.py:54-57, 77-80): detections count as true positives in association and decoding
             L.call('tmpnn_graph_force_det_scores', g.c, self.index.c, st)
-        self.edge_updates += self.index.n_edges
-        self.det_updates += self.index.n_dets
+        L.call('tmpnn_graph_counters', L.ptr(self.edge_updates), L.ptr(self.index.n_edges), L.ptr(self.det_updates),
+               L.ptr(self.index.n_dets), None, None, 0, None, st)
 
     def _start(self):
         g = self.ga
@@ -285,8 +285,8 @@ class TrackEngine:
         if ph:
             ph[3].record()
             self.profile_phases.append(ph)
-        self.frames_done += self.st['active'].sum()
-        self.t_dev += 1
+        L.call('tmpnn_graph_counters', None, None, None, None, L.ptr(self.frames_done), L.ptr(self.st['active']), self.S,
+               L.ptr(self.t_dev), st)
 
     # ---- driver --------------------------------------------------------------------------------
     def reset(self):
