@@ -386,6 +386,7 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
         tmem_ld8u(t0 + 192 + ch * 8, ahn);
         const int j0 = c0 + ch * 8;
         tmem_ld_wait();
+        f32x2 gr[4], gz[4], gn[4], gh[4];   // TRAIN: the chunk's 8 columns of every gate, stored as one 256-bit word each
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(bias + j0 + 4 * v);
@@ -394,7 +395,6 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
           const ulonglong2 bh = *reinterpret_cast<const ulonglong2*>(bias + 3 * H + j0 + 4 * v);
           const ulonglong2 hw = *reinterpret_cast<const ulonglong2*>(headw + j0 + 4 * v);
           f32x2 o[2];
-          f32x2 gr[2], gz[2], gn[2], gh[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int i = 4 * v + 2 * e;  // columns j0 + i, j0 + i + 1
@@ -408,14 +408,19 @@ k_mp_edge_tc(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh,
             const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[4 * ch + 2 * v + e]), ng);  // n + z (h - n) = (1 - z) n + z h
             o[e] = ov;
             dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
-            if (TRAIN) { gr[e] = rg; gz[e] = zg; gn[e] = ng; gh[e] = mul2(add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), INVS2); }
+            if (TRAIN) {
+              gr[2 * v + e] = rg; gz[2 * v + e] = zg; gn[2 * v + e] = ng;
+              gh[2 * v + e] = mul2(add2(pk2u(ahn[i], ahn[i + 1]), e ? bh.y : bh.x), INVS2);
+            }
           }
-          if (TRAIN && valid) {   // columns j0 + 4 v .. + 3 of the four gates of this row
-            float* gp = gates + row_cur * (4 * H) + j0 + 4 * v;
-            *reinterpret_cast<ulonglong2*>(gp) = make_ulonglong2(gr[0], gr[1]);
-            *reinterpret_cast<ulonglong2*>(gp + H) = make_ulonglong2(gz[0], gz[1]);
-            *reinterpret_cast<ulonglong2*>(gp + 2 * H) = make_ulonglong2(gn[0], gn[1]);
-            *reinterpret_cast<ulonglong2*>(gp + 3 * H) = make_ulonglong2(gh[0], gh[1]);
+          if (TRAIN && valid && v == 1) {
+            // columns j0 .. j0 + 7 of the four gates of this row: one 256-bit store (a full 32-byte sector) per gate -- the
+            // rows of a warp are 1 KB apart, so 16-byte stores wrote half sectors with twice the requests
+            float* gp = gates + row_cur * (4 * H) + j0;
+            st_global_256(gp, gr);
+            st_global_256(gp + H, gz);
+            st_global_256(gp + 2 * H, gn);
+            st_global_256(gp + 3 * H, gh);
           }
           *reinterpret_cast<ulonglong2*>(tbuf + lane * 128 + (((2 * ch + v) ^ (lane & 7)) << 4)) = make_ulonglong2(o[0], o[1]);
         }

@@ -194,6 +194,10 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// 32 bytes (four packed pairs) in one st.global.v4.b64: sm_100's 256-bit store (STG.E.256), address 32-byte aligned
+__device__ __forceinline__ void st_global_256(float* p, const f32x2* v) {
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+}
 __device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
