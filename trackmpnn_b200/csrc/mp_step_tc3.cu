@@ -62,6 +62,12 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_HEAD_EARLY
 #define TC3_HEAD_EARLY 0
 #endif
+// TC3_ST256: the transposed read-back writes h' with sm_100's 256-bit stores (8 rows x 128 B per instruction instead of 4):
+// 1.4 % slower (2.80 -> 2.84 ms, profiles/r02_ab_tc3_st256.txt) -- the stores were full lines already; where the 256-bit
+// store pays is the training kernel's row-strided gate stores (mp_step_tc.cu: 150 -> 103 us)
+#ifndef TC3_ST256
+#define TC3_ST256 0
+#endif
 
 namespace {
 
@@ -490,6 +496,36 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 #endif
       // transposed read-back: each store instruction writes 4 rows x 128 B (full lines).  Lane (rr, cc): float4 cc of
       // row rr; even cc from the hi image at the row's slot, odd cc from the lo image at row rr ^ 4
+#if TC3_ST256
+      {
+        // 256-bit stores: lane (rgrp, rsel, j) takes columns 8 j .. 8 j + 7 of row 8 k + rgrp + 4 rsel -- the hi-image chunk of
+        // the row and the lo-image chunk of row ^ 4 (rows r and r + 4 share a quarter warp: their swizzled slots are disjoint,
+        // so the shared-memory reads stay conflict-free); four store instructions of 8 rows x 128 B instead of eight of 4 rows
+        const int j = lane & 3, rl0 = (lane >> 3) + 4 * ((lane >> 2) & 1);
+        const unsigned char* a_hi = h_hi + sw128(quad * 32 + rl0, 4 * half + j);
+        const unsigned char* a_lo = h_lo + sw128(quad * 32 + (rl0 ^ 4), 4 * half + j);
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[2 * k] = *reinterpret_cast<const float4*>(a_hi + k * 1024);
+          v[2 * k + 1] = *reinterpret_cast<const float4*>(a_lo + k * 1024);
+        }
+        float* op = out0 + (size_t)rl0 * ldh + 8 * j;
+        const size_t step = (size_t)ldh * 8;
+        const uint32_t vm = vmask >> rl0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.u32 p, %0, 0;\n\t"
+              "@p st.global.v8.f32 [%1], {%2, %3, %4, %5, %6, %7, %8, %9};\n\t}"
+              ::"r"((vm >> (8 * k)) & 1u), "l"(op), "f"(v[2 * k].x), "f"(v[2 * k].y), "f"(v[2 * k].z), "f"(v[2 * k].w),
+                "f"(v[2 * k + 1].x), "f"(v[2 * k + 1].y), "f"(v[2 * k + 1].z), "f"(v[2 * k + 1].w)
+              : "memory");
+          op += step;
+        }
+      }
+#else
       {
         // all eight shared-memory reads first, then eight predicated stores off one running pointer (no branches, no
         // 64-bit multiply per row)
@@ -515,6 +551,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
           op += step;
         }
       }
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hfree + 8 * hb);  // h images read back: the producers may write the next own rows
       TC3_TRACE(it, 12, tr);
