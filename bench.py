@@ -500,7 +500,7 @@ def run_train_ddp_leg(a, dev, rank, world, barrier, reduce_):
             'replicas_in_sync': bool(abs(hi - lo) <= 1e-9 * max(1.0, abs(hi))),
             'ddp_gradient_vs_single_gpu': {'max_abs_err_over_max_abs_grad': err, 'ok': bool(err <= 1e-4),
                                            'what': f'all-reduced sum of {world} x {Bc}-chunk gradients vs one GPU over the {Bc * world} chunks '
-                                                   '(float atomics in the weight-gradient sums: not bit-identical)'}}
+                                                   '(another grouping of the per-rank sums: equal to round-off, not bit-identical; each run by itself is bit-reproducible)'}}
 
 
 def prepare_passes(eng):

@@ -318,11 +318,14 @@ int tmpnn_mp_det_fwd_train(const tmpnn_graph *g, const tmpnn_index *ix, const fl
  * ([n][192] each), dhself = dh' z ([n][64]).  Accumulates (atomically) the bias gradients of both cells
  * (gbias_*: [2][192] = d bias_ih | d bias_hh), the 64-wide head weight slices and, when the pointers are
  * non-null (pass them for group 0 only), the head biases. */
+/* partials: NULL = the CTAs add their bias / head-weight sums atomically (order not reproducible); else
+ * tmpnn_gate_bwd_partial_floats() floats of scratch: per-CTA sums, added in CTA order by a second kernel (bit-reproducible). */
+size_t tmpnn_gate_bwd_partial_floats(void);
 int tmpnn_gate_bwd(int n_rows, const int32_t *src, const float *gates, const float *h_prev, const float *h_new,
                    int ldh, int col, const float *dh_out, const float *dlogits, const float *dscores,
                    const float *score, const float *head_w_edge, const float *head_w_node, float *dgi, float *dgh,
                    float *dhself, float *gbias_edge, float *gbias_node, float *ghw_edge, float *ghw_node,
-                   float *ghb_edge, float *ghb_node, void *stream);
+                   float *ghb_edge, float *ghb_node, float *partials, void *stream);
 
 /* C[rc(i)][0:n] (+)= A[ra(i)][0:192] . W[192][n] for rows i < R (R = *r_dev or r_host) whose
  * mask[ra(i)] >= 0; ra = a_rows ? a_rows[i] : i, rc likewise.  n = 64 or 128.  (dx = dgi . W_ih,

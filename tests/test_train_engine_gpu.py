@@ -222,3 +222,29 @@ def test_graphed_train_step_equals_eager_steps():
         np.testing.assert_allclose(bm[1].running_mean.cpu().numpy(), br[1].running_mean.cpu().numpy(), rtol=0, atol=5e-3)
         np.testing.assert_allclose(bm[1].running_var.cpu().numpy(), br[1].running_var.cpu().numpy(), rtol=1e-3, atol=1e-6)
         assert int(bm[1].num_batches_tracked) == int(br[1].num_batches_tracked)
+
+
+def test_batched_training_step_is_bit_reproducible():
+    """Two optimizer steps of the batched trainer on the tensor-core path (40 detections / frame: > 8192 rows per step), run
+    twice from the same weights: every parameter equal BIT FOR BIT.  The weight gradients of the GRU cells come from the
+    tcgen05 contraction's per-SM partials, those of the input transform from per-chunk partials, the bias / head gradients
+    from tmpnn_gate_bwd's per-CTA partials -- all added in a fixed order, no float atomics on this path."""
+    from trackmpnn_b200.models.track_mpnn import TrackMPNN
+    from trackmpnn_b200.train_engine import TrainBatch, GraphedTrainStep
+    dev = torch.device('cuda:0')
+    chunks, _ = _kitti_chunks(dev, [80, 81, 82, 83, 84, 85], 40)
+    batch = TrainBatch(chunks, dev)
+    finals = []
+    for run in range(2):
+        torch.manual_seed(5)
+        model = TrackMPNN('2d', 3, 64, 0, 'diff').to(dev).train()
+        step = GraphedTrainStep(model, batch, lr=1e-3, weight_decay=5e-4)
+        for _ in range(2):
+            step.eager()
+        torch.cuda.synchronize()
+        finals.append([p.detach().cpu().numpy().copy() for p in model.parameters()])
+    changed = 0
+    for a, b in zip(*finals):
+        np.testing.assert_array_equal(a, b)
+        changed += int(np.abs(a).sum() > 0)
+    assert changed > 10

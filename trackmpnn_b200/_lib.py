@@ -111,7 +111,8 @@ _PROTOS = {
     'tmpnn_mp_det_fwd_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_step_fwd_train': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
     'tmpnn_mp_step_fwd_train_agg': ([C.POINTER(Graph), C.POINTER(Index), _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP], _I),
-    'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 16, _I),
+    'tmpnn_gate_bwd_partial_floats': ([], C.c_size_t),
+    'tmpnn_gate_bwd': ([_I] + [_VP] * 4 + [_I, _I] + [_VP] * 17, _I),
     'tmpnn_rows_times_w': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _VP], _I),
     'tmpnn_rows_outer': ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP], _I),
     'tmpnn_bwd_tc_image_bytes': ([], C.c_size_t),
@@ -210,7 +211,7 @@ KERNELS_PER_CALL = {
     'tmpnn_graph_associate': 2, 'tmpnn_graph_append': 4, 'tmpnn_graph_decode': 2, 'tmpnn_graph_prune_mask': 2,
     'tmpnn_graph_compact': 4, 'tmpnn_graph_phys_identity': 1, 'tmpnn_mp_edge_fwd_on_flag': 1, 'tmpnn_graph_force_det_scores': 1,
     'tmpnn_status_ack': 1, 'tmpnn_graph_counters': 1,
-    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_edge_fwd_tc_train': 1, 'tmpnn_mp_det_fwd_train': 1, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 1, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_rows_gemm_tc': 2, 'tmpnn_pack_w_tc': 1, 'tmpnn_scatter_bwd': 2,
+    'tmpnn_mp_step_fwd_train': 3, 'tmpnn_mp_edge_fwd_tc_train': 1, 'tmpnn_mp_det_fwd_train': 1, 'tmpnn_mp_step_fwd_train_agg': 2, 'tmpnn_gat_aggregate_dets_train': 3, 'tmpnn_gat_bwd': 4, 'tmpnn_gate_bwd': 2, 'tmpnn_rows_times_w': 1, 'tmpnn_rows_outer': 1, 'tmpnn_rows_gemm_tc': 2, 'tmpnn_pack_w_tc': 1, 'tmpnn_scatter_bwd': 2,
     'tmpnn_build_features': 1, 'tmpnn_input_bwd': 1, 'tmpnn_input_bwd_groups': 2, 'tmpnn_input_bn_groups_fwd': 3, 'tmpnn_loss_targets': 2, 'tmpnn_loss_ce_fwd': 2, 'tmpnn_loss_ce_bwd': 1, 'tmpnn_loss_focal_fwd': 2, 'tmpnn_loss_wbce_fwd': 2, 'tmpnn_loss_wbce_bwd': 1, 'tmpnn_rows_move': 1,
     'tmpnn_loss_focal_bwd': 1, 'tmpnn_graph_associate_hungarian': 2, 'tmpnn_lsap_solve': 1,
 }

@@ -32,6 +32,7 @@ constexpr int H = TMPNN_HIDDEN;
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_acc(float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 
+constexpr int GB_PART = 5 * H + 4;   // per CTA and row type: five 64-wide sums + the head-bias sum (+ pad)
 __global__ void __launch_bounds__(256)
 k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict__ gates,
            const float* __restrict__ h_prev, const float* __restrict__ h_new, int ldh, int col,
@@ -40,7 +41,8 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
            float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dhself,
            float* __restrict__ gb_e, float* __restrict__ gb_d,   // [2][192]: d bias_ih | d bias_hh
            float* __restrict__ ghw_e, float* __restrict__ ghw_d, // [64] head weight slices
-           float* __restrict__ ghb_e, float* __restrict__ ghb_d) // [1] head biases (group 0 only, else null)
+           float* __restrict__ ghb_e, float* __restrict__ ghb_d, // [1] head biases (group 0 only, else null)
+           float* __restrict__ partials)  // null: the CTAs add atomically; else [grid][2][GB_PART]: summed by k_gate_bwd_reduce
 {
   __shared__ float4 red[16][16];
   __shared__ float redb[16];
@@ -96,7 +98,9 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
         float v = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) v += reinterpret_cast<const float*>(&red[k][j >> 2])[j & 3];
-        if (v != 0.f) {
+        if (partials) {
+          partials[((size_t)blockIdx.x * 2 + t) * GB_PART + q * H + j] = v;
+        } else if (v != 0.f) {
           if (q < 3) atomicAdd(&gb[q * H + j], v);                  // d bias_ih
           if (q < 2) atomicAdd(&gb[3 * H + q * H + j], v);          // d bias_hh (r, z)
           if (q == 3) atomicAdd(&gb[3 * H + 2 * H + j], v);         // d bias_hh (n)
@@ -108,12 +112,57 @@ k_gate_bwd(int n_rows, const int32_t* __restrict__ src, const float* __restrict_
     if (l == 0) redb[rl] = accb[t];
     __syncthreads();
     float* ghb = t ? ghb_d : ghb_e;
-    if (threadIdx.x == 0 && ghb) {
+    if (threadIdx.x == 0 && (ghb || partials)) {
       float v = 0.f;
       for (int k = 0; k < 16; ++k) v += redb[k];
-      if (v != 0.f) atomicAdd(ghb, v);
+      if (partials) partials[((size_t)blockIdx.x * 2 + t) * GB_PART + 5 * H] = v;
+      else if (v != 0.f) atomicAdd(ghb, v);
     }
   }
+}
+// The CTAs' partial sums of k_gate_bwd added in CTA order (16 groups of CTAs per output, combined in a fixed order): the bias and
+// head-weight gradients come out bit-reproducible, which the float atomics could not give.  Outputs o < 640: (row type t, sum q,
+// hidden unit j); o = 640, 641: the two head biases.
+__global__ void __launch_bounds__(1024)
+k_gate_bwd_reduce(const float* __restrict__ partials, int n_blocks, float* __restrict__ gb_e, float* __restrict__ gb_d,
+                  float* __restrict__ ghw_e, float* __restrict__ ghw_d, float* __restrict__ ghb_e, float* __restrict__ ghb_d) {
+  __shared__ float part[16][64];
+  const int il = threadIdx.x & 63, pg = threadIdx.x >> 6;
+  const int o = blockIdx.x * 64 + il;
+  const bool bias = o >= 2 * 5 * H;
+  const int t = bias ? o - 2 * 5 * H : o / (5 * H), rem = bias ? 5 * H : o % (5 * H);
+  float s = 0.f;
+  if (t < 2) {
+    const float* p = partials + (size_t)t * GB_PART + rem;
+    for (int b0 = pg; b0 < n_blocks; b0 += 16 * 8) {   // eight loads in flight, added in CTA order
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int b = b0 + 16 * q;
+        v[q] = b < n_blocks ? p[(size_t)b * 2 * GB_PART] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += v[q];
+    }
+  }
+  part[pg][il] = s;
+  __syncthreads();
+  if (pg != 0 || t >= 2) return;
+  float v = part[0][il];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) v += part[k][il];
+  if (bias) {
+    float* ghb = t ? ghb_d : ghb_e;
+    if (ghb) *ghb += v;
+    return;
+  }
+  const int q = rem / H, j = rem % H;
+  float* gb = t ? gb_d : gb_e;
+  float* ghw = t ? ghw_d : ghw_e;
+  if (q < 3) gb[q * H + j] += v;                  // d bias_ih
+  if (q < 2) gb[3 * H + q * H + j] += v;          // d bias_hh (r, z)
+  if (q == 3) gb[3 * H + 2 * H + j] += v;         // d bias_hh (n)
+  if (q == 4) ghw[j] += v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -678,18 +727,24 @@ extern "C" int tmpnn_rows_move(const float* src, float* dst, const int32_t* seg_
   return TMPNN_OK;
 }
 
+extern "C" size_t tmpnn_gate_bwd_partial_floats(void) { return (size_t)TMPNN_SM_COUNT * 8 * 2 * GB_PART; }
 extern "C" int tmpnn_gate_bwd(int n_rows, const int32_t* src, const float* gates, const float* h_prev, const float* h_new,
                               int ldh, int col, const float* dh_out, const float* dlogits, const float* dscores,
                               const float* score, const float* head_w_edge, const float* head_w_node, float* dgi,
                               float* dgh, float* dhself, float* gbias_edge, float* gbias_node, float* ghw_edge,
-                              float* ghw_node, float* ghb_edge, float* ghb_node, void* stream) {
+                              float* ghw_node, float* ghb_edge, float* ghb_node, float* partials, void* stream) {
   TMPNN_REQUIRE(src && gates && h_prev && h_new && score && dgi && dgh && dhself, "null argument");
   if (n_rows <= 0) return TMPNN_OK;
   const int blocks = min(tmpnn_div_up(n_rows, 16), TMPNN_SM_COUNT * 8);
   k_gate_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, src, gates, h_prev, h_new, ldh, col, dh_out, dlogits, dscores,
                                                       score, head_w_edge, head_w_node, dgi, dgh, dhself, gbias_edge,
-                                                      gbias_node, ghw_edge, ghw_node, ghb_edge, ghb_node);
+                                                      gbias_node, ghw_edge, ghw_node, ghb_edge, ghb_node, partials);
   TMPNN_LAUNCH_CHECK();
+  if (partials) {
+    k_gate_bwd_reduce<<<11, 1024, 0, (cudaStream_t)stream>>>(partials, blocks, gbias_edge, gbias_node, ghw_edge, ghw_node, ghb_edge,
+                                                            ghb_node);
+    TMPNN_LAUNCH_CHECK();
+  }
   return TMPNN_OK;
 }
 

@@ -469,6 +469,15 @@ def _input_groups_forward(model, x, h_cur, ldh):
     return [(x.xd, xi, orow, nd, ne, per[k]) for k, (xi, orow, nd, ne) in enumerate(groups)]
 
 
+def _gate_bwd_partials(model, dev):
+    """Scratch of tmpnn_gate_bwd: per-CTA bias / head-weight sums, added in CTA order (reproducible) instead of atomically."""
+    sc = model.__dict__.setdefault('_tmpnn_bwd_tc', {})
+    t = sc.get('gate_partials')
+    if t is None or t.device != dev:
+        t = sc['gate_partials'] = torch.empty(int(L.lib().tmpnn_gate_bwd_partial_floats()), dtype=torch.float32, device=dev)
+    return t
+
+
 def _bwd_tc_partials(model, dev):
     """Scratch of the tensor-core backward contraction: one weight-gradient partial per SM."""
     sc = model.__dict__.setdefault('_tmpnn_bwd_tc', {})
@@ -623,7 +632,7 @@ class _MPStepFn(torch.autograd.Function):
                    L.ptr(dh_out), L.ptr(dlogits), L.ptr(dscores), L.ptr(ctx.p), L.ptr(hw_edge) + 4 * col,
                    L.ptr(hw_node) + 4 * col, L.ptr(dgi), L.ptr(dgh), L.ptr(dhself), L.ptr(gb_e), L.ptr(gb_d),
                    L.ptr(g_hw_edge) + 4 * col, L.ptr(g_hw_node) + 4 * col,
-                   L.ptr(g_hb_edge) if g == 0 else None, L.ptr(g_hb_node) if g == 0 else None, st)
+                   L.ptr(g_hb_edge) if g == 0 else None, L.ptr(g_hb_node) if g == 0 else None, L.ptr(_gate_bwd_partials(model, dev)), st)
             if not adj(b + 8):
                 grads[b + 8] += gb_e[0]; grads[b + 9] += gb_e[1]
             if not adj(b + 12):
