@@ -68,6 +68,15 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_ST256
 #define TC3_ST256 0
 #endif
+// TC3_LD1: single-set accumulator drain (see the gate loop): the next step's TMEM loads issued under the current step's MUFU
+// chains, P' / previous-state loads in front of tcgen05.wait::ld -- no difference (2.76 vs 2.76 ms,
+// profiles/r02_ab_tc3_ld1.txt): neither the TMEM-load nor the L1 latency at the top of a step is what bounds the gate phase
+#ifndef TC3_LD1
+#define TC3_LD1 0
+#endif
+#if TC3_LD1 && TC3_SPLIT
+#error "TC3_LD1 and TC3_SPLIT are separate experiments"
+#endif
 
 namespace {
 
@@ -392,6 +401,72 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       f32x2 dot2 = 0ull;
       auto gate_chunks = [&](auto half_c) {
       constexpr int HALF = decltype(half_c)::value;
+#if TC3_LD1
+      // Accumulator drain in steps of 4 columns x 4 gates out of ONE set of 16 registers: a step first folds its accumulators
+      // into the four pre-activations (8 packed registers), then issues the TMEM loads of the NEXT step into the registers it
+      // has just freed, so they land under the step's MUFU chains; everything a step reads from memory (P', previous
+      // state) is requested in front of tcgen05.wait::ld.  (wait::ld waits for ALL outstanding loads: the two-set form,
+      // which issued the loads of step s + 2 at the end of step s, waited for them at the top of step s + 1.)
+      uint32_t A[16];
+      auto ldstep = [&](int s, uint32_t* a) {
+        const uint32_t cb = t0 + (uint32_t)((s >> 1) * 8 + (s & 1) * 4);
+        tmem_ld4u(cb + 64, a);        // r
+        tmem_ld4u(cb + 128, a + 4);   // z
+        tmem_ld4u(cb + 192, a + 8);   // i_n
+        tmem_ld4u(cb, a + 12);        // h_n
+      };
+      ldstep(0, A);
+      f32x2 hp[4];
+      uint32_t off = 0;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int ch = s >> 1, v = s & 1;
+        const ulonglong2 br = s == 0 ? br0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
+        const ulonglong2 bz = s == 0 ? bz0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
+        const ulonglong2 bi = s == 0 ? bi0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+        if (v == 0) {
+          off = sw128(r, 4 * half + ch);
+          const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
+          const uint4 vl = *reinterpret_cast<const uint4*>(h_lo + off);
+          const __half2* ph = reinterpret_cast<const __half2*>(&vh);
+          const __half2* pl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 fh = __half22float2(ph[i]), fl = __half22float2(pl[i]);
+            hp[i] = add2(pk2(fh.x, fh.y), pk2(fl.x, fl.y));
+          }
+          __syncwarp();
+        }
+        const int jc = 32 * HALF + 8 * ch + 4 * v;  // compile-time after unrolling
+        const ulonglong2 bh = make_ulonglong2(pk2(c_tc3_tail[jc], c_tc3_tail[jc + 1]), pk2(c_tc3_tail[jc + 2], c_tc3_tail[jc + 3]));
+        const ulonglong2 hw = make_ulonglong2(pk2(c_tc3_tail[64 + jc], c_tc3_tail[64 + jc + 1]), pk2(c_tc3_tail[64 + jc + 2], c_tc3_tail[64 + jc + 3]));
+        tmem_ld_wait();
+        f32x2 xr[2], xz[2], hb[2], ib[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = 2 * e;
+          xr[e] = fma2(pk2u(A[i], A[i + 1]), NLOG2E2, e ? br.y : br.x);
+          xz[e] = fma2(pk2u(A[4 + i], A[5 + i]), NLOG2E2, e ? bz.y : bz.x);
+          hb[e] = add2(pk2u(A[12 + i], A[13 + i]), e ? bh.y : bh.x);
+          ib[e] = add2(pk2u(A[8 + i], A[9 + i]), e ? bi.y : bi.x);
+        }
+        if (s + 1 < 8) ldstep(s + 1, A);
+        f32x2 o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const f32x2 rg = rcp_2(add2(ex2_2(xr[e]), ONE2));
+          const f32x2 zg = rcp_2(add2(ex2_2(xz[e]), ONE2));
+          const f32x2 u = fma2(rg, hb[e], ib[e]);
+          const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
+          const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);
+          o[e] = ov;
+          dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
+        }
+        if (v == 0) *reinterpret_cast<ulonglong2*>(h_hi + off) = make_ulonglong2(o[0], o[1]);
+        else        *reinterpret_cast<ulonglong2*>(h_lo + sw128(r ^ 4, 4 * half + ch)) = make_ulonglong2(o[0], o[1]);
+      }
+      };
+#else
       // software-pipelined accumulator drain: two sets of 4 columns x 4 gates; the TMEM loads of step s + 2 are issued
       // as soon as step s has consumed its set, so they land during step s + 1 (same 32 accumulator registers)
       uint32_t A[2][16];
@@ -465,6 +540,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 #endif
       }
       };
+#endif
       if (half == 0) gate_chunks(std::integral_constant<int, 0>{});
       else gate_chunks(std::integral_constant<int, 1>{});
       float dot;
