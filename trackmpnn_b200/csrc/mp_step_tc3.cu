@@ -68,6 +68,12 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_ST256
 #define TC3_ST256 0
 #endif
+// TC3_RCP5: one reciprocal for the update gate and the tanh together (5 MUFU per element instead of 6, see the gate loop): parity
+// green, 1 % slower (2.80 -> 2.82 ms, profiles/r02_ab_tc3_rcp5.txt; 136 instead of 88 bytes of spills) -- 17 % fewer MUFU
+// instructions buy nothing, i.e. the MUFU pipe is not what bounds the gate phase either
+#ifndef TC3_RCP5
+#define TC3_RCP5 0
+#endif
 // TC3_LD1: single-set accumulator drain (see the gate loop): the next step's TMEM loads issued under the current step's MUFU
 // chains, P' / previous-state loads in front of tcgen05.wait::ld -- no difference (2.76 vs 2.76 ms,
 // profiles/r02_ab_tc3_ld1.txt): neither the TMEM-load nor the L1 latency at the top of a step is what bounds the gate phase
@@ -518,10 +524,22 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         for (int e = 0; e < 2; ++e) {
           const int i = 2 * e;
           const f32x2 rg = rcp_2(add2(ex2_2(fma2(pk2u(a[i], a[i + 1]), NLOG2E2, e ? br.y : br.x)), ONE2));
+#if TC3_RCP5
+          // five MUFU per element instead of six: z = 1 / (1 + B) and n = (E - 1) / (E + 1) share ONE reciprocal,
+          //   h' = n + z (h - n) = ((E - 1) B + h (E + 1)) / ((E + 1) (1 + B)),   B = 2^(-log2e x_z), E = 2^(2 log2e u),
+          // both exponents clamped at 57 (2^57 = 1.4e17: z < 1e-17, 1 - n < 2e-17, the product stays finite)
+          const f32x2 B = ex2_2(min2c(fma2(pk2u(a[4 + i], a[5 + i]), NLOG2E2, e ? bz.y : bz.x), 57.0f));
+          const f32x2 u = fma2(rg, add2(pk2u(a[12 + i], a[13 + i]), e ? bh.y : bh.x), add2(pk2u(a[8 + i], a[9 + i]), e ? bi.y : bi.x));
+          const f32x2 E = ex2_2(min2c(mul2(u, TWOLOG2E2), 57.0f));
+          const f32x2 t2 = add2(E, ONE2);
+          const f32x2 num = fma2(add2(E, NONE2), B, mul2(hp[2 * v + e], t2));
+          const f32x2 ov = mul2(num, rcp_2(mul2(t2, add2(B, ONE2))));
+#else
           const f32x2 zg = rcp_2(add2(ex2_2(fma2(pk2u(a[4 + i], a[5 + i]), NLOG2E2, e ? bz.y : bz.x)), ONE2));
           const f32x2 u = fma2(rg, add2(pk2u(a[12 + i], a[13 + i]), e ? bh.y : bh.x), add2(pk2u(a[8 + i], a[9 + i]), e ? bi.y : bi.x));
           const f32x2 ng = fma2(rcp_2(add2(ex2_2(mul2(u, TWOLOG2E2)), ONE2)), NTWO2, ONE2);
           const f32x2 ov = fma2(zg, fma2(ng, NONE2, hp[2 * v + e]), ng);
+#endif
           o[e] = ov;
           dot2 = fma2(ov, e ? hw.y : hw.x, dot2);
         }

@@ -198,6 +198,12 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ void st_global_256(float* p, const f32x2* v) {
   asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
 }
+// element-wise min(v, c) of a packed pair
+__device__ __forceinline__ f32x2 min2c(f32x2 v, float c) {
+  float a, b;
+  up2(v, a, b);
+  return pk2(fminf(a, c), fminf(b, c));
+}
 __device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
   float a, b;
   up2(v, a, b);
