@@ -41,8 +41,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// TMPNN_TC_WAIT_HINT_NS > 0: suspend-time hint of the hardware wait (the thread sleeps until the phase completes or the hint
+// expires, instead of the short system default): fewer spin iterations of idle warps without delaying their wake-up.
+// Measured with 2 us and 20 us (profiles/r02_ab_tc3_waithint.txt): no difference -- the spinning warps do not cost the epilogue
+// issue slots
+#ifndef TMPNN_TC_WAIT_HINT_NS
+#define TMPNN_TC_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if TMPNN_TC_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)TMPNN_TC_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -50,6 +66,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
