@@ -424,12 +424,27 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       ldstep(0, A);
       f32x2 hp[4];
       uint32_t off = 0;
+#if TC3_LD1 == 2
+      // P' one step ahead: the three 16-byte loads of step s + 1 are issued at the top of step s (the 28 KB L1 beside 227 KB of
+      // shared memory rarely holds the lines: an L2 round trip in front of every step's first FMA otherwise)
+      ulonglong2 nr = br0, nz = bz0, ni = bi0;
+#endif
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         const int ch = s >> 1, v = s & 1;
+#if TC3_LD1 == 2
+        const ulonglong2 br = nr, bz = nz, bi = ni;
+        if (s + 1 < 8) {
+          const int o1 = ((s + 1) >> 1) * 8 + 4 * ((s + 1) & 1);
+          nr = __ldg(reinterpret_cast<const ulonglong2*>(pp + o1));
+          nz = __ldg(reinterpret_cast<const ulonglong2*>(pp + H + o1));
+          ni = __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + o1));
+        }
+#else
         const ulonglong2 br = s == 0 ? br0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + ch * 8 + 4 * v));
         const ulonglong2 bz = s == 0 ? bz0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + H + ch * 8 + 4 * v));
         const ulonglong2 bi = s == 0 ? bi0 : __ldg(reinterpret_cast<const ulonglong2*>(pp + 2 * H + ch * 8 + 4 * v));
+#endif
         if (v == 0) {
           off = sw128(r, 4 * half + ch);
           const uint4 vh = *reinterpret_cast<const uint4*>(h_hi + off);
