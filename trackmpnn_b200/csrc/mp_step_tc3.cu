@@ -17,6 +17,9 @@
 // mbarriers per stage: full (8 producer warps), done (tcgen05.commit), gfree (8 team warps: gates done ->
 // accumulators drained and h images read), xfree (8 team warps: stores done -> x images / transpose buffer free).
 // Tiles are located through a table {slab's first global row, tile's first slab row, rows left} (k_tile_table).
+#include <cuda.h>
+#include <cstring>
+
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -74,6 +77,11 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_RCP5
 #define TC3_RCP5 0
 #endif
+// TC3_TMA: the far-endpoint images are fetched by the TMA engine (cp.async.bulk.tensor tile::gather4: four image rows per
+// instruction, written by the async proxy in the 128B-swizzled layout) instead of 2 048 16-byte cp.async per tile
+#ifndef TC3_TMA
+#define TC3_TMA 0
+#endif
 // TC3_LD1: single-set accumulator drain (see the gate loop): the next step's TMEM loads issued under the current step's MUFU
 // chains, P' / previous-state loads in front of tcgen05.wait::ld -- no difference (2.76 vs 2.76 ms,
 // profiles/r02_ab_tc3_ld1.txt): neither the TMEM-load nor the L1 latency at the top of a step is what bounds the gate phase
@@ -109,7 +117,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
               const int4* __restrict__ tab, const unsigned char* __restrict__ image, float* __restrict__ logit,
               float* __restrict__ score, int first_group, int last_group, int32_t* __restrict__ status,
               const int32_t* __restrict__ phys, const float* __restrict__ det_img, const float* __restrict__ det_p,
-              const int32_t* __restrict__ det_of_row, uint32_t xflags) {
+              const int32_t* __restrict__ det_of_row, uint32_t xflags, const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ unsigned char smem_dyn[];
   const int total = *n_tiles;
   if ((int)blockIdx.x >= total) return;  // uniform: whole CTA leaves before touching TMEM / barriers
@@ -159,7 +167,11 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       mbar_init(bar_hfull + 8 * b, PROD3);  // one arrive per producer warp: own rows written
       mbar_init(bar_hfree + 8 * b, 8);      // one arrive per warp of the tile's team: previous state + transpose buffer read back
     }
+#if TC3_TMA
+    mbar_init(bar_xfull, 4 * PROD3);        // four issuing lanes per producer warp, each expecting the 1 KB of its two gathers
+#else
     mbar_init(bar_xfull, 32 * PROD3);       // one arrive per producer THREAD: its far-endpoint copies landed
+#endif
     mbar_init(bar_xfree, 1);                // tcgen05.commit behind the far-endpoint MMAs: x images reusable
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_done + 8 * s, 1);       // tcgen05.commit behind the own-row MMAs: accumulators complete
@@ -269,12 +281,41 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     const uint32_t x_dst0 = sm_u + OFF_A + (uint32_t)(l >> 3) * A_PART + sw128(g, l & 7);  // + 2048 p: row g + 16 p
     const uint32_t h_off0 = sw128(g, l >> 1) + ((l & 1) << 3);
     // rows past the end of the slab repeat its last row; everything they produce is masked by the epilogue
+#if TC3_TMA
+    // lane k (mod 16) of producer warp wq keeps the GLOBAL image row of the far endpoint of tile row 16 wq + k
+    const int wq = warp - EPI3;
+    const int colh = 2 * col;   // first fp16 column of this group's hi half in an image row (the lo half follows 64 further)
+    auto ld_idx = [&](const int4 T) {
+      const int rr = T.y + min(16 * wq + (lane & 15), T.z - 1);
+      return T.x + (detm ? rr : max(__ldg(dst + T.x + rr), 0));   // -1 (a detection row inside the tile): any valid row will do
+    };
+#else
     auto ld_idx = [&](const int4 T) {
       const int rr = T.y + min(idx_row, T.z - 1);
       return detm ? rr : __ldg(dst + T.x + rr);
     };
+#endif
     auto ld_phys = [&](const int4 T) { return dfr ? __ldg(phys + T.x + T.y + min(idx_row, T.z - 1)) : 0; };
+#if TC3_TMA
+    auto issue_x = [&](uint32_t, int iv) {
+      const int q = 4 * (lane & 3);
+      const int r0 = __shfl_sync(FULL, iv, q), r1 = __shfl_sync(FULL, iv, q + 1), r2 = __shfl_sync(FULL, iv, q + 2),
+                r3 = __shfl_sync(FULL, iv, q + 3);
+      if (lane < 4) {   // rows 16 wq + 4 lane .. + 3: rows are 128 B apart in the swizzled image (8-row groups of 1024 B)
+        const uint32_t d = x_u + (uint32_t)(16 * wq + 4 * lane) * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_xfull), "r"(1024u) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+            ::"r"(d), "l"(&tmx), "r"(bar_xfull), "r"(colh), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+            ::"r"(d + A_PART), "l"(&tmx), "r"(bar_xfull), "r"(colh + 64), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+      }
+    };
+    auto issue_x_cp = [&](uint32_t b, int iv) {
+#else
     auto issue_x = [&](uint32_t b, int iv) {
+#endif
       const uint32_t s0 = x_dst0;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
@@ -345,7 +386,12 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       T0 = T1; T1 = T2; T2 = T3; pw1 = pw2; i1 = i2;
       if (++hb == 3) { hb = 0; hphase ^= 1u; }
     }
+#if TC3_TMA
+    mbar_wait(bar_xfull, (uint32_t)it & 1u, status);  // the gathers issued for the tile past the end have landed
+    (void)issue_x_cp;
+#else
     asm volatile("cp.async.wait_all;" ::: "memory");  // copies issued for tiles past the end
+#endif
   } else {
     // ================= epilogue: two teams of 8 warps, team t takes tiles it = t, t + 2, ... (stage t) =================
     const int team = warp >> 3, w8 = warp & 7;
@@ -711,6 +757,34 @@ extern "C" size_t tmpnn_tc_tile_table_bytes(int num_seqs, int cap_rows) {
   return (size_t)num_seqs * (size_t)tmpnn_div_up(cap_rows, TCM) * sizeof(int4) + sizeof(int4);
 }
 
+// Tensor map of the endpoint images for the TMA gathers: det_img as a 2-D fp16 tensor [S cap_rows rows] x [2 ldh columns]
+// (a row = per feature group 64 hi halves then 64 lo halves), box = 64 columns x 1 row (tile::gather4 takes four rows per
+// instruction), 128-byte swizzle = the UMMA layout of the x images.  Host-side encode (driver entry point fetched once).
+static int make_image_map(const float* det_img, long long rows, int ldh, CUtensorMap* tm) {
+#if TC3_TMA
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn enc = nullptr;
+  if (!enc) {
+    cudaDriverEntryPointQueryResult qr;
+    void* fn = nullptr;
+    TMPNN_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return tmpnn_set_error(TMPNN_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    enc = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)ldh * 2, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ldh * 4};
+  const cuuint32_t box[2] = {64, 1}, es[2] = {1, 1};
+  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)det_img, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return tmpnn_set_error(TMPNN_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+#else
+  (void)det_img; (void)rows; (void)ldh;
+  memset(tm, 0, sizeof(*tm));
+#endif
+  return TMPNN_OK;
+}
+
 // ---- detection rows on the same kernel (tmpnn_mp_det_fwd_tc) ---------------------------------------------------------------
 // Tiles over the detection segments of every slab (contiguous rows: the kernel writes its output at consecutive logical rows).
 // tab[0].x = number of tiles, tiles from tab[1] on.
@@ -790,10 +864,13 @@ extern "C" int tmpnn_mp_det_fwd_tc(const tmpnn_graph* g, const tmpnn_index* ix, 
                                                             ldh, group * H, det_p, g->status);
   TMPNN_LAUNCH_CHECK();
   TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_const, (const unsigned char*)node_image + OFF_BIAS + 3 * H * 4, 528, 0, cudaMemcpyDeviceToDevice, st));
+  CUtensorMap tmx;
+  rc = make_image_map(det_img, (long long)g->num_seqs * g->cap_rows, ldh, &tmx);
+  if (rc) return rc;
   // x = the aggregate enters with its own sign (no negation), bit 0: detection mode
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, reinterpret_cast<const int32_t*>(tab), tab + 1, (const unsigned char*)node_image,
-      g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys, det_img, det_p, ix->det_of_row, 1u);
+      g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys, det_img, det_p, ix->det_of_row, 1u, tmx);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
@@ -807,11 +884,13 @@ int tmpnn_edge_tc3_launch(const tmpnn_graph* g, const tmpnn_index* ix, const flo
     TMPNN_LAUNCH_CHECK();
   }
   TMPNN_CUDA_TRY(cudaMemcpyToSymbolAsync(c_tc3_const, (const unsigned char*)edge_image + OFF_BIAS + 3 * H * 4, 528, 0, cudaMemcpyDeviceToDevice, st));
+  CUtensorMap tmx;
+  { const int rc = make_image_map(det_img, (long long)g->num_seqs * g->cap_rows, ldh, &tmx); if (rc) return rc; }
   // 'diff': x = h[src] - h[dst]  ->  the far endpoint enters negated (instruction descriptor bit 13: negate A)
   k_mp_edge_tc3<<<TMPNN_SM_COUNT, TC3_THREADS, SMEM_BYTES, st>>>(
       h_in, h_out, ldh, group * H, g->src, g->dst, ix->tile128_ptr + g->num_seqs, (const int4*)tile_table,
       (const unsigned char*)edge_image, g->logit, g->score, group == 0, group == num_groups - 1, g->status, g->phys, det_img,
-      det_p, ix->det_of_row, concat ? 0u : (1u << 13));
+      det_p, ix->det_of_row, concat ? 0u : (1u << 13), tmx);
   TMPNN_LAUNCH_CHECK();
   return TMPNN_OK;
 }
