@@ -80,7 +80,7 @@ __constant__ float c_tc3_const[132];
 // TC3_TMA: the far-endpoint images are fetched by the TMA engine (cp.async.bulk.tensor tile::gather4: four image rows per
 // instruction, written by the async proxy in the 128B-swizzled layout) instead of 2 048 16-byte cp.async per tile
 #ifndef TC3_TMA
-#define TC3_TMA 0
+#define TC3_TMA 1
 #endif
 // TC3_LD1: single-set accumulator drain (see the gate loop): the next step's TMEM loads issued under the current step's MUFU
 // chains, P' / previous-state loads in front of tcgen05.wait::ld -- no difference (2.76 vs 2.76 ms,
