@@ -549,7 +549,7 @@ def rooflines(a, eng, r, ms):
     hbm_peak, peak_src = measured_peaks()
     achieved = BYTES_PER_EDGE_UPDATE * k_edges / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     tk = {'auto': 'pre'}.get(eng.tensor_kernel, eng.tensor_kernel)
-    kname = ({'pre': 'k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far endpoint copied by cp.async, '
+    kname = ({'pre': 'k_mp_edge_tc3 (fused edge step: endpoints prepared once per detection, far-endpoint images fetched by TMA tile::gather4, '
                      '24 tcgen05.mma kind::f16 per tile (3-term fp16 split, N = 192), TMEM accumulators, elect.sync MMA issuer warp, two '
                      'epilogue teams, own-row images triple-buffered and reused in place as the transpose buffer)',
               'gather': 'k_mp_edge_tc (fused gather-diff + GRU + head; tcgen05.mma kind::f16, 3-term fp16 split, TMEM accumulators)'}[tk]
