@@ -82,6 +82,11 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_TMA
 #define TC3_TMA 1
 #endif
+// TC3_HFIRST: own-row MMAs in front of the far-endpoint MMAs (see the issuer): parity green, 6-7 % slower with the TMA gathers too
+// (2.78 -> 2.97 ms, profiles/r02_ab_tc3_hfirst.txt) -- the x images are released 12 MMAs later, the next gathers start later
+#ifndef TC3_HFIRST
+#define TC3_HFIRST 0
+#endif
 // TC3_LD1: single-set accumulator drain (see the gate loop): the next step's TMEM loads issued under the current step's MUFU
 // chains, P' / previous-state loads in front of tcgen05.wait::ld -- no difference (2.76 vs 2.76 ms,
 // profiles/r02_ab_tc3_ld1.txt): neither the TMEM-load nor the L1 latency at the top of a step is what bounds the gate phase
@@ -203,7 +208,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     tmem_zero16(tz + 128);
   }
 #else
-  if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 32 * ((warp & 7) >> 2)));
+  if (warp < EPI3) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 3) * 256 + 32 * ((warp & 7) >> 2) + (TC3_HFIRST ? 192 : 0)));
 #endif
   tc_fence_before();
   __syncthreads();
@@ -241,6 +246,43 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         umma_commit(bar_xfree);  // x images reusable once these retire: the copies of tile it + 1 start here
         issue_group_mma_h(sm_u, d0 + 128, x_u + 2 * A_PART + (uint32_t)hb * H_BUF, 1);
         umma_commit(bar_doneB + 8 * stage);
+        TC3_TRACE(it, 7, true);
+#elif TC3_HFIRST
+        // own-row part first (its images are written up to two tiles ahead: no wait), far-endpoint part behind it: the wait for
+        // the gathered images hides under the first 12 MMAs.  The own-row part initialises h_n | r | z, the far-endpoint part
+        // accumulates into r | z | i_n, whose i_n columns the epilogue re-zeroed.
+        mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);
+        TC3_TRACE(it, 5, true);
+        mbar_wait(bar_hfull + 8 * hb, hphase, status);
+        tc_fence_after();
+        {
+          const uint32_t h_u = x_u + 2 * A_PART + (uint32_t)hb * H_BUF;
+          const uint32_t ah[3] = {h_u, h_u + A_PART, h_u};
+          const uint32_t bh[3] = {sm_u + OFF_BH_HI, sm_u + OFF_BH_HI, sm_u + OFF_BH_LO};
+          uint32_t acc = 0;
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              umma_f16(d0, umma_desc(ah[t] + 32 * j), umma_desc(bh[t] + 32 * j), umma_idesc(192), acc);
+              acc = 1;
+            }
+        }
+        TC3_TRACE(it, 10, true);
+        mbar_wait(bar_xfull, (uint32_t)it & 1u, status);
+        TC3_TRACE(it, 6, true);
+        tc_fence_after();
+        {
+          const uint32_t ax[3] = {x_u, x_u + A_PART, x_u};
+          const uint32_t bx[3] = {sm_u + OFF_BX_HI, sm_u + OFF_BX_HI, sm_u + OFF_BX_LO};
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_f16(d0 + 64, umma_desc(ax[t] + 32 * j), umma_desc(bx[t] + 32 * j), umma_idesc(192) | xflags, 1);
+        }
+        umma_commit(bar_xfree);
+        umma_commit(bar_done + 8 * stage);
         TC3_TRACE(it, 7, true);
 #else
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
@@ -635,7 +677,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfreeB + 8 * stage);  // second hidden group drained
 #else
-      tmem_zero32(t0);
+      tmem_zero32(t0 + (TC3_HFIRST ? 192u : 0u));   // the columns the accumulate-only half of the next tile's MMAs adds into
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfree + 8 * stage);  // accumulator stage drained: the next far-endpoint MMAs may start
