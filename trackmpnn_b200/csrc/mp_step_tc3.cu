@@ -82,6 +82,9 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_TMA
 #define TC3_TMA 1
 #endif
+#ifndef TC3_XFENCE
+#define TC3_XFENCE 0
+#endif
 // TC3_HFIRST: own-row MMAs in front of the far-endpoint MMAs (see the issuer): parity green, 6-7 % slower with the TMA gathers too
 // (2.78 -> 2.97 ms, profiles/r02_ab_tc3_hfirst.txt) -- the x images are released 12 MMAs later, the next gathers start later
 #ifndef TC3_HFIRST
@@ -289,7 +292,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         TC3_TRACE(it, 5, true);
         mbar_wait(bar_xfull, (uint32_t)it & 1u, status);       // far-endpoint images landed (issued a tile ago)
         TC3_TRACE(it, 6, true);
-        fence_proxy_async();  // the copies were generic-proxy writes of other threads, observed through the barrier
+#if !TC3_TMA || TC3_XFENCE
+        fence_proxy_async();  // cp.async copies are generic-proxy writes of other threads, observed through the barrier (the
+                              // TMA gathers write through the async proxy themselves: no proxy fence in front of the MMAs)
+#endif
         tc_fence_after();
         issue_tile_mma_x_first(sm_u, d0, x_u, xflags);
         umma_commit(bar_xfree);  // x images reusable once these retire: the copies of tile it + 1 start here
