@@ -85,6 +85,15 @@ __constant__ float c_tc3_const[132];
 #ifndef TC3_XFENCE
 #define TC3_XFENCE 0
 #endif
+// TC3_XSPLIT (with TC3_TMA): the lo and the hi image of the far endpoints are handed over separately -- the x_lo . B_hi term
+// goes first, so the lo image is released after 4 MMAs, its gathers for the next tile start early, and the next tile's first
+// four MMAs run while its hi gathers are still landing
+#ifndef TC3_XSPLIT
+#define TC3_XSPLIT 1
+#endif
+#if TC3_XSPLIT && (!TC3_TMA || TC3_SPLIT || TC3_HFIRST)
+#error "TC3_XSPLIT needs TC3_TMA and excludes TC3_SPLIT / TC3_HFIRST"
+#endif
 // TC3_HFIRST: own-row MMAs in front of the far-endpoint MMAs (see the issuer): parity green, 6-7 % slower with the TMA gathers too
 // (2.78 -> 2.97 ms, profiles/r02_ab_tc3_hfirst.txt) -- the x images are released 12 MMAs later, the next gathers start later
 #ifndef TC3_HFIRST
@@ -142,6 +151,9 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
   const uint32_t bar_hfull = sm_u + OFF_BAR, bar_hfree = bar_hfull + 24, bar_xfull = bar_hfull + 48, bar_xfree = bar_hfull + 56,
                  bar_done = bar_hfull + 64, bar_gfree = bar_hfull + 80, bar_doneB = bar_hfull + 96, bar_gfreeB = bar_hfull + 112;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 128);
+#if TC3_XSPLIT
+  const uint32_t bar_xfull_hi = bar_doneB, bar_xfree_hi = bar_doneB + 8;   // the slots of the (excluded) TC3_SPLIT experiment
+#endif
 
   // resident weight image (generic-proxy stores, made visible to the async proxy below)
   {
@@ -175,7 +187,11 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       mbar_init(bar_hfull + 8 * b, PROD3);  // one arrive per producer warp: own rows written
       mbar_init(bar_hfree + 8 * b, 8);      // one arrive per warp of the tile's team: previous state + transpose buffer read back
     }
-#if TC3_TMA
+#if TC3_XSPLIT
+    mbar_init(bar_xfull, 4 * PROD3);        // lo images: four issuing lanes per producer warp, 512 B each
+    mbar_init(bar_xfull_hi, 4 * PROD3);     // hi images
+    mbar_init(bar_xfree_hi, 1);
+#elif TC3_TMA
     mbar_init(bar_xfull, 4 * PROD3);        // four issuing lanes per producer warp, each expecting the 1 KB of its two gathers
 #else
     mbar_init(bar_xfull, 32 * PROD3);       // one arrive per producer THREAD: its far-endpoint copies landed
@@ -184,8 +200,10 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_done + 8 * s, 1);       // tcgen05.commit behind the own-row MMAs: accumulators complete
       mbar_init(bar_gfree + 8 * s, 8);      // one arrive per warp of the stage's team: accumulators drained
+#if TC3_SPLIT
       mbar_init(bar_doneB + 8 * s, 1);      // TC3_SPLIT: the same pair for the second hidden group of the stage
       mbar_init(bar_gfreeB + 8 * s, 8);
+#endif
     }
 #if TC3_HEAD_EARLY
     for (int q = 0; q < 16; ++q) mbar_init(sm_u + OFF_HEADW + 8 * q, 1);  // head partials published / consumed, per (team, quadrant)
@@ -290,6 +308,32 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 #else
         mbar_wait(bar_gfree + 8 * stage, phase ^ 1u, status);  // accumulator stage drained by the tile two back
         TC3_TRACE(it, 5, true);
+#if TC3_XSPLIT
+        {
+          // x_lo . B_hi first (initialises r | z | i_n), lo image released; then x_hi . B_hi and x_hi . B_lo, hi image released
+          mbar_wait(bar_xfull, (uint32_t)it & 1u, status);
+          TC3_TRACE(it, 6, true);
+          tc_fence_after();
+          uint32_t acc = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            umma_f16(d0 + 64, umma_desc(x_u + A_PART + 32 * j), umma_desc(sm_u + OFF_BX_HI + 32 * j), umma_idesc(192) | xflags, acc);
+            acc = 1;
+          }
+          umma_commit(bar_xfree);
+          mbar_wait(bar_xfull_hi, (uint32_t)it & 1u, status);
+          tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_f16(d0 + 64, umma_desc(x_u + 32 * j), umma_desc(sm_u + (t ? OFF_BX_LO : OFF_BX_HI) + 32 * j), umma_idesc(192) | xflags, 1);
+          umma_commit(bar_xfree_hi);
+        }
+        if (false) {
+#else
+        {
+#endif
         mbar_wait(bar_xfull, (uint32_t)it & 1u, status);       // far-endpoint images landed (issued a tile ago)
         TC3_TRACE(it, 6, true);
 #if !TC3_TMA || TC3_XFENCE
@@ -299,6 +343,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
         tc_fence_after();
         issue_tile_mma_x_first(sm_u, d0, x_u, xflags);
         umma_commit(bar_xfree);  // x images reusable once these retire: the copies of tile it + 1 start here
+        }
         // own rows: written up to two tiles ahead into the third buffer, so this wait is normally over already and
         // a team's hand-over from one tile to its next is the 36 MMAs only
         mbar_wait(bar_hfull + 8 * hb, hphase, status);
@@ -345,10 +390,29 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
 #endif
     auto ld_phys = [&](const int4 T) { return dfr ? __ldg(phys + T.x + T.y + min(idx_row, T.z - 1)) : 0; };
 #if TC3_TMA
-    auto issue_x = [&](uint32_t, int iv) {
+    auto issue_x = [&](uint32_t, int iv, bool xwait = false, uint32_t xpar = 0) {
+      (void)xwait; (void)xpar;
       const int q = 4 * (lane & 3);
       const int r0 = __shfl_sync(FULL, iv, q), r1 = __shfl_sync(FULL, iv, q + 1), r2 = __shfl_sync(FULL, iv, q + 2),
                 r3 = __shfl_sync(FULL, iv, q + 3);
+#if TC3_XSPLIT
+      // lo image first (released first by the issuer), then the hi image: each behind its own xfree barrier
+      const uint32_t d = x_u + (uint32_t)(16 * wq + 4 * lane) * 128u;
+      if (xwait) mbar_wait(bar_xfree, xpar, status);
+      if (lane < 4) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_xfull), "r"(512u) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+            ::"r"(d + A_PART), "l"(&tmx), "r"(bar_xfull), "r"(colh + 64), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+      }
+      if (xwait) mbar_wait(bar_xfree_hi, xpar, status);
+      if (lane < 4) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_xfull_hi), "r"(512u) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+            ::"r"(d), "l"(&tmx), "r"(bar_xfull_hi), "r"(colh), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+      }
+#else
       if (lane < 4) {   // rows 16 wq + 4 lane .. + 3: rows are 128 B apart in the swizzled image (8-row groups of 1024 B)
         const uint32_t d = x_u + (uint32_t)(16 * wq + 4 * lane) * 128u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_xfull), "r"(1024u) : "memory");
@@ -359,6 +423,7 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
             "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
             ::"r"(d + A_PART), "l"(&tmx), "r"(bar_xfull), "r"(colh + 64), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
       }
+#endif
     };
     auto issue_x_cp = [&](uint32_t b, int iv) {
 #else
@@ -424,9 +489,14 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
       }
       // far-endpoint images of the next tile: the single pair of x images is free as soon as this tile's MMAs on it retire
       TC3_TRACE(it, 0, tr);
+#if TC3_XSPLIT
+      issue_x((uint32_t)T1.x, i1, true, (uint32_t)it & 1u);   // waits for the lo / hi image in turn
+      TC3_TRACE(it, 1, tr);
+#else
       mbar_wait(bar_xfree, (uint32_t)it & 1u, status);
       TC3_TRACE(it, 1, tr);
       issue_x((uint32_t)T1.x, i1);
+#endif
       float amax = 0.f;
 #pragma unroll
       for (int p = 0; p < 8; ++p) split4(own[p], hh[p], hl[p], amax);
@@ -436,6 +506,9 @@ k_mp_edge_tc3(const float* __restrict__ h_in, float* __restrict__ h_out, int ldh
     }
 #if TC3_TMA
     mbar_wait(bar_xfull, (uint32_t)it & 1u, status);  // the gathers issued for the tile past the end have landed
+#if TC3_XSPLIT
+    mbar_wait(bar_xfull_hi, (uint32_t)it & 1u, status);
+#endif
     (void)issue_x_cp;
 #else
     asm volatile("cp.async.wait_all;" ::: "memory");  // copies issued for tiles past the end
